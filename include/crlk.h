@@ -1,0 +1,216 @@
+/*
+ * crlk.h -- C ABI of libcrlk.so: the B200 (sm_100a) implementation of
+ * crl_kino's kinodynamic-RRT extend path.
+ *
+ * The reference is pure Python and has no FFI; its "plugin API" is duck-typed
+ * Python.  Each entry point below names the reference
+ * interface it replaces (file:line in the reference checkout); the host-side
+ * mirror of those interfaces lives in crl_kino_b200/ and binds this header
+ * with ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (CRLK_E_*);
+ *     crlk_last_error() returns a thread-local message for the last failure.
+ *   - pointers documented "dev" are device pointers owned by the caller
+ *     (e.g. PyTorch tensors); the library never frees or retains them past the
+ *     call.  Pointers documented "host" are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Launches are asynchronous; no entry point synchronises unless stated.
+ *   - state = [x, y, theta, v, omega] float64[5]; obstacle = [left, bottom,
+ *     right, top] float32[4] (rigid.py:146 stores float32).
+ *   - handles are opaque, bound to the CUDA device current at creation and
+ *     are safe to use from one thread at a time.
+ */
+#ifndef CRLK_H
+#define CRLK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRLK_OK 0
+#define CRLK_E_INVALID (-1)   /* bad argument */
+#define CRLK_E_CUDA (-2)      /* CUDA runtime error (message has the detail) */
+#define CRLK_E_NODEVICE (-3)  /* no CUDA device: there is NO CPU fallback */
+#define CRLK_E_CAPACITY (-4)  /* a caller-provided capacity is too small */
+
+#define CRLK_ABI_VERSION 1
+
+/* status codes written by the extend kernels (rrt.py:121-128) */
+#define CRLK_EXT_TIMEOUT 0    /* n_max_extend steps executed */
+#define CRLK_EXT_COLLISION 1  /* valid_state_check failed; open segment dropped */
+#define CRLK_EXT_REACHED 2    /* ||xy - target|| <= reach_radius */
+
+typedef struct CrlkEnv CrlkEnv;          /* DifferentialDriveEnv + obstacle set */
+typedef struct CrlkPolicy CrlkPolicy;    /* DDPG actor MLP */
+typedef struct CrlkEstimator CrlkEstimator; /* estimator + classifier CNN pair */
+
+/* DifferentialDriveEnv.__init__ (env/differential_env.py:28-53). */
+typedef struct {
+    double max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt;
+    double env_bounds[4];   /* xmin xmax ymin ymax */
+    float robot_rect[4];    /* RectRobot rect, float32 values (differential_env.py:41) */
+} CrlkEnvParams;
+
+/* DWA.__init__ / set_dwa (policy/dwa.py:13-33).  use_clearance = 0 is the
+ * shipped behaviour (dwa.py:64-69 is commented out: the obstacle term is the
+ * constant 1/100); 1 evaluates those lines. */
+typedef struct {
+    double v_res, w_res, dt, predict_time;
+    double to_goal_cost_gain, ob_gain, speed_cost_gain;
+    int32_t skip;
+    int32_t use_clearance;
+} CrlkDwaParams;
+
+/* RRT.steer constants (planner/rrt.py:99-112): n_max_extend = round(10/0.2),
+ * n_tree = round(5/0.2), step_dt = 0.2, reach_radius = 1.0. */
+typedef struct {
+    int32_t n_max_extend;
+    int32_t n_tree;
+    double step_dt;
+    double reach_radius;
+} CrlkExtendParams;
+
+const char *crlk_last_error(void);
+int crlk_abi_version(void);
+/* number of CUDA devices visible (0 => every compute entry point fails). */
+int crlk_device_count(void);
+
+/* ---- environment: DifferentialDriveEnv (env/differential_env.py:27-169) ---- */
+
+/* set_obs (differential_env.py:120-123) + ctor.  rects_host: M x 4 float32. */
+int crlk_env_create(const CrlkEnvParams *params, const float *rects_host, int32_t M, CrlkEnv **out);
+int crlk_env_destroy(CrlkEnv *env);
+int crlk_env_set_obs(CrlkEnv *env, const float *rects_host, int32_t M);
+int crlk_env_num_obs(const CrlkEnv *env);
+
+/* valid_state_check (differential_env.py:146-151) and get_clearance (:126-132)
+ * for B states (dev, B x 5 f64, row stride 5).
+ *   valid          dev u8[B]  (nullable) 1 = collision free
+ *   clearance      dev f64[B] (nullable) min(100, min_obs dis2obs), -1 if colliding
+ *   near_boundary  dev u8[B]  (nullable) 1 if some obstacle's distance is within
+ *                  1e-6 of the 0.05 collision threshold (rigid.py:311): parity
+ *                  with the reference is not claimed for those states. */
+int crlk_valid_state(const CrlkEnv *env, const double *states, int32_t B, uint8_t *valid,
+                     double *clearance, uint8_t *near_boundary, void *stream);
+
+/* valid_point_check (differential_env.py:135-144): points dev K x 2 f64. */
+int crlk_valid_points(const CrlkEnv *env, const double *points, int32_t K, uint8_t *valid,
+                      void *stream);
+
+/* motion_velocity (differential_env.py:55-73): states_in/out dev B x 5, cmds dev B x 2. */
+int crlk_motion_velocity(const CrlkEnv *env, const double *states_in, const double *cmds,
+                         double duration, int32_t B, double *states_out, void *stream);
+/* motion (differential_env.py:76-83): acceleration command. */
+int crlk_motion(const CrlkEnv *env, const double *states_in, const double *acc, double duration,
+                int32_t B, double *states_out, void *stream);
+/* dynamic_window (differential_env.py:107-114): out dev B x 4 [v_lo v_hi w_lo w_hi]. */
+int crlk_dynamic_window(const CrlkEnv *env, const double *states, double dt, int32_t B,
+                        double *out, void *stream);
+
+/* DifferentialDriveGym._obs (env/differential_gym.py:180-190): goal in body
+ * frame, v, omega, 27 x 27 local occupancy map (:62-91).
+ *   goals   dev B x goal_stride f64 (only [0], [1] are read)
+ *   obs64   dev f64[B x 733] (nullable)   the reference's float64 observation
+ *   obs32   dev f32[B x ld32] (nullable)  same values cast to float32 (net.py:142),
+ *           ld32 >= 733 (736 for the tensor-core MLP); padding is zero-filled
+ *   near_boundary dev u8[B] (nullable): some sample point within 1e-9 of an
+ *           obstacle face. */
+int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals,
+                   int32_t goal_stride, int32_t B, double *obs64, float *obs32, int32_t ld32,
+                   uint8_t *near_boundary, void *stream);
+
+/* ---- steering: DWA.control (policy/dwa.py:45-86) ---- */
+
+/* One dynamic-window control decision per (state, goal) pair.
+ *   opt_v     dev f64[B x 2]
+ *   opt_idx   dev i32[B]   v-major index of the first minimum (np.argmin)
+ *   opt_cost  dev f64[B]   (nullable)
+ *   opt_traj  dev f64[B x traj_rows x 5] (nullable); traj_rows from crlk_dwa_traj_rows
+ *   n_rollouts dev i32[B]  (nullable) realised grid size nv * nw
+ *   near_tie  dev u8[B]    (nullable) second-best cost within 1e-9 relative. */
+int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, const double *states,
+                     const double *goals, int32_t goal_stride, int32_t B, double *opt_v,
+                     int32_t *opt_idx, double *opt_cost, double *opt_traj, int32_t *n_rollouts,
+                     uint8_t *near_tie, void *stream);
+/* rows of DWA.calc_trajectory (dwa.py:35-43) for these parameters (7 for dt 0.2). */
+int crlk_dwa_traj_rows(const CrlkEnv *env, const CrlkDwaParams *dwa);
+/* upper bound of the rollout grid size for these parameters. */
+int crlk_dwa_max_rollouts(const CrlkEnv *env, const CrlkDwaParams *dwa);
+
+/* ---- nearest node: RRT.choose_parent (planner/rrt.py:156-161) ---- */
+
+/* Q independent trees in SoA form.  Tree q occupies elements [q*stride,
+ * q*stride + n_nodes[q]) of each array.
+ *   x64, y64   dev f64   exact coordinates (rescoring)
+ *   x32, y32   dev f32   the same coordinates rounded to float32 (the scanned
+ *                        copy: 8 bytes per node); nullable => scan f64 directly
+ *   targets    dev f64[Q x target_stride]
+ *   idx        dev i32[Q]; dist dev f64[Q]; near_tie dev u8[Q] (nullable)
+ *   scratch    dev bytes, crlk_nearest_scratch_bytes(Q, max_nodes) of them. */
+int crlk_nearest(const double *x64, const double *y64, const float *x32, const float *y32,
+                 int64_t stride, const int32_t *n_nodes, int32_t max_nodes, const double *targets,
+                 int32_t target_stride, int32_t Q, int32_t *idx, double *dist, uint8_t *near_tie,
+                 void *scratch, void *stream);
+int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes);
+
+/* ---- extension: RRT.steer (planner/rrt.py:99-135), DWA steering ---- */
+
+/* One extension per (from, target) pair, all control steps on the device.
+ *   from_states, targets  dev f64[Q x 5]
+ *   path       dev f64[Q x n_max_extend x 5]  executed states, step 1..n_steps
+ *   n_steps    dev i32[Q]
+ *   status     dev i32[Q]  CRLK_EXT_*
+ *   node_step  dev i32[Q x (n_max_extend/n_tree + 1)]  1-based step of each emitted node
+ *   n_nodes    dev i32[Q]
+ *   ctrl_idx   dev i32[Q x n_max_extend] (nullable) chosen rollout index per step
+ *   flags      dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin
+ *   active     dev u8[Q] (nullable) 0 => skip this pair (n_steps = 0, n_nodes = 0). */
+int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
+                    const double *from_states, const double *targets, int32_t Q, double *path,
+                    int32_t *n_steps, int32_t *status, int32_t *node_step, int32_t *n_nodes,
+                    int32_t *ctrl_idx, uint8_t *flags, const uint8_t *active, void *stream);
+
+/* ---- learned steering: policy_forward (policy/rl_policy.py:83-109) ---- */
+
+/* Actor MLP (policy/net.py:114-154).  weights_host[i]: [dims[i+1] x dims[i]]
+ * float32 row-major (torch nn.Linear layout), biases_host[i]: [dims[i+1]].
+ * low/high: action range, float32[dims[n_layers]] (gym Box float32). */
+int crlk_policy_create(int32_t n_layers, const int32_t *dims, const float *const *weights_host,
+                       const float *const *biases_host, const float *low, const float *high,
+                       CrlkPolicy **out);
+int crlk_policy_destroy(CrlkPolicy *p);
+/* obs dev f32[B x ld_obs]; noise dev f32[B x 2] (nullable: no exploration
+ * noise); act dev f32[B x 2] = clamp(tanh(mlp) + noise*eps) * scale + bias).
+ * workspace dev bytes from crlk_policy_workspace_bytes(p, B). */
+int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_t ld_obs, const float *noise,
+                        float eps, int32_t B, float *act, void *workspace, void *stream);
+int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
+
+/* RRT_RL.steer (planner/rrt_rl.py:22-63): like crlk_extend_dwa with the policy
+ * as controller.  noise dev f32[Q x n_max_extend x 2] (nullable), consumed one
+ * row per executed step.  workspace: crlk_extend_rl_workspace_bytes. */
+int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
+                   const double *from_states, const double *targets, int32_t Q, const float *noise,
+                   float eps, double *path, int32_t *n_steps, int32_t *status, int32_t *node_step,
+                   int32_t *n_nodes, float *actions, uint8_t *flags, const uint8_t *active,
+                   void *workspace, void *stream);
+int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q);
+
+/* ---- learned parent selection (estimator/network.py, rrt_rl_estimator.py:57-74) ---- */
+
+/* params_host: the 10 tensors of one CNN state dict in the order
+ * conv1.w conv1.b conv2.w conv2.b conv3.w conv3.b conv4.w conv4.b linear.w linear.b. */
+int crlk_estimator_create(const float *const *est_params_host, const float *const *cls_params_host,
+                          CrlkEstimator **out);
+int crlk_estimator_destroy(CrlkEstimator *e);
+/* obs dev f32[B x ld_obs] (the 733-vector of crlk_local_obs); est, prob dev f32[B]. */
+int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, int32_t ld_obs, int32_t B,
+                           float *est, float *prob, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRLK_H */
