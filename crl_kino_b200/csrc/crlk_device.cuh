@@ -1,0 +1,217 @@
+// Device-side building blocks of the extend path (double precision, compiled
+// with --fmad=false so that no multiply-add is fused unless written as fma()).
+//
+// Design notes (B200-first, not a translation of the Python reference):
+//   * the velocity chain (v, omega) of a differential-drive rollout does not
+//     depend on the pose, and the heading chain depends only on the omega
+//     command, so a DWA grid of nv x nw rollouts needs only nw sincos chains
+//     and nv velocity chains; positions are then pure multiply/add work;
+//   * robot-vs-obstacle tests are an FP32 conservative screen over the whole
+//     obstacle set followed by an exact FP64 evaluation of the few survivors.
+#pragma once
+#include "crlk_internal.h"
+
+#define CRLK_PI 3.141592653589793
+#define CRLK_TWO_PI 6.283185307179586
+#define CRLK_COLLISION_DIS 0.05     // rigid.py:311
+#define CRLK_NEAR_EPS 1e-6          // states this close to the threshold are reported, not compared
+#define CRLK_CULL_MARGIN 1e-3f      // FP32 screen slack (coordinates are O(50): 1 ulp ~ 4e-6)
+#define CRLK_CLEARANCE_CAP 100.0    // differential_env.py:127
+
+// Python builtin min/max semantics on floats (first argument wins ties).
+__device__ __forceinline__ double pymin(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double pymax(double a, double b) { return (b > a) ? b : a; }
+
+// differential_env.py:20-24 (floor-mod by 2*pi, then wrap into (-pi, pi]).
+__device__ __forceinline__ double normalize_angle(double a)
+{
+    double m = fmod(a, CRLK_TWO_PI);
+    if (m != 0.0) {
+        if (m < 0.0) m += CRLK_TWO_PI;
+    } else {
+        m = 0.0;
+    }
+    if (m > CRLK_PI) m -= CRLK_TWO_PI;
+    return m;
+}
+
+// One base_dt sub-step of one velocity axis under a velocity command:
+// differential_env.py:70 (input_u) + :87-95 (clamp into dynamic_window(state, base_dt)).
+__device__ __forceinline__ double vel_substep(double cur, double cmd, double acc, double lo,
+                                              double hi, double dt)
+{
+    double iu = (cmd - cur) / dt;
+    double u = cur + iu * dt;
+    double wlo = pymax(cur - acc * dt, lo);
+    double whi = pymin(cur + acc * dt, hi);
+    u = pymax(wlo, u);
+    u = pymin(whi, u);
+    return u;
+}
+
+// Same under an acceleration command (differential_env.py:76-95).
+__device__ __forceinline__ double acc_substep(double cur, double a, double acc, double lo,
+                                              double hi, double dt)
+{
+    double u = cur + a * dt;
+    double wlo = pymax(cur - acc * dt, lo);
+    double whi = pymin(cur + acc * dt, hi);
+    u = pymax(wlo, u);
+    u = pymin(whi, u);
+    return u;
+}
+
+// Pose update of one sub-step (differential_env.py:97-103) given the new (u0, u1).
+__device__ __forceinline__ void pose_substep(double *s, double u0, double u1, double dt)
+{
+    double th = normalize_angle(s[2] + u1 * dt);
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    s[2] = th;
+    s[0] = s[0] + u0 * cs * dt;
+    s[1] = s[1] + u0 * sn * dt;
+    s[3] = u0;
+    s[4] = u1;
+}
+
+// motion_velocity (differential_env.py:55-73) with n_sub pre-counted sub-steps.
+__device__ __forceinline__ void motion_velocity_dev(const EnvP &e, double *s, double cv, double cw,
+                                                    int n_sub)
+{
+    for (int k = 0; k < n_sub; k++) {
+        double u0 = vel_substep(s[3], cv, e.max_acc_v, e.min_v, e.max_v, e.base_dt);
+        double u1 = vel_substep(s[4], cw, e.max_acc_w, -e.max_w, e.max_w, e.base_dt);
+        pose_substep(s, u0, u1, e.base_dt);
+    }
+}
+
+// ------------------------------------------------------------------ geometry
+
+struct RobotPose {
+    double x, y, c, s;
+    double wx[4], wy[4];   // robot corners in the world frame: (l,b) (l,t) (r,t) (r,b)
+};
+
+__device__ __forceinline__ void robot_pose_setup(const EnvP &e, double x, double y, double th,
+                                                 RobotPose &g)
+{
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    g.x = x; g.y = y; g.c = cs; g.s = sn;
+    const double bx[4] = {(double)e.rl, (double)e.rl, (double)e.rr, (double)e.rr};
+    const double by[4] = {(double)e.rb, (double)e.rt, (double)e.rt, (double)e.rb};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        g.wx[i] = (cs * bx[i] + (-sn) * by[i]) + x;   // rigid.py:223-227
+        g.wy[i] = (sn * bx[i] + cs * by[i]) + y;
+    }
+}
+
+// Segment s->g against a closed AABB: slab test (rigid.py:45-116) in
+// unnormalised form; t in [0, 1] spans the segment, zero direction components
+// use the reference's 1e300 reciprocal.
+__device__ __forceinline__ bool seg_hits_aabb(double sx, double sy, double gx, double gy, double l,
+                                              double b, double r, double t)
+{
+    double dx = gx - sx, dy = gy - sy;
+    double fx = (dx == 0.0) ? 1e300 : 1.0 / dx;
+    double fy = (dy == 0.0) ? 1e300 : 1.0 / dy;
+    double t1 = (l - sx) * fx, t2 = (r - sx) * fx;
+    double t3 = (b - sy) * fy, t4 = (t - sy) * fy;
+    double tmin = fmax(fmin(t1, t2), fmin(t3, t4));
+    double tmax = fmin(fmax(t1, t2), fmax(t3, t4));
+    return (tmax >= 0.0) && (tmin <= tmax) && (tmin <= 1.0);
+}
+
+// Squared distance from a point to the BOUNDARY of a rectangle (what the min
+// over the four RectObs.dis2point edges is, rigid.py:168-180): outside it is
+// the distance to the solid, inside the smallest margin.
+__device__ __forceinline__ double point_rect_boundary_d2(double px, double py, double l, double b,
+                                                         double r, double t)
+{
+    double ex = fmax(fmax(l - px, px - r), 0.0);
+    double ey = fmax(fmax(b - py, py - t), 0.0);
+    double in = fmin(fmin(px - l, r - px), fmin(py - b, t - py));
+    return (in > 0.0) ? in * in : ex * ex + ey * ey;
+}
+
+// RectRobot.dis2obs (rigid.py:265-313): -1 on collision, else the distance.
+// `definite` / `marginal` classify the decision against the 0.05 threshold.
+__device__ __forceinline__ double dis2obs_exact(const EnvP &e, const RobotPose &g, float4 o,
+                                                bool &definite, bool &marginal)
+{
+    double l = o.x, b = o.y, r = o.z, t = o.w;
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        hit |= seg_hits_aabb(g.wx[i], g.wy[i], g.wx[j], g.wy[j], l, b, r, t);
+    }
+    if (hit) { definite = true; marginal = false; return -1.0; }
+    double d2 = 1e300;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d2 = fmin(d2, point_rect_boundary_d2(g.wx[i], g.wy[i], l, b, r, t));
+    const double ox[4] = {l, l, r, r}, oy[4] = {b, t, t, b};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double qx = ox[i] - g.x, qy = oy[i] - g.y;       // rigid.py:231-237 as R^T (p - t)
+        double px = g.c * qx + g.s * qy;
+        double py = (-g.s) * qx + g.c * qy;
+        d2 = fmin(d2, point_rect_boundary_d2(px, py, (double)e.rl, (double)e.rb, (double)e.rr,
+                                             (double)e.rt));
+    }
+    double dis = sqrt(d2);
+    marginal = fabs(dis - CRLK_COLLISION_DIS) < CRLK_NEAR_EPS;
+    definite = dis <= CRLK_COLLISION_DIS - CRLK_NEAR_EPS;
+    return (dis > CRLK_COLLISION_DIS) ? dis : -1.0;
+}
+
+// FP32 screen: squared distance from the robot's body origin to the solid AABB.
+__device__ __forceinline__ float aabb_center_d2(float4 o, float px, float py)
+{
+    float ex = fmaxf(fmaxf(o.x - px, px - o.z), 0.0f);
+    float ey = fmaxf(fmaxf(o.y - py, py - o.w), 0.0f);
+    return ex * ex + ey * ey;
+}
+
+// ---------------------------------------------------------------- reductions
+
+__device__ __forceinline__ double warp_min_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// lexicographic (value, index) minimum: the FIRST minimum wins (np.argmin).
+__device__ __forceinline__ void warp_argmin(double &v, int &i)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// numpy pairwise summation (umath DOUBLE_pairwise_sum) leaf: n <= 128.
+template <class F>
+__device__ __forceinline__ double np_leaf_sum(F f, int off, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res += f(off + i);
+        return res;
+    }
+    double r0 = f(off), r1 = f(off + 1), r2 = f(off + 2), r3 = f(off + 3);
+    double r4 = f(off + 4), r5 = f(off + 5), r6 = f(off + 6), r7 = f(off + 7);
+    int i;
+    int lim = n - (n % 8);
+    for (i = 8; i < lim; i += 8) {
+        r0 += f(off + i);     r1 += f(off + i + 1); r2 += f(off + i + 2); r3 += f(off + i + 3);
+        r4 += f(off + i + 4); r5 += f(off + i + 5); r6 += f(off + i + 6); r7 += f(off + i + 7);
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; i++) res += f(off + i);
+    return res;
+}

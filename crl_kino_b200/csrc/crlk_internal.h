@@ -1,0 +1,89 @@
+// Internal declarations shared by the translation units of libcrlk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/crlk.h"
+
+// Plain-old-data copies of the parameter structs as the kernels see them.
+struct EnvP {
+    double max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt;
+    float rl, rb, rr, rt;   // robot rectangle (float32 values)
+    float rc;               // circumradius of the robot rectangle about the body origin
+};
+
+struct DwaP {
+    double v_res, w_res, dt, predict_time;
+    double g_goal, g_ob, g_speed;
+    int skip, use_clearance;
+    int n_sub;     // base_dt sub-steps per dt      (differential_env.py:69 loop count)
+    int n_outer;   // dt steps per rollout           (dwa.py:39 loop count)
+    int nv_max, nw_max;
+};
+
+struct ExtP {
+    int n_max_extend, n_tree;
+    int n_sub_step;        // base_dt sub-steps per executed control step
+    double reach_radius;
+};
+
+struct CrlkEnv {
+    int device;
+    CrlkEnvParams host;
+    EnvP p;
+    float4 *d_rects;  // M obstacles [l, b, r, t]
+    int M;
+};
+
+struct CrlkPolicy {
+    int device;
+    int n_layers;
+    int dims[9];
+    int kpad[8];          // dims[i] rounded up to 8 (row stride of activations / weights)
+    float *d_w[8];        // [dims[i+1]][kpad[i]] row-major, zero padded
+    float *d_b[8];
+    float low[2], high[2], scale[2], bias[2];
+    int max_dim;
+};
+
+struct CrlkEstimator {
+    int device;
+    float *d_params;      // est params then cls params, each packed (see crlk_nets.cu)
+};
+
+void crlk_set_error(const char *fmt, ...);
+int crlk_count_loop_lt(double limit, double step);   // t = 0; while (t <  limit) t += step
+int crlk_count_loop_le(double limit, double step);   // t = 0; while (t <= limit) t += step
+int crlk_make_dwa(const CrlkEnv *env, const CrlkDwaParams *in, DwaP *out);
+size_t crlk_dwa_smem_bytes(const DwaP &d);
+int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x);
+
+#define CRLK_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            crlk_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return CRLK_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define CRLK_REQUIRE(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            crlk_set_error("invalid argument: %s", msg);         \
+            return CRLK_E_INVALID;                                \
+        }                                                         \
+    } while (0)
+
+#define CRLK_LAUNCH_CHECK()                                                               \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            crlk_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return CRLK_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+int crlk_require_device(void);

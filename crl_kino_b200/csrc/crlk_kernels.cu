@@ -1,0 +1,1233 @@
+// libcrlk.so -- environment, DWA, nearest-node and fused-extend kernels (sm_100a).
+// Compiled with --fmad=false: the float64 arithmetic must round exactly like
+// the reference's scalar Python/numpy code; fused operations are explicit.
+#include <math_constants.h>
+#include <stdarg.h>
+
+#include "crlk_device.cuh"
+
+// ------------------------------------------------------------ error plumbing
+
+static thread_local char g_err[512] = "";
+
+void crlk_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *crlk_last_error(void) { return g_err; }
+extern "C" int crlk_abi_version(void) { return CRLK_ABI_VERSION; }
+
+extern "C" int crlk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int crlk_require_device(void)
+{
+    if (crlk_device_count() <= 0) {
+        crlk_set_error("no CUDA device visible: libcrlk has no CPU fallback");
+        return CRLK_E_NODEVICE;
+    }
+    return CRLK_OK;
+}
+
+// Float loops of the reference whose trip count depends on rounding
+// (differential_env.py:69 `while t < duration`, dwa.py:39 `while t <= predict_time`).
+int crlk_count_loop_lt(double limit, double step)
+{
+    int n = 0;
+    double t = 0.0;
+    while (t < limit && n < 1000000) { t += step; n++; }
+    return n;
+}
+int crlk_count_loop_le(double limit, double step)
+{
+    int n = 0;
+    double t = 0.0;
+    while (t <= limit && n < 1000000) { t += step; n++; }
+    return n;
+}
+
+// ------------------------------------------------------------------- handles
+
+static void fill_envp(const CrlkEnvParams *in, EnvP *p)
+{
+    p->max_v = in->max_v; p->min_v = in->min_v; p->max_w = in->max_w;
+    p->max_acc_v = in->max_acc_v; p->max_acc_w = in->max_acc_w; p->base_dt = in->base_dt;
+    p->rl = in->robot_rect[0]; p->rb = in->robot_rect[1];
+    p->rr = in->robot_rect[2]; p->rt = in->robot_rect[3];
+    float m = 0.f;
+    const float xs[2] = {p->rl, p->rr}, ys[2] = {p->rb, p->rt};
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) m = fmaxf(m, sqrtf(xs[i] * xs[i] + ys[j] * ys[j]));
+    p->rc = m * 1.0001f;
+}
+
+extern "C" int crlk_env_set_obs(CrlkEnv *env, const float *rects_host, int32_t M)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_REQUIRE(M >= 0 && (M == 0 || rects_host != nullptr), "rects");
+    CRLK_CUDA(cudaSetDevice(env->device));
+    if (env->d_rects) { CRLK_CUDA(cudaFree(env->d_rects)); env->d_rects = nullptr; }
+    env->M = M;
+    // one spare element so that a zero-obstacle env still has a valid pointer
+    CRLK_CUDA(cudaMalloc(&env->d_rects, sizeof(float4) * (size_t)(M + 1)));
+    if (M > 0)
+        CRLK_CUDA(cudaMemcpy(env->d_rects, rects_host, sizeof(float4) * (size_t)M,
+                             cudaMemcpyHostToDevice));
+    return CRLK_OK;
+}
+
+extern "C" int crlk_env_create(const CrlkEnvParams *params, const float *rects_host, int32_t M,
+                               CrlkEnv **out)
+{
+    CRLK_REQUIRE(params != nullptr && out != nullptr, "params/out is NULL");
+    CRLK_REQUIRE(params->base_dt > 0, "base_dt must be positive");
+    int rc = crlk_require_device();
+    if (rc) return rc;
+    CrlkEnv *e = new CrlkEnv();
+    memset(e, 0, sizeof *e);
+    CRLK_CUDA(cudaGetDevice(&e->device));
+    e->host = *params;
+    fill_envp(params, &e->p);
+    rc = crlk_env_set_obs(e, rects_host, M);
+    if (rc) { delete e; return rc; }
+    *out = e;
+    return CRLK_OK;
+}
+
+extern "C" int crlk_env_destroy(CrlkEnv *env)
+{
+    if (!env) return CRLK_OK;
+    if (env->d_rects) cudaFree(env->d_rects);
+    delete env;
+    return CRLK_OK;
+}
+
+extern "C" int crlk_env_num_obs(const CrlkEnv *env) { return env ? env->M : 0; }
+
+// --------------------------------------------------- collision / clearance (K2)
+
+#define WQ_CAP 64   // per-warp survivor queue
+
+// Drain a warp's survivor queue: each lane evaluates one obstacle exactly.
+__device__ __forceinline__ void warp_drain(const EnvP &e, const RobotPose &g, const float4 *rects,
+                                           const int *queue, int count, double &best,
+                                           bool &definite, bool &marginal)
+{
+    int lane = threadIdx.x & 31;
+    for (int base = 0; base < count; base += 32) {
+        int k = base + lane;
+        if (k < count) {
+            bool d, m;
+            double dis = dis2obs_exact(e, g, __ldg(&rects[queue[k]]), d, m);
+            definite |= d;
+            marginal |= m;
+            best = fmin(best, dis);   // -1 (collision) wins every min, as in get_clearance
+        }
+    }
+}
+
+// One warp per pose.  mode_clearance = 0: flag only (screen at 0.05);
+// 1: exact min distance (screen against the running best).
+__global__ void __launch_bounds__(256)
+k_valid_state(EnvP e, const float4 *__restrict__ rects, int M, const double *__restrict__ states,
+              int B, uint8_t *valid, double *clearance, uint8_t *near_boundary)
+{
+    __shared__ int s_queue[8][WQ_CAP];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int pose = blockIdx.x * 8 + warp;
+    if (pose >= B) return;
+    const double *st = states + 5 * (size_t)pose;
+    RobotPose g;
+    robot_pose_setup(e, st[0], st[1], st[2], g);
+    float px = (float)g.x, py = (float)g.y;
+    int *queue = s_queue[warp];
+    double best = CRLK_CLEARANCE_CAP;
+    bool definite = false, marginal = false;
+    const bool want_clear = clearance != nullptr;
+
+    float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
+    if (want_clear) {
+        // pass 1: every lane finds its obstacle of smallest lower bound and
+        // evaluates it exactly; the warp minimum is an upper bound of the answer.
+        float lmin = CUDART_INF_F;
+        int limin = -1;
+        for (int o = lane; o < M; o += 32) {
+            float d2 = aabb_center_d2(__ldg(&rects[o]), px, py);
+            if (d2 < lmin) { lmin = d2; limin = o; }
+        }
+        if (limin >= 0) {
+            bool d, m;
+            double dis = dis2obs_exact(e, g, __ldg(&rects[limin]), d, m);
+            definite |= d; marginal |= m;
+            best = fmin(best, dis);
+        }
+        best = warp_min_d(best);
+        // pass 2 screens against that bound (never below the collision screen)
+        float b = (float)fmax(best, 0.0) * 1.0001f + e.rc + CRLK_CULL_MARGIN;
+        thr = fmaxf(thr, b);
+    }
+    float thr2 = thr * thr;
+    int count = 0;   // warp-uniform
+    for (int base = 0; base < M; base += 32) {
+        int o = base + lane;
+        bool keep = false;
+        if (o < M) keep = aabb_center_d2(__ldg(&rects[o]), px, py) <= thr2;
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (mask) {
+            int pos = count + __popc(mask & ((1u << lane) - 1u));
+            if (keep) queue[pos] = o;
+            count += __popc(mask);
+            __syncwarp();
+            if (count > WQ_CAP - 32) {
+                warp_drain(e, g, rects, queue, count, best, definite, marginal);
+                count = 0;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    warp_drain(e, g, rects, queue, count, best, definite, marginal);
+    best = warp_min_d(best);
+    bool any_def = __any_sync(0xffffffffu, definite);
+    bool any_mar = __any_sync(0xffffffffu, marginal);
+    if (lane == 0) {
+        if (valid) valid[pose] = (best < 0.0) ? 0 : 1;
+        if (clearance) clearance[pose] = (best < 0.0) ? -1.0 : best;
+        if (near_boundary) near_boundary[pose] = (any_mar && !any_def) ? 1 : 0;
+    }
+}
+
+extern "C" int crlk_valid_state(const CrlkEnv *env, const double *states, int32_t B, uint8_t *valid,
+                                double *clearance, uint8_t *near_boundary, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_REQUIRE(B >= 0 && (B == 0 || states != nullptr), "states");
+    if (B == 0) return CRLK_OK;
+    k_valid_state<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        env->p, env->d_rects, env->M, states, B, valid, clearance, near_boundary);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// valid_point_check: one thread per point, obstacles broadcast through L1.
+__global__ void __launch_bounds__(256)
+k_valid_points(const float4 *__restrict__ rects, int M, const double *__restrict__ pts, int K,
+               uint8_t *valid)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    double x = pts[2 * (size_t)i], y = pts[2 * (size_t)i + 1];
+    bool col = false;
+    for (int o = 0; o < M; o++) {
+        float4 r = __ldg(&rects[o]);
+        col |= (x >= (double)r.x && x <= (double)r.z && y >= (double)r.y && y <= (double)r.w);
+    }
+    valid[i] = col ? 0 : 1;
+}
+
+extern "C" int crlk_valid_points(const CrlkEnv *env, const double *points, int32_t K, uint8_t *valid,
+                                 void *stream)
+{
+    CRLK_REQUIRE(env != nullptr && valid != nullptr, "env/valid is NULL");
+    CRLK_REQUIRE(K >= 0 && (K == 0 || points != nullptr), "points");
+    if (K == 0) return CRLK_OK;
+    k_valid_points<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env->d_rects, env->M, points,
+                                                                     K, valid);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------------------------ dynamics kernels
+
+__global__ void k_motion(EnvP e, const double *__restrict__ sin_, const double *__restrict__ cmd,
+                         int n_sub, int B, int accel, double *sout)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double s[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) s[k] = sin_[5 * (size_t)i + k];
+    double c0 = cmd[2 * (size_t)i], c1 = cmd[2 * (size_t)i + 1];
+    if (!accel) {
+        motion_velocity_dev(e, s, c0, c1, n_sub);
+    } else {
+        for (int k = 0; k < n_sub; k++) {
+            double u0 = acc_substep(s[3], c0, e.max_acc_v, e.min_v, e.max_v, e.base_dt);
+            double u1 = acc_substep(s[4], c1, e.max_acc_w, -e.max_w, e.max_w, e.base_dt);
+            pose_substep(s, u0, u1, e.base_dt);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) sout[5 * (size_t)i + k] = s[k];
+}
+
+static int launch_motion(const CrlkEnv *env, const double *sin_, const double *cmd, double duration,
+                         int B, int accel, double *sout, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_REQUIRE(B >= 0 && (B == 0 || (sin_ && cmd && sout)), "NULL array");
+    if (B == 0) return CRLK_OK;
+    int n_sub = crlk_count_loop_lt(duration, env->p.base_dt);
+    k_motion<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, sin_, cmd, n_sub, B, accel,
+                                                               sout);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+extern "C" int crlk_motion_velocity(const CrlkEnv *env, const double *states_in, const double *cmds,
+                                    double duration, int32_t B, double *states_out, void *stream)
+{
+    return launch_motion(env, states_in, cmds, duration, B, 0, states_out, stream);
+}
+
+extern "C" int crlk_motion(const CrlkEnv *env, const double *states_in, const double *acc,
+                           double duration, int32_t B, double *states_out, void *stream)
+{
+    return launch_motion(env, states_in, acc, duration, B, 1, states_out, stream);
+}
+
+__global__ void k_dynamic_window(EnvP e, const double *__restrict__ states, double dt, int B,
+                                 double *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double v = states[5 * (size_t)i + 3], w = states[5 * (size_t)i + 4];
+    out[4 * (size_t)i + 1] = pymin(v + e.max_acc_v * dt, e.max_v);
+    out[4 * (size_t)i + 0] = pymax(v - e.max_acc_v * dt, e.min_v);
+    out[4 * (size_t)i + 3] = pymin(w + e.max_acc_w * dt, e.max_w);
+    out[4 * (size_t)i + 2] = pymax(w - e.max_acc_w * dt, -e.max_w);
+}
+
+extern "C" int crlk_dynamic_window(const CrlkEnv *env, const double *states, double dt, int32_t B,
+                                   double *out, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_REQUIRE(B >= 0 && (B == 0 || (states && out)), "NULL array");
+    if (B == 0) return CRLK_OK;
+    k_dynamic_window<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, states, dt, B, out);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// -------------------------------------------------------- local observation (R9)
+
+#define OBS_NPTS 729
+#define OBS_SIDE 27
+#define OBS_TILE 1024
+#define OBS_NEAR_EPS 1e-9
+
+struct ObsGrid {      // np.arange(-2, 6, 0.3) / np.arange(-4, 4, 0.3) (differential_gym.py:67-71)
+    double ba0, ba1, bad;   // start, start+step, delta
+    double lr0, lr1, lrd;
+};
+
+__device__ __forceinline__ double arange_at(double a0, double a1, double d, int i)
+{
+    return (i == 0) ? a0 : (i == 1) ? a1 : a0 + (double)i * d;
+}
+
+// One CTA per observation: FP32 screen of the obstacle set against the local
+// window's bounding circle, then exact closed-interval tests (rigid.py:158-166).
+__global__ void __launch_bounds__(256)
+k_local_obs(ObsGrid og, const float4 *__restrict__ rects, int M, const double *__restrict__ states,
+            const double *__restrict__ goals, int goal_stride, int B, double *obs64, float *obs32,
+            int ld32, uint8_t *near_boundary)
+{
+    __shared__ float4 s_tile[OBS_TILE];
+    __shared__ int s_cnt;
+    __shared__ int s_near;
+    int b = blockIdx.x;
+    if (b >= B) return;
+    const double *st = states + 5 * (size_t)b;
+    double x = st[0], y = st[1], th = st[2];
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    // window centre in the body frame and its radius (+ slack)
+    double cbx = 0.5 * (og.ba0 + arange_at(og.ba0, og.ba1, og.bad, OBS_SIDE - 1));
+    double cby = 0.5 * (og.lr0 + arange_at(og.lr0, og.lr1, og.lrd, OBS_SIDE - 1));
+    double hx = arange_at(og.ba0, og.ba1, og.bad, OBS_SIDE - 1) - cbx;
+    double hy = arange_at(og.lr0, og.lr1, og.lrd, OBS_SIDE - 1) - cby;
+    float wcx = (float)((cs * cbx + (-sn) * cby) + x);
+    float wcy = (float)((sn * cbx + cs * cby) + y);
+    float rad = (float)sqrt(hx * hx + hy * hy) * 1.001f + 1e-3f;
+    float rad2 = rad * rad;
+
+    // this thread's sample points (3 per thread at 256 threads)
+    double pxs[3], pys[3];
+    bool occ[3] = {false, false, false};
+    bool nearp = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int p = threadIdx.x + k * 256;
+        int ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;
+        double bx = arange_at(og.ba0, og.ba1, og.bad, ib);
+        double by = arange_at(og.lr0, og.lr1, og.lrd, il);
+        pxs[k] = (cs * bx + (-sn) * by) + x;     // differential_gym.py:83 (wTb @ [bx, by, 1])
+        pys[k] = (sn * bx + cs * by) + y;
+    }
+    if (threadIdx.x == 0) s_near = 0;
+    for (int base = 0; base < M; base += OBS_TILE) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (int o = base + threadIdx.x; o < min(M, base + OBS_TILE); o += 256) {
+            float4 r = __ldg(&rects[o]);
+            if (aabb_center_d2(r, wcx, wcy) <= rad2) s_tile[atomicAdd(&s_cnt, 1)] = r;
+        }
+        __syncthreads();
+        int cnt = s_cnt;
+        for (int i = 0; i < cnt; i++) {
+            float4 r = s_tile[i];
+            double l = r.x, bo = r.y, rr = r.z, t = r.w;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double px = pxs[k], py = pys[k];
+                bool in = (px >= l && px <= rr && py >= bo && py <= t);
+                occ[k] |= in;
+                bool in_big = (px >= l - OBS_NEAR_EPS && px <= rr + OBS_NEAR_EPS &&
+                               py >= bo - OBS_NEAR_EPS && py <= t + OBS_NEAR_EPS);
+                bool in_small = (px >= l + OBS_NEAR_EPS && px <= rr - OBS_NEAR_EPS &&
+                                 py >= bo + OBS_NEAR_EPS && py <= t - OBS_NEAR_EPS);
+                nearp |= (in_big && !in_small) && (threadIdx.x + k * 256 < OBS_NPTS);
+            }
+        }
+    }
+    if (nearp) s_near = 1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int p = threadIdx.x + k * 256;
+        if (p < OBS_NPTS) {
+            double v = occ[k] ? 0.0 : 1.0;
+            if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
+            if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double *g = goals + (size_t)goal_stride * b;
+        double qx = g[0] - x, qy = g[1] - y;     // differential_gym.py:186-187 as R^T (g - t)
+        double gbx = cs * qx + sn * qy;
+        double gby = (-sn) * qx + cs * qy;
+        if (obs64) {
+            double *o = obs64 + (size_t)b * (4 + OBS_NPTS);
+            o[0] = gbx; o[1] = gby; o[2] = st[3]; o[3] = st[4];
+        }
+        if (obs32) {
+            float *o = obs32 + (size_t)b * ld32;
+            o[0] = (float)gbx; o[1] = (float)gby; o[2] = (float)st[3]; o[3] = (float)st[4];
+            for (int k = 4 + OBS_NPTS; k < ld32; k++) o[k] = 0.f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && near_boundary) near_boundary[b] = (uint8_t)s_near;
+}
+
+static ObsGrid make_obs_grid()
+{
+    ObsGrid g;
+    g.ba0 = -2.0; g.ba1 = -2.0 + 0.3; g.bad = g.ba1 - g.ba0;
+    g.lr0 = -4.0; g.lr1 = -4.0 + 0.3; g.lrd = g.lr1 - g.lr0;
+    return g;
+}
+
+extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals,
+                              int32_t goal_stride, int32_t B, double *obs64, float *obs32,
+                              int32_t ld32, uint8_t *near_boundary, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_REQUIRE(B >= 0 && (B == 0 || (states && goals)), "NULL array");
+    CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
+    CRLK_REQUIRE(obs32 == nullptr || ld32 >= 4 + OBS_NPTS, "ld32 < 733");
+    if (B == 0) return CRLK_OK;
+    k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->d_rects, env->M, states,
+                                                    goals, goal_stride, B, obs64, obs32, ld32,
+                                                    near_boundary);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------------------------------- DWA (K1)
+
+#define DWA_THREADS 256
+#define PW_BLOCK 128
+
+struct DwaSmem {
+    double *c0, *c1;
+    double *vtab, *vlast, *c2n;
+    double *wcos, *wsin, *wth;
+    double *leaf;          // [3][lmax]
+    int *loff, *llen;      // [lmax]
+    double *red_v, *red_s; // [32]
+    int *red_i;            // [32]
+    double *scal;          // [16]
+    int *iscal;            // [8]
+    int *queue;            // [DWA_THREADS] scratch for the collision survivor list
+    int spos, rmax, lmax;
+};
+
+__host__ __device__ inline int dwa_spos(const DwaP &d)
+{
+    return d.use_clearance ? d.n_sub * d.n_outer : d.n_sub;
+}
+__host__ __device__ inline int dwa_rmax(const DwaP &d) { return d.nv_max * d.nw_max; }
+__host__ __device__ inline int dwa_lmax(const DwaP &d) { return dwa_rmax(d) / 32 + 8; }
+
+__host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, DwaSmem *s)
+{
+    size_t off = 0;
+    int spos = dwa_spos(d), rmax = dwa_rmax(d), lmax = dwa_lmax(d);
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    size_t o_c0 = take(sizeof(double) * rmax);
+    size_t o_c1 = take(d.use_clearance ? sizeof(double) * rmax : 0);
+    size_t o_vtab = take(sizeof(double) * d.nv_max * spos);
+    size_t o_vlast = take(sizeof(double) * d.nv_max);
+    size_t o_c2n = take(sizeof(double) * d.nv_max);
+    size_t o_wcos = take(sizeof(double) * d.nw_max * spos);
+    size_t o_wsin = take(sizeof(double) * d.nw_max * spos);
+    size_t o_wth = take(sizeof(double) * d.nw_max * d.n_outer);
+    size_t o_leaf = take(sizeof(double) * 3 * lmax);
+    size_t o_loff = take(sizeof(int) * lmax);
+    size_t o_llen = take(sizeof(int) * lmax);
+    size_t o_rv = take(sizeof(double) * 32);
+    size_t o_rs = take(sizeof(double) * 32);
+    size_t o_ri = take(sizeof(int) * 32);
+    size_t o_sc = take(sizeof(double) * 16);
+    size_t o_is = take(sizeof(int) * 8);
+    size_t o_q = take(sizeof(int) * 1024);
+    if (s) {
+        s->c0 = (double *)(base + o_c0); s->c1 = (double *)(base + o_c1);
+        s->vtab = (double *)(base + o_vtab); s->vlast = (double *)(base + o_vlast);
+        s->c2n = (double *)(base + o_c2n);
+        s->wcos = (double *)(base + o_wcos); s->wsin = (double *)(base + o_wsin);
+        s->wth = (double *)(base + o_wth);
+        s->leaf = (double *)(base + o_leaf);
+        s->loff = (int *)(base + o_loff); s->llen = (int *)(base + o_llen);
+        s->red_v = (double *)(base + o_rv); s->red_s = (double *)(base + o_rs);
+        s->red_i = (int *)(base + o_ri);
+        s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
+        s->queue = (int *)(base + o_q);
+        s->spos = spos; s->rmax = rmax; s->lmax = lmax;
+    }
+    return off;
+}
+
+size_t crlk_dwa_smem_bytes(const DwaP &d) { return dwa_carve(d, nullptr, nullptr); }
+
+// np.arange(lo, hi + res, res): length and the (a0, a1, delta) triple.
+__host__ __device__ inline int arange_len(double start, double stop, double step)
+{
+    double v = (stop - start) / step;
+    double c = ceil(v);
+    if (!(c > 0.0)) return 0;
+    if (c > 1e6) return 1000000;
+    return (int)c;
+}
+
+int crlk_make_dwa(const CrlkEnv *env, const CrlkDwaParams *in, DwaP *d)
+{
+    CRLK_REQUIRE(env && in && d, "NULL dwa params");
+    CRLK_REQUIRE(in->v_res > 0 && in->w_res > 0 && in->dt > 0 && in->predict_time >= 0, "dwa params");
+    CRLK_REQUIRE(in->skip >= 1, "skip < 1");
+    d->v_res = in->v_res; d->w_res = in->w_res; d->dt = in->dt; d->predict_time = in->predict_time;
+    d->g_goal = in->to_goal_cost_gain; d->g_ob = in->ob_gain; d->g_speed = in->speed_cost_gain;
+    d->skip = in->skip; d->use_clearance = in->use_clearance ? 1 : 0;
+    d->n_sub = crlk_count_loop_lt(in->dt, env->p.base_dt);
+    d->n_outer = crlk_count_loop_le(in->predict_time, in->dt);
+    // the window is at most 2*acc*dt wide (and never wider than the velocity range)
+    double wv = fmin(2.0 * env->p.max_acc_v * in->dt, env->p.max_v - env->p.min_v);
+    double ww = fmin(2.0 * env->p.max_acc_w * in->dt, 2.0 * env->p.max_w);
+    d->nv_max = arange_len(0.0, wv + in->v_res, in->v_res) + 2;
+    d->nw_max = arange_len(0.0, ww + in->w_res, in->w_res) + 2;
+    CRLK_REQUIRE(d->n_sub >= 1 && d->n_outer >= 1 && d->n_sub * d->n_outer <= 4096, "dwa horizon");
+    CRLK_REQUIRE((long)d->nv_max * d->nw_max <= 16384, "rollout grid too large (> 16384)");
+    return CRLK_OK;
+}
+
+// Leaves of numpy's pairwise-sum recursion over n elements, left to right.
+__device__ int pw_enumerate(int n, int *loff, int *llen)
+{
+    int so[32], sn[32];
+    int sp = 0, cnt = 0;
+    so[0] = 0; sn[0] = n; sp = 1;
+    while (sp) {
+        sp--;
+        int o = so[sp], m = sn[sp];
+        if (m <= PW_BLOCK) {
+            loff[cnt] = o; llen[cnt] = m; cnt++;
+        } else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            so[sp] = o + n2; sn[sp] = m - n2; sp++;
+            so[sp] = o;      sn[sp] = n2;     sp++;
+        }
+    }
+    return cnt;
+}
+
+// Combine leaf sums in the recursion's own association order.
+__device__ double pw_combine(int n, const double *leaf, int &cur)
+{
+    if (n <= PW_BLOCK) return leaf[cur++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    double a = pw_combine(n2, leaf, cur);
+    double b = pw_combine(n - n2, leaf, cur);
+    return a + b;
+}
+
+struct DwaResult {
+    double v, w, cost;
+    int idx, R;
+    int near_tie;
+};
+
+// get_clearance for one pose by one thread (used only when use_clearance = 1).
+__device__ double clearance_thread(const EnvP &e, const float4 *__restrict__ rects, int M, double x,
+                                   double y, double th)
+{
+    RobotPose g;
+    robot_pose_setup(e, x, y, th, g);
+    float px = (float)x, py = (float)y;
+    float lmin = CUDART_INF_F;
+    int limin = -1;
+    for (int o = 0; o < M; o++) {
+        float d2 = aabb_center_d2(__ldg(&rects[o]), px, py);
+        if (d2 < lmin) { lmin = d2; limin = o; }
+    }
+    double best = CRLK_CLEARANCE_CAP;
+    bool d, m;
+    if (limin >= 0) best = fmin(best, dis2obs_exact(e, g, __ldg(&rects[limin]), d, m));
+    if (best < 0.0) return -1.0;
+    float thr = (float)best * 1.0001f + e.rc + CRLK_CULL_MARGIN;
+    float thr2 = thr * thr;
+    for (int o = 0; o < M; o++) {
+        float4 r = __ldg(&rects[o]);
+        if (aabb_center_d2(r, px, py) <= thr2) {
+            best = fmin(best, dis2obs_exact(e, g, r, d, m));
+            if (best < 0.0) return -1.0;
+        }
+    }
+    return best;
+}
+
+// DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
+// doubles) and the goal must be block-uniform.  Every thread returns the result.
+__device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float4 *__restrict__ rects,
+                                       int M, const double *st, double gx, double gy,
+                                       const DwaSmem &sm)
+{
+    const int tid = threadIdx.x, T = DWA_THREADS;
+    const int lane = tid & 31, warp = tid >> 5;
+    const double dt = e.base_dt;
+    // dynamic window over d.dt (dwa.py:46, differential_env.py:107-114)
+    double v_hi = pymin(st[3] + e.max_acc_v * d.dt, e.max_v);
+    double v_lo = pymax(st[3] - e.max_acc_v * d.dt, e.min_v);
+    double w_hi = pymin(st[4] + e.max_acc_w * d.dt, e.max_w);
+    double w_lo = pymax(st[4] - e.max_acc_w * d.dt, -e.max_w);
+    int nv = min(arange_len(v_lo, v_hi + d.v_res, d.v_res), d.nv_max);
+    int nw = min(arange_len(w_lo, w_hi + d.w_res, d.w_res), d.nw_max);
+    double v1 = v_lo + d.v_res, vd = v1 - v_lo;
+    double w1 = w_lo + d.w_res, wd = w1 - w_lo;
+    const int R = nv * nw;
+    const int S = d.n_sub * d.n_outer, spos = sm.spos;
+
+    __syncthreads();   // previous users of the shared tables are done
+    // velocity chains (one per v command) and heading chains (one per w command)
+    for (int i = tid; i < nv; i += T) {
+        double cv = arange_at(v_lo, v1, vd, i);
+        double cur = st[3];
+        for (int k = 0; k < S; k++) {
+            cur = vel_substep(cur, cv, e.max_acc_v, e.min_v, e.max_v, dt);
+            if (k < spos) sm.vtab[i * spos + k] = cur;
+        }
+        sm.vlast[i] = cur;
+    }
+    for (int j = T - 1 - tid; j < nw; j += T) {
+        double cw = arange_at(w_lo, w1, wd, j);
+        double cur = st[4], th = st[2];
+        for (int k = 0; k < spos; k++) {
+            cur = vel_substep(cur, cw, e.max_acc_w, -e.max_w, e.max_w, dt);
+            th = normalize_angle(th + cur * dt);
+            double sn, cs;
+            sincos(th, &sn, &cs);
+            sm.wcos[j * spos + k] = cs;
+            sm.wsin[j * spos + k] = sn;
+            if ((k + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (k + 1) / d.n_sub - 1] = th;
+        }
+    }
+    if (tid == 0) sm.iscal[0] = pw_enumerate(R, sm.loff, sm.llen);
+    // clearance of the shared first row (dwa.py:65-67, i = 0)
+    double clr0 = CRLK_CLEARANCE_CAP;
+    if (d.use_clearance) clr0 = pymax(clearance_thread(e, rects, M, st[0], st[1], st[2]), 0.001);
+    __syncthreads();
+
+    // rollouts: heading cost from trajectory row 1 (dwa.py:58-62)
+    for (int r = tid; r < R; r += T) {
+        int i = r / nw, j = r - i * nw;
+        double x = st[0], y = st[1];
+        const double *vt = sm.vtab + i * spos;
+        const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
+        for (int k = 0; k < d.n_sub; k++) {
+            x = x + vt[k] * wc[k] * dt;
+            y = y + vt[k] * ws[k] * dt;
+        }
+        double ang = atan2(gy - y, gx - x);
+        double c0 = fabs(ang - sm.wth[j * d.n_outer]);
+        c0 = pymin(c0, CRLK_TWO_PI - c0);
+        sm.c0[r] = c0;
+        if (d.use_clearance) {
+            double min_dis = pymin(clr0, 100.0);
+            for (int row = 1; row <= d.n_outer; row++) {
+                if (row > 1)
+                    for (int k = (row - 1) * d.n_sub; k < row * d.n_sub; k++) {
+                        x = x + vt[k] * wc[k] * dt;
+                        y = y + vt[k] * ws[k] * dt;
+                    }
+                if (row % d.skip == 0) {
+                    double dis = pymax(clearance_thread(e, rects, M, x, y, sm.wth[j * d.n_outer + row - 1]),
+                                       0.001);
+                    min_dis = pymin(dis, min_dis);
+                }
+            }
+            sm.c1[r] = 1.0 / min_dis;
+        }
+    }
+    __syncthreads();
+
+    // column sums in numpy's pairwise order (dwa.py:76-78)
+    const int L = sm.iscal[0];
+    if (warp < 3) {
+        for (int l = lane; l < L; l += 32) {
+            int off = sm.loff[l], n = sm.llen[l];
+            double s;
+            if (warp == 0) {
+                const double *c0 = sm.c0;
+                s = np_leaf_sum([&](int q) { return c0[q]; }, off, n);
+            } else if (warp == 1) {
+                if (d.use_clearance) {
+                    const double *c1 = sm.c1;
+                    s = np_leaf_sum([&](int q) { return c1[q]; }, off, n);
+                } else {
+                    s = np_leaf_sum([&](int) { return 1.0 / 100.0; }, off, n);
+                }
+            } else {
+                const double *vl = sm.vlast;
+                s = np_leaf_sum([&](int q) { return v_hi - vl[q / nw]; }, off, n);
+            }
+            sm.leaf[warp * sm.lmax + l] = s;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int cur = 0;
+            sm.scal[warp] = pw_combine(R, sm.leaf + warp * sm.lmax, cur);
+        }
+    }
+    __syncthreads();
+    const double S0 = sm.scal[0], S1 = sm.scal[1], S2 = sm.scal[2];
+    for (int i = tid; i < nv; i += T) {
+        double c2 = v_hi - sm.vlast[i];
+        sm.c2n[i] = (S2 != 0.0) ? c2 / S2 : c2;
+    }
+    __syncthreads();
+
+    // weighted sum and first argmin (dwa.py:79-82), plus the runner-up for near_tie
+    double best = CUDART_INF, second = CUDART_INF;
+    int bi = 0x7fffffff;
+    const double c1n_const = (S1 != 0.0) ? (1.0 / 100.0) / S1 : (1.0 / 100.0);
+    for (int r = tid; r < R; r += T) {
+        int i = r / nw;
+        double c0n = (S0 != 0.0) ? sm.c0[r] / S0 : sm.c0[r];
+        double c1n = c1n_const;
+        if (d.use_clearance) c1n = (S1 != 0.0) ? sm.c1[r] / S1 : sm.c1[r];
+        double c = d.g_goal * c0n + d.g_ob * c1n + d.g_speed * sm.c2n[i];
+        if (c < best) { second = best; best = c; bi = r; }
+        else if (c < second) second = c;
+    }
+    // warp level: merge (best, idx, second)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        double os = __shfl_xor_sync(0xffffffffu, second, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        second = fmin(fmin(second, os), fmax(best, ob));
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sm.red_v[warp] = best; sm.red_s[warp] = second; sm.red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        double b = sm.red_v[0], s2 = sm.red_s[0];
+        int ix = sm.red_i[0];
+        for (int w = 1; w < T / 32; w++) {
+            double ob = sm.red_v[w], os = sm.red_s[w];
+            int oi = sm.red_i[w];
+            double loser = fmax(b, ob);
+            if (ob < b || (ob == b && oi < ix)) { b = ob; ix = oi; }
+            s2 = fmin(fmin(s2, os), loser);
+        }
+        int i = ix / nw, j = ix - i * nw;
+        sm.scal[4] = arange_at(v_lo, v1, vd, i);
+        sm.scal[5] = arange_at(w_lo, w1, wd, j);
+        sm.scal[6] = b;
+        sm.iscal[1] = ix;
+        double gap = s2 - b;
+        sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(b)) ? 1 : 0;
+    }
+    __syncthreads();
+    DwaResult res;
+    res.v = sm.scal[4]; res.w = sm.scal[5]; res.cost = sm.scal[6];
+    res.idx = sm.iscal[1]; res.near_tie = sm.iscal[2]; res.R = R;
+    return res;
+}
+
+__global__ void __launch_bounds__(DWA_THREADS)
+k_dwa_control(EnvP e, DwaP d, const float4 *__restrict__ rects, int M,
+              const double *__restrict__ states, const double *__restrict__ goals, int goal_stride,
+              int B, double *opt_v, int *opt_idx, double *opt_cost, double *opt_traj,
+              int *n_rollouts, uint8_t *near_tie)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DwaSmem sm;
+    dwa_carve(d, smem_raw, &sm);
+    __shared__ double s_state[5];
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
+        __syncthreads();
+        double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
+        DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm);
+        if (threadIdx.x == 0) {
+            opt_v[2 * (size_t)b] = r.v;
+            opt_v[2 * (size_t)b + 1] = r.w;
+            if (opt_idx) opt_idx[b] = r.idx;
+            if (opt_cost) opt_cost[b] = r.cost;
+            if (n_rollouts) n_rollouts[b] = r.R;
+            if (near_tie) near_tie[b] = (uint8_t)r.near_tie;
+            if (opt_traj) {   // dwa.py:35-43 for the winner
+                double s[5];
+                for (int k = 0; k < 5; k++) s[k] = s_state[k];
+                double *tr = opt_traj + (size_t)b * (d.n_outer + 1) * 5;
+                for (int k = 0; k < 5; k++) tr[k] = s[k];
+                for (int row = 1; row <= d.n_outer; row++) {
+                    motion_velocity_dev(e, s, r.v, r.w, d.n_sub);
+                    for (int k = 0; k < 5; k++) tr[row * 5 + k] = s[k];
+                }
+            }
+        }
+    }
+}
+
+static int set_smem_attr(const void *fn, size_t bytes)
+{
+    CRLK_REQUIRE(bytes <= 220 * 1024, "shared memory request exceeds 220 KB");
+    if (bytes > 48 * 1024)
+        CRLK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CRLK_OK;
+}
+
+extern "C" int crlk_dwa_traj_rows(const CrlkEnv *env, const CrlkDwaParams *dwa)
+{
+    DwaP d;
+    int rc = crlk_make_dwa(env, dwa, &d);
+    return rc ? rc : d.n_outer + 1;
+}
+
+extern "C" int crlk_dwa_max_rollouts(const CrlkEnv *env, const CrlkDwaParams *dwa)
+{
+    DwaP d;
+    int rc = crlk_make_dwa(env, dwa, &d);
+    return rc ? rc : d.nv_max * d.nw_max;
+}
+
+extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, const double *states,
+                                const double *goals, int32_t goal_stride, int32_t B, double *opt_v,
+                                int32_t *opt_idx, double *opt_cost, double *opt_traj,
+                                int32_t *n_rollouts, uint8_t *near_tie, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    DwaP d;
+    int rc = crlk_make_dwa(env, dwa, &d);
+    if (rc) return rc;
+    CRLK_REQUIRE(B >= 0 && (B == 0 || (states && goals && opt_v)), "NULL array");
+    CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
+    if (B == 0) return CRLK_OK;
+    size_t smem = crlk_dwa_smem_bytes(d);
+    rc = set_smem_attr((const void *)k_dwa_control, smem);
+    if (rc) return rc;
+    k_dwa_control<<<B, DWA_THREADS, smem, (cudaStream_t)stream>>>(
+        env->p, d, env->d_rects, env->M, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
+        opt_traj, n_rollouts, near_tie);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------------- fused extend, DWA steering (R1)
+
+// valid_state_check for a block-uniform pose by the whole CTA: FP32 screen of
+// all M obstacles, survivors queued in shared memory, exact FP64 tests spread
+// over the threads.  Returns bit0 = collision, bit1 = the decision is within
+// 1e-6 of the 0.05 threshold (reported, not claimed).
+__device__ int collision_block(const EnvP &e, const float4 *__restrict__ rects, int M, double x,
+                               double y, double th, int *s_queue /*1024*/, int *s_ctl /*4*/)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    RobotPose g;
+    robot_pose_setup(e, x, y, th, g);
+    float px = (float)x, py = (float)y;
+    float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
+    float thr2 = thr * thr;
+    __syncthreads();
+    if (tid < 4) s_ctl[tid] = 0;
+    __syncthreads();
+    bool coll = false, definite = false, marginal = false;
+    for (int o = tid; o < M; o += T) {
+        float4 r = __ldg(&rects[o]);
+        if (aabb_center_d2(r, px, py) <= thr2) {
+            int pos = atomicAdd(&s_ctl[0], 1);
+            if (pos < 1024) s_queue[pos] = o;
+            else {   // queue overflow: evaluate in place
+                bool d, m;
+                coll |= dis2obs_exact(e, g, r, d, m) < 0.0;
+                definite |= d; marginal |= m;
+            }
+        }
+    }
+    __syncthreads();
+    int cnt = min(s_ctl[0], 1024);
+    for (int k = tid; k < cnt; k += T) {
+        bool d, m;
+        coll |= dis2obs_exact(e, g, __ldg(&rects[s_queue[k]]), d, m) < 0.0;
+        definite |= d; marginal |= m;
+    }
+    if (coll) atomicOr(&s_ctl[1], 1);
+    if (definite) atomicOr(&s_ctl[2], 1);
+    if (marginal) atomicOr(&s_ctl[3], 1);
+    __syncthreads();
+    int res = (s_ctl[1] ? 1 : 0) | ((s_ctl[3] && !s_ctl[2]) ? 2 : 0);
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(DWA_THREADS)
+k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
+             const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
+             double *path, int *n_steps, int *status, int *node_step, int *n_nodes, int *ctrl_idx,
+             uint8_t *flags, const uint8_t *__restrict__ active, int *work_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DwaSmem sm;
+    dwa_carve(d, smem_raw, &sm);
+    __shared__ double s_state[5];
+    __shared__ int s_ctl[8];
+    __shared__ int s_q;
+    const int per = x.n_max_extend / x.n_tree + 1;
+    const int tid = threadIdx.x;
+    for (;;) {
+        // dynamic work distribution: extensions finish after very different step counts
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int q = s_q;
+        if (q >= Q) break;
+        if (active && !active[q]) {
+            if (tid == 0) {
+                n_steps[q] = 0; status[q] = CRLK_EXT_TIMEOUT; n_nodes[q] = 0;
+                if (flags) flags[q] = 0;
+            }
+            continue;
+        }
+        if (tid < 5) s_state[tid] = from_states[5 * (size_t)q + tid];
+        __syncthreads();
+        const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
+        int nn = 0, st_code = CRLK_EXT_TIMEOUT, steps = 0, fl = 0;
+        for (int k = 1; k <= x.n_max_extend; k++) {
+            DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm);   // rrt.py:116
+            fl |= r.near_tie ? 2 : 0;
+            __syncthreads();
+            if (tid == 0) {
+                double s[5];
+                for (int c = 0; c < 5; c++) s[c] = s_state[c];
+                motion_velocity_dev(e, s, r.v, r.w, x.n_sub_step);                  // rrt.py:118
+                for (int c = 0; c < 5; c++) {
+                    s_state[c] = s[c];
+                    path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
+                }
+                if (ctrl_idx) ctrl_idx[(size_t)q * x.n_max_extend + (k - 1)] = r.idx;
+            }
+            __syncthreads();
+            steps = k;
+            // rrt.py:121: valid_state_check on the new state
+            int col = collision_block(e, rects, M, s_state[0], s_state[1], s_state[2], sm.queue, s_ctl);
+            if (col & 2) fl |= 1;
+            col &= 1;
+            if (col == 1) { st_code = CRLK_EXT_COLLISION; break; }
+            double ddx = s_state[0] - gx, ddy = s_state[1] - gy;
+            double dist = sqrt(fma(ddy, ddy, ddx * ddx));                            // rrt.py:124
+            if (dist <= x.reach_radius) {
+                if (tid == 0) node_step[(size_t)q * per + nn] = k;
+                nn++; st_code = CRLK_EXT_REACHED; break;
+            }
+            if (k % x.n_tree == 0) {                                                 // rrt.py:128
+                if (tid == 0) node_step[(size_t)q * per + nn] = k;
+                nn++;
+            }
+        }
+        if (tid == 0) {
+            n_steps[q] = steps; status[q] = st_code; n_nodes[q] = nn;
+            if (flags) flags[q] = (uint8_t)fl;
+        }
+    }
+}
+
+int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x)
+{
+    CRLK_REQUIRE(in != nullptr, "extend params NULL");
+    CRLK_REQUIRE(in->n_max_extend >= 1 && in->n_tree >= 1 && in->step_dt > 0, "extend params");
+    x->n_max_extend = in->n_max_extend;
+    x->n_tree = in->n_tree;
+    x->n_sub_step = crlk_count_loop_lt(in->step_dt, env->p.base_dt);
+    x->reach_radius = in->reach_radius;
+    return CRLK_OK;
+}
+
+static int *g_work_counter[64] = {nullptr};
+
+// A per-device 4-byte counter used by the persistent extend kernels.
+static int get_work_counter(int device, int **out, cudaStream_t stream)
+{
+    CRLK_REQUIRE(device >= 0 && device < 64, "device index");
+    if (!g_work_counter[device]) CRLK_CUDA(cudaMalloc(&g_work_counter[device], 256));
+    CRLK_CUDA(cudaMemsetAsync(g_work_counter[device], 0, 256, stream));
+    *out = g_work_counter[device];
+    return CRLK_OK;
+}
+
+extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
+                               const double *from_states, const double *targets, int32_t Q,
+                               double *path, int32_t *n_steps, int32_t *status, int32_t *node_step,
+                               int32_t *n_nodes, int32_t *ctrl_idx, uint8_t *flags,
+                               const uint8_t *active, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    DwaP d;
+    ExtP x;
+    int rc = crlk_make_dwa(env, dwa, &d);
+    if (rc) return rc;
+    rc = crlk_make_ext(env, ext, &x);
+    if (rc) return rc;
+    CRLK_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(from_states && targets && path && n_steps && status && node_step && n_nodes,
+                 "NULL array");
+    size_t smem = crlk_dwa_smem_bytes(d);
+    rc = set_smem_attr((const void *)k_extend_dwa, smem);
+    if (rc) return rc;
+    int dev = env->device, sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_dwa, DWA_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sms * per_sm;
+    if (grid > Q) grid = Q;
+    int *counter = nullptr;
+    rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
+    if (rc) return rc;
+    k_extend_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
+        env->p, d, x, env->d_rects, env->M, from_states, targets, Q, path, n_steps, status, node_step,
+        n_nodes, ctrl_idx, flags, active, counter);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------------------------ nearest node (K3)
+
+#define NN_THREADS 256
+#define NN_CAND 512
+
+struct NNPartial { double d, second; int idx; int pad; };
+
+__device__ __forceinline__ void nn_merge(double &d, int &i, double &s, double od, int oi, double os)
+{
+    s = fmin(fmin(s, os), fmax(d, od));
+    if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+}
+
+// Block-wide exact (d, idx, second) reduction; result valid in thread 0.
+__device__ void nn_block_reduce(double &d, int &i, double &s, double *sv, double *ss, int *si)
+{
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, d, o);
+        double os = __shfl_xor_sync(0xffffffffu, s, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        nn_merge(d, i, s, od, oi, os);
+    }
+    if (lane == 0) { sv[warp] = d; ss[warp] = s; si[warp] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < NN_THREADS / 32; w++) nn_merge(d, i, s, sv[w], si[w], ss[w]);
+}
+
+// Scan one segment of one tree.  grid = Q * splits CTAs.
+//   f32 path: squared distances in float32 over the SoA float copies (8 B per
+//   node of HBM traffic); every node whose value falls inside a guard band of
+//   the running block minimum is queued and re-scored exactly in float64.
+//   f64 path (x32 == NULL): exact distances straight from the float64 arrays.
+__global__ void __launch_bounds__(NN_THREADS)
+k_nearest(const double *__restrict__ x64, const double *__restrict__ y64,
+          const float *__restrict__ x32, const float *__restrict__ y32, long long stride,
+          const int *__restrict__ n_nodes, const double *__restrict__ targets, int target_stride,
+          float band_abs, int splits, int vec_ok, NNPartial *partial)
+{
+    __shared__ unsigned s_minbits;
+    __shared__ int s_cnt;
+    __shared__ int s_ci[NN_CAND];
+    __shared__ float s_cv[NN_CAND];
+    __shared__ double sv[NN_THREADS / 32], ss[NN_THREADS / 32];
+    __shared__ int si[NN_THREADS / 32];
+    const int q = blockIdx.x / splits, split = blockIdx.x - q * splits;
+    const int n = n_nodes[q];
+    const double tx = targets[(size_t)target_stride * q], ty = targets[(size_t)target_stride * q + 1];
+    // segment bounds, multiples of 4 so that vector loads stay aligned
+    int per = (((n + splits - 1) / splits) + 3) & ~3;
+    int lo = min(n, split * per), hi = min(n, lo + per);
+    const size_t base = (size_t)stride * q;
+    double bd = CUDART_INF, bs = CUDART_INF;
+    int bi = 0x7fffffff;
+    bool exact_scan = (x32 == nullptr);
+
+    if (!exact_scan) {
+        if (threadIdx.x == 0) { s_minbits = 0x7f800000u; s_cnt = 0; }
+        __syncthreads();
+        const float ftx = (float)tx, fty = (float)ty;
+        const float *xs = x32 + base, *ys = y32 + base;
+        volatile unsigned *vmin = &s_minbits;
+        auto visit = [&](float e2, int idx) {
+            float m2 = __uint_as_float(*vmin);
+            if (e2 <= m2 * 1.001f + band_abs) {
+                if (e2 < m2) atomicMin(&s_minbits, __float_as_uint(e2));
+                int pos = atomicAdd(&s_cnt, 1);
+                if (pos < NN_CAND) { s_ci[pos] = idx; s_cv[pos] = e2; }
+            }
+        };
+        int hi4 = lo + ((hi - lo) & ~3);
+        if (vec_ok) {
+            for (int i = lo + threadIdx.x * 4; i < hi4; i += NN_THREADS * 4) {
+                float4 vx = __ldcs(reinterpret_cast<const float4 *>(xs + i));
+                float4 vy = __ldcs(reinterpret_cast<const float4 *>(ys + i));
+                float dx0 = vx.x - ftx, dy0 = vy.x - fty, dx1 = vx.y - ftx, dy1 = vy.y - fty;
+                float dx2 = vx.z - ftx, dy2 = vy.z - fty, dx3 = vx.w - ftx, dy3 = vy.w - fty;
+                float e0 = dx0 * dx0 + dy0 * dy0, e1 = dx1 * dx1 + dy1 * dy1;
+                float e2 = dx2 * dx2 + dy2 * dy2, e3 = dx3 * dx3 + dy3 * dy3;
+                float em = fminf(fminf(e0, e1), fminf(e2, e3));
+                float m2 = __uint_as_float(*vmin);
+                if (em <= m2 * 1.001f + band_abs) {
+                    visit(e0, i); visit(e1, i + 1); visit(e2, i + 2); visit(e3, i + 3);
+                }
+            }
+        } else {
+            hi4 = lo;
+        }
+        for (int j = hi4 + threadIdx.x; j < hi; j += NN_THREADS) {
+            float dx = xs[j] - ftx, dy = ys[j] - fty;
+            visit(dx * dx + dy * dy, j);
+        }
+        __syncthreads();
+        if (s_cnt > NN_CAND) exact_scan = true;      // (block-uniform) queue overflow: rescan exactly
+        else {
+            float m2 = __uint_as_float(s_minbits);
+            float lim = m2 * 1.001f + band_abs;
+            for (int c = threadIdx.x; c < s_cnt; c += NN_THREADS) {
+                if (s_cv[c] <= lim) {
+                    int j = s_ci[c];
+                    double dx = x64[base + j] - tx, dy = y64[base + j] - ty;
+                    double dd = sqrt(fma(dy, dy, dx * dx));            // np.linalg.norm (rrt.py:159)
+                    nn_merge(bd, bi, bs, dd, j, CUDART_INF);
+                }
+            }
+        }
+    }
+    if (exact_scan) {
+        bd = CUDART_INF; bs = CUDART_INF; bi = 0x7fffffff;
+        for (int j = lo + threadIdx.x; j < hi; j += NN_THREADS) {
+            double dx = x64[base + j] - tx, dy = y64[base + j] - ty;
+            double dd = sqrt(fma(dy, dy, dx * dx));
+            nn_merge(bd, bi, bs, dd, j, CUDART_INF);
+        }
+    }
+    nn_block_reduce(bd, bi, bs, sv, ss, si);
+    if (threadIdx.x == 0) {
+        NNPartial p;
+        p.d = bd; p.second = bs; p.idx = bi; p.pad = 0;
+        partial[(size_t)q * splits + split] = p;
+    }
+}
+
+__global__ void k_nearest_final(const NNPartial *__restrict__ partial, int splits, int Q, int *idx,
+                                double *dist, uint8_t *near_tie)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    double d = CUDART_INF, s = CUDART_INF;
+    int i = 0x7fffffff;
+    for (int k = 0; k < splits; k++) {
+        NNPartial p = partial[(size_t)q * splits + k];
+        nn_merge(d, i, s, p.d, p.idx, p.second);
+    }
+    idx[q] = (i == 0x7fffffff) ? 0 : i;
+    dist[q] = d;
+    if (near_tie) {
+        double gap = s - d;
+        near_tie[q] = (gap > 0.0 && gap <= 1e-12 * fabs(d)) ? 1 : 0;
+    }
+}
+
+static int nn_splits(int Q, int max_nodes)
+{
+    int want = (2 * 148 + Q - 1) / Q;                  // fill the machine twice over
+    int cap = (max_nodes + 8191) / 8192;               // at least 8k nodes per CTA
+    int s = want < cap ? want : cap;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes)
+{
+    if (Q <= 0) return 0;
+    return (int64_t)sizeof(NNPartial) * Q * nn_splits(Q, max_nodes);
+}
+
+extern "C" int crlk_nearest(const double *x64, const double *y64, const float *x32, const float *y32,
+                            int64_t stride, const int32_t *n_nodes, int32_t max_nodes,
+                            double coord_bound, const double *targets, int32_t target_stride,
+                            int32_t Q, int32_t *idx, double *dist, uint8_t *near_tie, void *scratch,
+                            void *stream)
+{
+    CRLK_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(x64 && y64 && n_nodes && targets && idx && dist && scratch, "NULL array");
+    CRLK_REQUIRE((x32 == nullptr) == (y32 == nullptr), "x32/y32 must both be given or both NULL");
+    CRLK_REQUIRE(target_stride >= 2 && max_nodes >= 1 && stride >= max_nodes, "shape");
+    CRLK_REQUIRE(x32 == nullptr || coord_bound > 0, "coord_bound must be > 0 with the float32 scan");
+    // guard band of the float32 screen: |d_f - d| <= delta = 8 * bound * 2^-24
+    double delta = 8.0 * coord_bound * 5.9604644775390625e-08;
+    float band_abs = (float)(1.7e7 * delta * delta);
+    int splits = nn_splits(Q, max_nodes);
+    int vec_ok = (x32 != nullptr) && (stride % 4 == 0) && (((uintptr_t)x32 & 15) == 0) &&
+                 (((uintptr_t)y32 & 15) == 0);
+    CRLK_REQUIRE((long long)Q * splits < 2147483647LL, "grid too large");
+    k_nearest<<<Q * splits, NN_THREADS, 0, (cudaStream_t)stream>>>(x64, y64, x32, y32, (long long)stride,
+                                                            n_nodes, targets, target_stride,
+                                                            band_abs, splits, vec_ok,
+                                                            (NNPartial *)scratch);
+    CRLK_LAUNCH_CHECK();
+    k_nearest_final<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>((NNPartial *)scratch, splits,
+                                                                       Q, idx, dist, near_tie);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}

@@ -1,0 +1,535 @@
+// libcrlk.so -- learned steering: actor MLP, estimator/classifier CNN and the
+// RL extend loop (float32; FMA contraction allowed, tolerance-based parity).
+#include <math_constants.h>
+
+#include "crlk_device.cuh"
+
+// ---------------------------------------------------------------- policy MLP
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+extern "C" int crlk_policy_create(int32_t n_layers, const int32_t *dims,
+                                  const float *const *weights_host, const float *const *biases_host,
+                                  const float *low, const float *high, CrlkPolicy **out)
+{
+    CRLK_REQUIRE(out && dims && weights_host && biases_host && low && high, "NULL argument");
+    CRLK_REQUIRE(n_layers >= 2 && n_layers <= 8, "n_layers must be in [2, 8]");
+    CRLK_REQUIRE(dims[n_layers] == 2, "the actor must output 2 actions (v, omega)");
+    int rc = crlk_require_device();
+    if (rc) return rc;
+    CrlkPolicy *p = new CrlkPolicy();
+    memset(p, 0, sizeof *p);
+    CRLK_CUDA(cudaGetDevice(&p->device));
+    p->n_layers = n_layers;
+    p->max_dim = 0;
+    for (int i = 0; i <= n_layers; i++) {
+        CRLK_REQUIRE(dims[i] >= 1, "layer width < 1");
+        p->dims[i] = dims[i];
+    }
+    for (int i = 0; i < n_layers; i++) {
+        int K = dims[i], N = dims[i + 1];
+        int kp = round_up(K, 16);
+        p->kpad[i] = kp;
+        if (i > 0 && kp > p->max_dim) p->max_dim = kp;
+        float *hw = (float *)calloc((size_t)N * kp, sizeof(float));
+        for (int n = 0; n < N; n++) memcpy(hw + (size_t)n * kp, weights_host[i] + (size_t)n * K, sizeof(float) * K);
+        CRLK_CUDA(cudaMalloc(&p->d_w[i], sizeof(float) * (size_t)N * kp));
+        CRLK_CUDA(cudaMemcpy(p->d_w[i], hw, sizeof(float) * (size_t)N * kp, cudaMemcpyHostToDevice));
+        free(hw);
+        CRLK_CUDA(cudaMalloc(&p->d_b[i], sizeof(float) * N));
+        CRLK_CUDA(cudaMemcpy(p->d_b[i], biases_host[i], sizeof(float) * N, cudaMemcpyHostToDevice));
+    }
+    for (int k = 0; k < 2; k++) {
+        // net.py:134-138 in float32
+        p->low[k] = low[k]; p->high[k] = high[k];
+        p->bias[k] = (low[k] + high[k]) / 2.0f;
+        p->scale[k] = (high[k] - low[k]) / 2.0f;
+    }
+    *out = p;
+    return CRLK_OK;
+}
+
+extern "C" int crlk_policy_destroy(CrlkPolicy *p)
+{
+    if (!p) return CRLK_OK;
+    for (int i = 0; i < p->n_layers; i++) {
+        if (p->d_w[i]) cudaFree(p->d_w[i]);
+        if (p->d_b[i]) cudaFree(p->d_b[i]);
+    }
+    delete p;
+    return CRLK_OK;
+}
+
+extern "C" int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B)
+{
+    if (!p || B <= 0) return 0;
+    return (int64_t)sizeof(float) * 2 * (int64_t)round_up(B, 64) * p->max_dim + 256;
+}
+
+// C[B, N] = relu(A[B, lda] . W[N, K]^T + b), K % 16 == 0, rows of A/W 16-byte aligned.
+// 64 x 64 output tile, 16-deep k slices, 4 x 4 register block per thread.
+#define GM_BM 64
+#define GM_BN 64
+#define GM_BK 16
+__global__ void __launch_bounds__(256)
+k_linear_relu(const float *__restrict__ A, int lda, const float *__restrict__ W, int K,
+              const float *__restrict__ bias, float *__restrict__ Cout, int ldc, int B, int N,
+              const int *__restrict__ row_active)
+{
+    __shared__ float As[GM_BK][GM_BM + 4];
+    __shared__ float Ws[GM_BK][GM_BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    const int tr = tid / 16, tc = tid % 16;        // 16 x 16 threads, each 4 x 4 outputs
+    const int lr = tid / 4, lk = (tid % 4) * 4;    // loader: row lr, k offset lk
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += GM_BK) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
+        if (m0 + lr < B) a = *reinterpret_cast<const float4 *>(A + (size_t)(m0 + lr) * lda + k0 + lk);
+        if (n0 + lr < N) w = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(n0 + lr) * K + k0 + lk));
+        As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+        Ws[lk + 0][lr] = w.x; Ws[lk + 1][lr] = w.y; Ws[lk + 2][lr] = w.z; Ws[lk + 3][lr] = w.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GM_BK; k++) {
+            float4 av = *reinterpret_cast<const float4 *>(&As[k][tr * 4]);
+            float4 wv = *reinterpret_cast<const float4 *>(&Ws[k][tc * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int m = m0 + tr * 4 + i;
+        if (m >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int n = n0 + tc * 4 + j;
+            if (n < N) Cout[(size_t)m * ldc + n] = fmaxf(acc[i][j] + __ldg(&bias[n]), 0.f);
+        }
+    }
+}
+
+struct HeadP { float low[2], high[2], scale[2], bias[2]; };
+
+// Last layer (K -> 2) + tanh + exploration noise + scale/bias + clamp
+// (net.py:145-153, ddpg.py:126-130).  One warp per row.
+__global__ void __launch_bounds__(256)
+k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W, int K,
+              const float *__restrict__ bias, const float *__restrict__ noise, long long noise_stride,
+              float eps, HeadP hp, int B, float *__restrict__ act)
+{
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float *a = A + (size_t)row * lda;
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float x = a[k];
+        s0 = fmaf(x, __ldg(&W[k]), s0);
+        s1 = fmaf(x, __ldg(&W[K + k]), s1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane < 2) {
+        float z = (lane == 0 ? s0 : s1) + __ldg(&bias[lane]);
+        z = tanhf(z);
+        if (noise) z = z + noise[(size_t)row * noise_stride + lane] * eps;
+        z = z * hp.scale[lane] + hp.bias[lane];
+        z = fminf(fmaxf(z, hp.low[lane]), hp.high[lane]);
+        act[2 * (size_t)row + lane] = z;
+    }
+}
+
+static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs, const float *noise,
+                               long long noise_stride, float eps, int B, float *act, void *workspace,
+                               cudaStream_t st)
+{
+    const int L = p->n_layers;
+    float *buf[2];
+    size_t half = (size_t)round_up(B, 64) * p->max_dim;
+    buf[0] = (float *)workspace;
+    buf[1] = buf[0] + half;
+    const float *in = obs;
+    int ld_in = ld_obs;
+    for (int i = 0; i < L - 1; i++) {
+        int N = p->dims[i + 1];
+        int ldc = p->kpad[i + 1];
+        float *outb = buf[i & 1];
+        dim3 grid((N + GM_BN - 1) / GM_BN, (B + GM_BM - 1) / GM_BM);
+        k_linear_relu<<<grid, 256, 0, st>>>(in, ld_in, p->d_w[i], p->kpad[i], p->d_b[i], outb, ldc, B, N,
+                                           nullptr);
+        CRLK_LAUNCH_CHECK();
+        in = outb;
+        ld_in = ldc;
+    }
+    HeadP hp;
+    for (int k = 0; k < 2; k++) {
+        hp.low[k] = p->low[k]; hp.high[k] = p->high[k]; hp.scale[k] = p->scale[k]; hp.bias[k] = p->bias[k];
+    }
+    k_policy_head<<<(B + 7) / 8, 256, 0, st>>>(in, ld_in, p->d_w[L - 1], p->kpad[L - 1], p->d_b[L - 1],
+                                              noise, noise_stride, eps, hp, B, act);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+extern "C" int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_t ld_obs,
+                                   const float *noise, float eps, int32_t B, float *act,
+                                   void *workspace, void *stream)
+{
+    CRLK_REQUIRE(p != nullptr, "policy is NULL");
+    CRLK_REQUIRE(B >= 0, "B < 0");
+    if (B == 0) return CRLK_OK;
+    CRLK_REQUIRE(obs && act && workspace, "NULL array");
+    CRLK_REQUIRE(ld_obs >= p->kpad[0] && ld_obs % 4 == 0,
+                 "ld_obs must be >= the input width rounded up to 16, zero padded");
+    CRLK_REQUIRE(((uintptr_t)obs & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "16-byte alignment");
+    return policy_forward_impl(p, obs, ld_obs, noise, 2, eps, B, act, workspace, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------- estimator CNNs (R11)
+
+#define CNN_PARAMS 24452
+#define CNN_THREADS 128
+// packed parameter offsets of one net
+#define O_W1 0
+#define O_B1 72
+#define O_W2 80
+#define O_B2 1232
+#define O_W3 1248
+#define O_B3 5856
+#define O_W4 5888
+#define O_B4 24320
+#define O_WL 24384
+#define O_BL 24451
+
+extern "C" int crlk_estimator_create(const float *const *est_params_host,
+                                     const float *const *cls_params_host, CrlkEstimator **out)
+{
+    CRLK_REQUIRE(est_params_host && cls_params_host && out, "NULL argument");
+    int rc = crlk_require_device();
+    if (rc) return rc;
+    static const int sizes[10] = {72, 8, 1152, 16, 4608, 32, 18432, 64, 67, 1};
+    float *h = (float *)malloc(sizeof(float) * 2 * CNN_PARAMS);
+    for (int net = 0; net < 2; net++) {
+        const float *const *src = net ? cls_params_host : est_params_host;
+        size_t off = (size_t)net * CNN_PARAMS;
+        for (int i = 0; i < 10; i++) {
+            if (!src[i]) { free(h); crlk_set_error("invalid argument: NULL parameter tensor"); return CRLK_E_INVALID; }
+            memcpy(h + off, src[i], sizeof(float) * sizes[i]);
+            off += sizes[i];
+        }
+    }
+    CrlkEstimator *e = new CrlkEstimator();
+    CRLK_CUDA(cudaGetDevice(&e->device));
+    CRLK_CUDA(cudaMalloc(&e->d_params, sizeof(float) * 2 * CNN_PARAMS));
+    CRLK_CUDA(cudaMemcpy(e->d_params, h, sizeof(float) * 2 * CNN_PARAMS, cudaMemcpyHostToDevice));
+    free(h);
+    *out = e;
+    return CRLK_OK;
+}
+
+extern "C" int crlk_estimator_destroy(CrlkEstimator *e)
+{
+    if (!e) return CRLK_OK;
+    if (e->d_params) cudaFree(e->d_params);
+    delete e;
+    return CRLK_OK;
+}
+
+// conv3x3(pad 1) + ReLU + maxpool2 from in[CI][H][H] to out[CO][H/2][H/2] (shared memory).
+template <int CI, int CO, int H>
+__device__ __forceinline__ void conv_relu_pool(const float *__restrict__ w, const float *__restrict__ b,
+                                               const float *in, float *out)
+{
+    constexpr int P = H / 2;
+    for (int o = threadIdx.x; o < CO * P * P; o += CNN_THREADS) {
+        int co = o / (P * P), r = o - co * P * P, py = r / P, px = r - py * P;
+        float best = -CUDART_INF_F;
+#pragma unroll
+        for (int sy = 0; sy < 2; sy++)
+#pragma unroll
+            for (int sx = 0; sx < 2; sx++) {
+                int y = 2 * py + sy, x = 2 * px + sx;
+                float acc = __ldg(&b[co]);
+                for (int ci = 0; ci < CI; ci++) {
+                    const float *wp = w + (co * CI + ci) * 9;
+                    const float *ip = in + ci * H * H;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++) {
+                        int yy = y + ky - 1;
+                        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+                            int xx = x + kx - 1;
+                            if (xx < 0 || xx >= H) continue;
+                            acc = fmaf(ip[yy * H + xx], __ldg(&wp[ky * 3 + kx]), acc);
+                        }
+                    }
+                }
+                best = fmaxf(best, acc);
+            }
+        out[o] = fmaxf(best, 0.f);
+    }
+}
+
+// One CTA per (sample, net): estimator/network.py:39-69 and :97-127.
+__global__ void __launch_bounds__(CNN_THREADS)
+k_estimator(const float *__restrict__ params, const float *__restrict__ obs, int ld_obs, int B,
+            float *__restrict__ est, float *__restrict__ prob)
+{
+    __shared__ float s_in[27 * 27];
+    __shared__ float s_a[8 * 13 * 13];
+    __shared__ float s_b[16 * 6 * 6];
+    __shared__ float s_c[32 * 3 * 3];
+    __shared__ float s_d[64];
+    const int b = blockIdx.x, net = blockIdx.y;
+    if (b >= B) return;
+    const float *P = params + (size_t)net * CNN_PARAMS;
+    const float *o = obs + (size_t)b * ld_obs;
+    for (int i = threadIdx.x; i < 729; i += CNN_THREADS) s_in[i] = o[4 + i];
+    __syncthreads();
+    conv_relu_pool<1, 8, 27>(P + O_W1, P + O_B1, s_in, s_a);
+    __syncthreads();
+    conv_relu_pool<8, 16, 13>(P + O_W2, P + O_B2, s_a, s_b);
+    __syncthreads();
+    conv_relu_pool<16, 32, 6>(P + O_W3, P + O_B3, s_b, s_c);
+    __syncthreads();
+    // conv4 + ReLU + global average pool over 3 x 3
+    for (int co = threadIdx.x; co < 64; co += CNN_THREADS) {
+        float sum = 0.f;
+        for (int y = 0; y < 3; y++)
+            for (int x = 0; x < 3; x++) {
+                float acc = __ldg(&P[O_B4 + co]);
+                for (int ci = 0; ci < 32; ci++) {
+                    const float *wp = P + O_W4 + (co * 32 + ci) * 9;
+                    const float *ip = s_c + ci * 9;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++) {
+                        int yy = y + ky - 1;
+                        if (yy < 0 || yy >= 3) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+                            int xx = x + kx - 1;
+                            if (xx < 0 || xx >= 3) continue;
+                            acc = fmaf(ip[yy * 3 + xx], __ldg(&wp[ky * 3 + kx]), acc);
+                        }
+                    }
+                }
+                sum += fmaxf(acc, 0.f);
+            }
+        s_d[co] = sum / 9.0f;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int lane = threadIdx.x;
+        float acc = 0.f;
+        for (int k = lane; k < 64; k += 32) acc = fmaf(s_d[k], __ldg(&P[O_WL + k]), acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            // ext = [||goal_body||, v, omega] (rrt_rl_estimator.py:59-62), float32
+            float gx = o[0], gy = o[1];
+            float e0 = sqrtf(gx * gx + gy * gy);
+            acc = fmaf(e0, __ldg(&P[O_WL + 64]), acc);
+            acc = fmaf(o[2], __ldg(&P[O_WL + 65]), acc);
+            acc = fmaf(o[3], __ldg(&P[O_WL + 66]), acc);
+            acc += __ldg(&P[O_BL]);
+            if (net == 0) est[b] = acc;
+            else prob[b] = 1.0f / (1.0f + expf(-acc));
+        }
+    }
+}
+
+extern "C" int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, int32_t ld_obs,
+                                      int32_t B, float *est, float *prob, void *stream)
+{
+    CRLK_REQUIRE(e != nullptr, "estimator is NULL");
+    CRLK_REQUIRE(B >= 0, "B < 0");
+    if (B == 0) return CRLK_OK;
+    CRLK_REQUIRE(obs && est && prob, "NULL array");
+    CRLK_REQUIRE(ld_obs >= 733, "ld_obs < 733");
+    dim3 grid(B, 2);
+    k_estimator<<<grid, CNN_THREADS, 0, (cudaStream_t)stream>>>(e->d_params, obs, ld_obs, B, est, prob);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------------ RL extend (rrt_rl.py:22-63)
+
+#define WQ_CAP_RL 64
+
+struct RlWs {
+    double *state;     // [Q][5]
+    int *done;         // [Q]
+    int *nn;           // [Q]
+    float *obs;        // [Q][736]
+    float *act;        // [Q][2]
+    void *mlp;         // policy workspace
+};
+
+static size_t rl_carve(const CrlkPolicy *p, int Q, unsigned char *base, RlWs *w)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_state = take(sizeof(double) * 5 * Q);
+    size_t o_done = take(sizeof(int) * Q);
+    size_t o_nn = take(sizeof(int) * Q);
+    size_t o_obs = take(sizeof(float) * 736 * (size_t)Q);
+    size_t o_act = take(sizeof(float) * 2 * Q);
+    size_t o_mlp = take((size_t)crlk_policy_workspace_bytes(p, Q));
+    if (w) {
+        w->state = (double *)(base + o_state); w->done = (int *)(base + o_done);
+        w->nn = (int *)(base + o_nn); w->obs = (float *)(base + o_obs);
+        w->act = (float *)(base + o_act); w->mlp = base + o_mlp;
+    }
+    return off;
+}
+
+extern "C" int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q)
+{
+    if (!p || Q <= 0) return 0;
+    return (int64_t)rl_carve(p, Q, nullptr, nullptr);
+}
+
+__global__ void k_rl_init(const double *__restrict__ from_states, const uint8_t *__restrict__ active,
+                          int Q, double *state, int *done, int *nn, int *n_steps, int *status,
+                          int *n_nodes, uint8_t *flags)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    for (int c = 0; c < 5; c++) state[5 * (size_t)q + c] = from_states[5 * (size_t)q + c];
+    done[q] = (active && !active[q]) ? 1 : 0;
+    nn[q] = 0;
+    n_steps[q] = 0; status[q] = CRLK_EXT_TIMEOUT; n_nodes[q] = 0;
+    if (flags) flags[q] = 0;
+}
+
+// One warp per query: apply the action (differential_gym.py:139), then the
+// planner's checks (rrt_rl.py:48-57).
+__global__ void __launch_bounds__(256)
+k_rl_step(EnvP e, ExtP x, const float4 *__restrict__ rects, int M, const double *__restrict__ targets,
+          const float *__restrict__ act, int k, int Q, double *state, int *done, int *nn, double *path,
+          int *n_steps, int *status, int *node_step, int *n_nodes, float *actions, uint8_t *flags)
+{
+    __shared__ int s_queue[8][WQ_CAP_RL];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int q = blockIdx.x * 8 + warp;
+    if (q >= Q) return;
+    if (done[q]) return;
+    const int per = x.n_max_extend / x.n_tree + 1;
+    double s[5];
+    for (int c = 0; c < 5; c++) s[c] = state[5 * (size_t)q + c];
+    // the float32 action promoted to float64 (differential_env.py:67-70)
+    double cv = (double)act[2 * (size_t)q], cw = (double)act[2 * (size_t)q + 1];
+    motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
+    // collision test (flag only)
+    RobotPose g;
+    robot_pose_setup(e, s[0], s[1], s[2], g);
+    float px = (float)s[0], py = (float)s[1];
+    float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
+    float thr2 = thr * thr;
+    int *queue = s_queue[warp];
+    bool coll = false, definite = false, marginal = false;
+    int count = 0;
+    for (int base = 0; base < M; base += 32) {
+        int o = base + lane;
+        bool keep = false;
+        if (o < M) keep = aabb_center_d2(__ldg(&rects[o]), px, py) <= thr2;
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (mask) {
+            int pos = count + __popc(mask & ((1u << lane) - 1u));
+            if (keep) queue[pos] = o;
+            count += __popc(mask);
+            __syncwarp();
+            if (count > WQ_CAP_RL - 32) {
+                for (int b0 = 0; b0 < count; b0 += 32)
+                    if (b0 + lane < count) {
+                        bool d, m;
+                        coll |= dis2obs_exact(e, g, __ldg(&rects[queue[b0 + lane]]), d, m) < 0.0;
+                        definite |= d; marginal |= m;
+                    }
+                count = 0;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    for (int b0 = 0; b0 < count; b0 += 32)
+        if (b0 + lane < count) {
+            bool d, m;
+            coll |= dis2obs_exact(e, g, __ldg(&rects[queue[b0 + lane]]), d, m) < 0.0;
+            definite |= d; marginal |= m;
+        }
+    coll = __any_sync(0xffffffffu, coll);
+    definite = __any_sync(0xffffffffu, definite);
+    marginal = __any_sync(0xffffffffu, marginal);
+    if (lane != 0) return;
+    for (int c = 0; c < 5; c++) {
+        state[5 * (size_t)q + c] = s[c];
+        path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
+    }
+    if (actions) {
+        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2] = act[2 * (size_t)q];
+        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2 + 1] = act[2 * (size_t)q + 1];
+    }
+    n_steps[q] = k;
+    if (flags && marginal && !definite) flags[q] |= 1;
+    const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
+    double ddx = s[0] - gx, ddy = s[1] - gy;
+    double dist = sqrt(fma(ddy, ddy, ddx * ddx));
+    if (coll) {
+        status[q] = CRLK_EXT_COLLISION; done[q] = 1;
+    } else if (dist <= x.reach_radius) {
+        node_step[(size_t)q * per + nn[q]] = k;
+        nn[q] += 1; n_nodes[q] = nn[q];
+        status[q] = CRLK_EXT_REACHED; done[q] = 1;
+    } else if (k % x.n_tree == 0) {
+        node_step[(size_t)q * per + nn[q]] = k;
+        nn[q] += 1; n_nodes[q] = nn[q];
+    }
+}
+
+extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
+                              const double *from_states, const double *targets, int32_t Q,
+                              const float *noise, float eps, double *path, int32_t *n_steps,
+                              int32_t *status, int32_t *node_step, int32_t *n_nodes, float *actions,
+                              uint8_t *flags, const uint8_t *active, void *workspace, void *stream)
+{
+    CRLK_REQUIRE(env && p, "env/policy is NULL");
+    CRLK_REQUIRE(p->dims[0] == 733, "the actor must take the 733-vector observation");
+    ExtP x;
+    int rc = crlk_make_ext(env, ext, &x);
+    if (rc) return rc;
+    CRLK_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(from_states && targets && path && n_steps && status && node_step && n_nodes && workspace,
+                 "NULL array");
+    CRLK_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    RlWs w;
+    rl_carve(p, Q, (unsigned char *)workspace, &w);
+    k_rl_init<<<(Q + 127) / 128, 128, 0, st>>>(from_states, active, Q, w.state, w.done, w.nn, n_steps,
+                                              status, n_nodes, flags);
+    CRLK_LAUNCH_CHECK();
+    for (int k = 1; k <= x.n_max_extend; k++) {
+        // observation of the current state (rrt_rl.py:34 / differential_gym.py:141)
+        rc = crlk_local_obs(env, w.state, targets, 5, Q, nullptr, w.obs, 736, nullptr, stream);
+        if (rc) return rc;
+        // action = policy(obs) (rrt_rl.py:41)
+        rc = policy_forward_impl(p, w.obs, 736, noise ? noise + (size_t)(k - 1) * 2 : nullptr,
+                                 (long long)x.n_max_extend * 2, eps, Q, w.act, w.mlp, st);
+        if (rc) return rc;
+        k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->d_rects, env->M, targets, w.act, k, Q,
+                                              w.state, w.done, w.nn, path, n_steps, status, node_step,
+                                              n_nodes, actions, flags);
+        CRLK_LAUNCH_CHECK();
+    }
+    return CRLK_OK;
+}

@@ -147,12 +147,14 @@ int crlk_dwa_max_rollouts(const CrlkEnv *env, const CrlkDwaParams *dwa);
  *   x64, y64   dev f64   exact coordinates (rescoring)
  *   x32, y32   dev f32   the same coordinates rounded to float32 (the scanned
  *                        copy: 8 bytes per node); nullable => scan f64 directly
+ *   coord_bound upper bound of |coordinate| over the trees and targets (e.g. the
+ *              env bounds); sizes the float32 screening band.  Ignored if x32 is NULL.
  *   targets    dev f64[Q x target_stride]
  *   idx        dev i32[Q]; dist dev f64[Q]; near_tie dev u8[Q] (nullable)
  *   scratch    dev bytes, crlk_nearest_scratch_bytes(Q, max_nodes) of them. */
 int crlk_nearest(const double *x64, const double *y64, const float *x32, const float *y32,
-                 int64_t stride, const int32_t *n_nodes, int32_t max_nodes, const double *targets,
-                 int32_t target_stride, int32_t Q, int32_t *idx, double *dist, uint8_t *near_tie,
+                 int64_t stride, const int32_t *n_nodes, int32_t max_nodes, double coord_bound,
+                 const double *targets, int32_t target_stride, int32_t Q, int32_t *idx, double *dist, uint8_t *near_tie,
                  void *scratch, void *stream);
 int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes);
 

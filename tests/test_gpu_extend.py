@@ -1,0 +1,123 @@
+"""Fused extend kernel and the RRT drop-in class vs goldens / oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from gpu_util import fixture_map, make_envs, np_
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _extend(env, froms, targets, **dwa_kw):
+    from crl_kino_b200 import ops
+    from crl_kino_b200.policy.dwa import DWA
+    d = DWA(env)
+    d.set_dwa(**(dwa_kw or dict(dt=0.2, v_res=0.02)))
+    return ops.extend_dwa(env.handle, d.params(), ops.extend_params(), froms, targets, want_ctrl=True)
+
+
+def _compare(out, ref, what):
+    fl = np_(out["flags"])
+    clean = fl == 0
+    assert clean.mean() > 0.9, f"{what}: too many flagged extensions"
+    for key in ("n_steps", "status", "n_nodes"):
+        assert np.array_equal(np_(out[key])[clean], np.asarray(ref[key])[clean]), (what, key)
+    path, rpath = np_(out["path"]), ref["path"]
+    for q in np.where(clean)[0]:
+        n = ref["n_steps"][q]
+        np.testing.assert_allclose(path[q, :n], rpath[q, :n], rtol=1e-9, atol=1e-11)
+        k = ref["n_nodes"][q]
+        assert np.array_equal(np_(out["node_step"])[q, :k], np.asarray(ref["node_step"])[q, :k])
+        if ref.get("ctrl_idx") is not None:
+            assert np.array_equal(np_(out["ctrl_idx"])[q, :n], ref["ctrl_idx"][q, :n])
+
+
+@pytest.mark.parametrize("mname", ("test_env1", "test_env2"))
+def test_steer_dwa_golden(mname):
+    g = golden("steer_dwa")
+    env, o = make_envs(fixture_map(mname))
+    out = _extend(env, g[mname + "_from"], g[mname + "_target"])
+    fl = np_(out["flags"])
+    clean = fl == 0
+    assert np.array_equal(np_(out["n_steps"])[clean], g[mname + "_nsteps"][clean])
+    assert np.array_equal(np_(out["status"])[clean], g[mname + "_status"][clean])
+    assert np.array_equal(np_(out["n_nodes"])[clean], g[mname + "_nnodes"][clean])
+    for q in np.where(clean)[0]:
+        n = g[mname + "_nsteps"][q]
+        np.testing.assert_allclose(np_(out["path"])[q, :n], g[mname + "_path"][q, :n], rtol=1e-9, atol=1e-11)
+
+
+def test_extend_vs_oracle_many():
+    from crl_kino_b200.workloads import free_states, random_states
+    env, o = make_envs(fixture_map("test_env1"))
+    rng = np.random.default_rng(8)
+    froms = free_states(lambda c: o.valid_state_batch(c)[1], rng, 300, 0.1, moving=True)
+    targets = random_states(rng, 300)
+    out = _extend(env, froms, targets)
+    ref = orc.Dwa(o, dt=0.2, v_res=0.02).extend_batch(froms, targets, want_ctrl=True)
+    _compare(out, ref, "test_env1")
+    assert set(np.unique(ref["status"])) == {0, 1, 2}
+
+
+def test_extend_dense_map_vs_oracle():
+    """cfg4 shape: 10,004 obstacles, ~4096-rollout windows."""
+    from crl_kino_b200.workloads import DENSE_DWA, dense_map, query_pairs
+    rects = dense_map()
+    env, o = make_envs(rects)
+    s, g = query_pairs(lambda c: o.valid_state_batch(c)[1], 24)
+    out = _extend(env, s, g, **DENSE_DWA)
+    ref = orc.Dwa(o, **DENSE_DWA).extend_batch(s, g, want_ctrl=True)
+    _compare(out, ref, "dense")
+
+
+def test_extend_inactive_and_empty():
+    import torch
+    from crl_kino_b200 import ops
+    from crl_kino_b200.policy.dwa import DWA
+    env, o = make_envs(fixture_map("test_env1"))
+    d = DWA(env)
+    d.set_dwa(dt=0.2, v_res=0.02)
+    s = np.array([[-5, -15, 0, 0, 0.0]] * 3)
+    t = np.array([[10, 10, 0, 0, 0.0]] * 3)
+    act = torch.tensor([1, 0, 1], dtype=torch.uint8, device="cuda")
+    out = ops.extend_dwa(env.handle, d.params(), ops.extend_params(), s, t, active=act)
+    ns = np_(out["n_steps"])
+    assert ns[1] == 0 and ns[0] == ns[2] > 0 and np_(out["n_nodes"])[1] == 0
+    out = ops.extend_dwa(env.handle, d.params(), ops.extend_params(), np.zeros((0, 5)), np.zeros((0, 5)))
+    assert out["n_steps"].numel() == 0
+
+
+@pytest.mark.parametrize("run,seed", ((0, 0), (2, 3)))
+def test_rrt_class_reproduces_reference_run(run, seed):
+    """The drop-in RRT with the reference's own RNG seeds rebuilds the reference's tree."""
+    from crl_kino_b200.planner.rrt import RRT
+    g = golden("plan_dwa")
+    env, _ = make_envs(fixture_map(str(g[f"run{run}_map"])))
+    p = RRT(env, max_iter=int(g[f"run{run}_max_iter"]))
+    p.verbose = False
+    p.set_start_and_goal(g[f"run{run}_start"], g[f"run{run}_goal"])
+    random.seed(seed)
+    np.random.seed(seed)
+    path = p.planning()
+    index = {id(n): i for i, n in enumerate(p.node_list)}
+    parents = np.array([-1 if n.parent is None else index[id(n.parent)] for n in p.node_list])
+    states = np.array([n.state for n in p.node_list])
+    assert p.n_control_steps == int(g[f"run{run}_ctrl_steps"])
+    assert np.array_equal(parents, g[f"run{run}_parents"])
+    assert np.array_equal(np.array([len(n.path) for n in p.node_list]), g[f"run{run}_plen"])
+    np.testing.assert_allclose(states, g[f"run{run}_node_states"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(np.array(path), g[f"run{run}_path"], rtol=1e-9, atol=1e-11)
+    assert p.reach_exactly == bool(g[f"run{run}_reach"])
+
+
+def test_rrt_api_errors():
+    from crl_kino_b200.planner.rrt import RRT
+    env, _ = make_envs(fixture_map("test_env1"))
+    p = RRT(env)
+    with pytest.raises(ValueError):
+        p.planning()
+    with pytest.raises(AssertionError):
+        p.set_start_and_goal(np.array([0, -21.0, 0, 0, 0]), np.array([10, 10, 0, 0, 0.0]))

@@ -1,0 +1,127 @@
+"""Actor MLP, estimator CNNs and RL steering vs goldens / oracle."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from gpu_util import fixture_map, make_envs, np_
+from oracle import oracle as orc
+from test_oracle_golden import _seeded_actor
+
+pytestmark = pytest.mark.gpu
+
+
+def _policy(seed=0):
+    from crl_kino_b200.env import DifferentialDriveGym
+    from crl_kino_b200.policy.rl_policy import load_policy
+    pol = load_policy(DifferentialDriveGym(), [1024, 512, 512, 512], None, seed=seed)
+    return pol
+
+
+def _estimators():
+    from crl_kino_b200.estimator import load_estimator
+    w = golden("estimator_weights")
+    est = {k[4:]: w[k] for k in w.files if k.startswith("est.")}
+    cls = {k[4:]: w[k] for k in w.files if k.startswith("cls.")}
+    return load_estimator(est, cls), est, cls
+
+
+def test_policy_forward_golden():
+    from crl_kino_b200.policy.rl_policy import policy_forward
+    g = golden("policy")
+    pol = _policy(int(g["seed"]))
+    Ws, bs = _seeded_actor(int(g["seed"]))
+    assert all(np.array_equal(a, b) for a, b in zip(pol.actor.weights, Ws))
+    a0 = policy_forward(pol, g["obs"], eps=0.0)
+    np.testing.assert_allclose(a0, g["act_eps0"], rtol=1e-4, atol=1e-5)
+    a1 = policy_forward(pol, g["obs"], eps=0.05, noise=g["noise"])
+    np.testing.assert_allclose(a1, g["act_eps005"], rtol=1e-4, atol=1e-5)
+    one = policy_forward(pol, g["obs"][7])
+    assert one.shape == (1, 2)
+    np.testing.assert_allclose(one[0], g["act_eps0"][7], rtol=1e-4, atol=1e-5)
+
+
+def test_policy_forward_batches_vs_oracle():
+    from crl_kino_b200.policy.rl_policy import policy_forward
+    pol = _policy(3)
+    rng = np.random.default_rng(0)
+    for B in (1, 63, 64, 65, 1000):
+        obs = np.concatenate([rng.normal(0, 5, (B, 4)), (rng.uniform(0, 1, (B, 729)) > 0.3).astype(float)], 1)
+        noise = rng.normal(0, 1, (B, 2)).astype(np.float32)
+        got = policy_forward(pol, obs, eps=0.05, noise=noise)
+        ref = orc.actor_forward(pol.actor.weights, pol.actor.biases, obs, noise, 0.05)
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_estimator_golden():
+    from crl_kino_b200 import ops
+    g = golden("estimator")
+    (est, cls), esd, csd = _estimators()
+    obs32 = ops.pad_obs(g["obs"])
+    np.testing.assert_allclose(np_(est.forward_obs(obs32)), g["est"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(np_(cls.forward_obs(obs32)), g["cls"], rtol=1e-4, atol=1e-5)
+    sp, ext = orc.estimator_inputs(g["obs"])
+    np.testing.assert_allclose(np_(est(sp, ext))[:, 0], g["est"], rtol=1e-4, atol=1e-5)   # reference call form
+
+
+def test_estimator_choose_parent_golden():
+    from crl_kino_b200.planner.rrt_rl_estimator import RRT_RL_Estimator
+    g = golden("estimator")
+    (est, cls), _, _ = _estimators()
+    env, _ = make_envs(fixture_map("test_env2"))
+    p = RRT_RL_Estimator(env, _policy(0), est, cls)
+    for k in range(3):
+        nodes = [p.Node(s) for s in g[f"cp{k}_nodes"]]
+        for t, i, c in zip(g[f"cp{k}_targets"], g[f"cp{k}_idx"], g[f"cp{k}_cost"]):
+            gi, gc = p.choose_parent(nodes, p.Node(t))
+            assert gi == i
+            assert gc == pytest.approx(c, rel=1e-4)
+
+
+@pytest.mark.parametrize("tag,eps", (("eps0", 0.0), ("eps005", 0.05)))
+def test_steer_rl_golden(tag, eps):
+    """RRT_RL.steer: closed loop with the float32 policy; states to 1e-4, flags exact
+    unless the kernel reported a near-boundary decision."""
+    from crl_kino_b200 import ops
+    g = golden("steer_rl")
+    env, _ = make_envs(fixture_map("test_env1"))
+    pol = _policy(int(g["seed"]))
+    out = ops.extend_rl(env.handle, pol.actor.handle, ops.extend_params(), g[tag + "_from"], g[tag + "_target"],
+                        g[tag + "_noise"] if eps else None, eps, want_actions=True)
+    fl = np_(out["flags"])
+    ns = np_(out["n_steps"])
+    for q in range(len(ns)):
+        n_ref = int(g[tag + "_nsteps"][q])
+        n = min(n_ref, ns[q])
+        np.testing.assert_allclose(np_(out["actions"])[q, :n], g[tag + "_act"][q, :n], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(np_(out["path"])[q, :n], g[tag + "_path"][q, :n], rtol=1e-4, atol=1e-4)
+        if fl[q] == 0:
+            assert ns[q] == n_ref
+            assert np_(out["status"])[q] == g[tag + "_status"][q]
+            assert np_(out["n_nodes"])[q] == g[tag + "_nnodes"][q]
+
+
+def test_extend_rl_vs_oracle_teacher_forced():
+    """Per-step parity with teacher forcing: feed the kernel's own actions to the oracle dynamics."""
+    from crl_kino_b200 import ops
+    from crl_kino_b200.workloads import free_states, random_states
+    env, o = make_envs(fixture_map("test_env2"))
+    pol = _policy(1)
+    rng = np.random.default_rng(2)
+    froms = free_states(lambda c: o.valid_state_batch(c)[1], rng, 40, 0.5)
+    targets = random_states(rng, 40)
+    out = ops.extend_rl(env.handle, pol.actor.handle, ops.extend_params(), froms, targets, None, 0.0,
+                        want_actions=True)
+    ns, acts, path = np_(out["n_steps"]), np_(out["actions"]), np_(out["path"])
+    for q in range(40):
+        st = froms[q].copy()
+        for k in range(ns[q]):
+            obs = o.local_obs(st, targets[q])
+            a = orc.actor_forward(pol.actor.weights, pol.actor.biases, obs)[0]
+            np.testing.assert_allclose(acts[q, k], a, rtol=2e-3, atol=2e-4)
+            st = o.motion_velocity(st, acts[q, k].astype(np.float64), 0.2)
+            np.testing.assert_allclose(path[q, k], st, rtol=1e-9, atol=1e-11)
+            code = 1 if not o.valid_state_check(st) else (2 if np.hypot(*(st[:2] - targets[q, :2])) <= 1.0 else 0)
+            if k < ns[q] - 1:
+                assert code == 0
+        if np_(out["flags"])[q] == 0:
+            assert code == np_(out["status"])[q] or (code == 0 and ns[q] == 50)
