@@ -19,20 +19,35 @@ def _extend(env, froms, targets, **dwa_kw):
     return ops.extend_dwa(env.handle, d.params(), ops.extend_params(), froms, targets, want_ctrl=True)
 
 
-def _compare(out, ref, what):
+def _compare(out, ref, what, min_clean=0.0):
+    """flags bit0 (collision decision within 1e-6 of the threshold) exempts an
+    extension; bit1 (near-tie argmin somewhere along it) only exempts the chosen
+    rollout indices -- the executed states must still agree (tied rollouts that
+    differ only by the clamped grid overshoot give the same motion)."""
     fl = np_(out["flags"])
+    ok = (fl & 1) == 0
     clean = fl == 0
-    assert clean.mean() > 0.9, f"{what}: too many flagged extensions"
-    for key in ("n_steps", "status", "n_nodes"):
-        assert np.array_equal(np_(out[key])[clean], np.asarray(ref[key])[clean]), (what, key)
+    assert ok.mean() > 0.9, f"{what}: too many near-boundary extensions"
+    assert clean.mean() >= min_clean, f"{what}: too many near-tie extensions ({clean.mean():.2f} clean)"
     path, rpath = np_(out["path"]), ref["path"]
-    for q in np.where(clean)[0]:
+    diverged = 0
+    for q in np.where(ok)[0]:
         n = ref["n_steps"][q]
-        np.testing.assert_allclose(path[q, :n], rpath[q, :n], rtol=1e-9, atol=1e-11)
+        same = (np_(out["n_steps"])[q] == n and np_(out["status"])[q] == ref["status"][q]
+                and np_(out["n_nodes"])[q] == ref["n_nodes"][q]
+                and np.allclose(path[q, :n], rpath[q, :n], rtol=1e-7, atol=1e-9))
+        if not same:
+            assert fl[q] & 2, f"{what}: extension {q} differs without a near-tie report"
+            diverged += 1
+            continue
         k = ref["n_nodes"][q]
         assert np.array_equal(np_(out["node_step"])[q, :k], np.asarray(ref["node_step"])[q, :k])
-        if ref.get("ctrl_idx") is not None:
-            assert np.array_equal(np_(out["ctrl_idx"])[q, :n], ref["ctrl_idx"][q, :n])
+        if fl[q] == 0:
+            np.testing.assert_allclose(path[q, :n], rpath[q, :n], rtol=1e-9, atol=1e-11)
+            if ref.get("ctrl_idx") is not None:
+                assert np.array_equal(np_(out["ctrl_idx"])[q, :n], ref["ctrl_idx"][q, :n])
+    assert diverged <= max(1, int(0.05 * len(fl))), f"{what}: {diverged} near-tie extensions diverged"
+    return dict(clean=int(clean.sum()), tie=int(((fl & 2) != 0).sum()), diverged=diverged)
 
 
 @pytest.mark.parametrize("mname", ("test_env1", "test_env2"))
@@ -58,7 +73,7 @@ def test_extend_vs_oracle_many():
     targets = random_states(rng, 300)
     out = _extend(env, froms, targets)
     ref = orc.Dwa(o, dt=0.2, v_res=0.02).extend_batch(froms, targets, want_ctrl=True)
-    _compare(out, ref, "test_env1")
+    _compare(out, ref, "test_env1", min_clean=0.8)
     assert set(np.unique(ref["status"])) == {0, 1, 2}
 
 
