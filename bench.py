@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- RRT extensions/s of the batched extend path on B200.
+
+One "step" = one pass of the hot path over one batch: for each of Q queries,
+nearest node of its sample over the query's tree, then one whole extension
+(<= 50 closed-loop DWA control steps with motion + collision checks).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); queries are independent,
+so ranks share nothing but the final reduction of the counters ("weak" scaling:
+every rank runs the full per-GPU workload).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_FLOP_ROLLOUT = 406.0      # FP ops per DWA rollout
+M_FLOP_PAIR = 860.0         # FP ops per (pose, obstacle) pair, brute force
+FP64_LANES_PER_SM = 64      # B200: 64 FP64 FMA lanes per SM
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--tree-nodes", type=int, default=1024)
+    ap.add_argument("--cells", type=int, default=10000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="extensions in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def dist_info():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(args, env, rank):
+    """cfg4: dense 10,004-obstacle map, Q queries with pre-filled trees of free
+    nodes, and (steps + warmup) batches of accepted samples (valid state,
+    nearest-node distance in [1, 20), rrt.py:66-69)."""
+    import torch
+    from crl_kino_b200 import ops
+    from crl_kino_b200.planner.batched import Forest
+    from crl_kino_b200.workloads import free_states, random_states
+    rng = np.random.default_rng(100 + rank)
+    Q, N = args.queries, args.tree_nodes
+
+    def clearance(c):
+        return env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
+    nodes = free_states(clearance, rng, Q * N, 0.5, batch=1 << 18)
+    nodes[:, 3:] = 0.0
+    forest = Forest(Q, N)
+    forest.fill(nodes.reshape(Q, N, 5))
+    nb = args.steps + args.warmup
+    batches = np.zeros((nb, Q, 5))
+    need = np.ones((nb, Q), dtype=bool)
+    while need.any():
+        cand = random_states(rng, nb * Q, moving=True).reshape(nb, Q, 5)
+        v = env.valid_state_batch(cand.reshape(-1, 5))[0].cpu().numpy().astype(bool).reshape(nb, Q)
+        for b in range(nb):
+            _, dist, _ = ops.nearest(forest.x, forest.y, forest.n_nodes, cand[b], x32=forest.x32,
+                                     y32=forest.y32, coord_bound=env.coord_bound())
+            d = dist.cpu().numpy()
+            ok = need[b] & v[b] & (d >= 1.0) & (d < 20.0)
+            batches[b, ok] = cand[b, ok]
+            need[b, ok] = False
+    return forest, batches
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_info()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from crl_kino_b200 import ops
+    from crl_kino_b200.env import DifferentialDriveEnv
+    from crl_kino_b200.planner.batched import BatchedExtender
+    from crl_kino_b200.policy.dwa import DWA
+    from crl_kino_b200.workloads import DENSE_DWA, dense_map
+
+    rects = dense_map(n_cells=args.cells)
+    env = DifferentialDriveEnv(1.0, -0.1, np.pi, 1.0, np.pi)
+    env.set_obs(rects)
+    dwa = DWA(env)
+    dwa.set_dwa(**DENSE_DWA)
+    forest, batches = build_workload(args, env, rank)
+    ext = BatchedExtender(env, forest, dwa=dwa)
+    dev_batches = ops.as_dev(batches)
+    K, W, Q = args.steps, args.warmup, args.queries
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ------------------------------------------------
+    for w in range(W):
+        ext.step(dev_batches[w])
+    barrier()
+    ext.stats.zero_()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures only the timed region
+    t_wall = time.time()
+    for k in range(K):
+        flush.fill_(k & 0xff)                      # L2 flush between timed iterations (untimed)
+        ext.step(dev_batches[W + k], events=evs[k])
+    barrier()
+    t_wall = time.time() - t_wall
+    torch.cuda.profiler.stop()
+    clocks = sampler.stop()
+    t_near = sum(e[0].elapsed_time(e[1]) for e in evs)
+    t_gath = sum(e[1].elapsed_time(e[2]) for e in evs)
+    t_ext = sum(e[2].elapsed_time(e[3]) for e in evs)
+    t_total_ms = t_near + t_gath + t_ext
+    stats = ext.stats.cpu().numpy().astype(np.float64)
+    n_ext, n_ctrl, n_roll = stats[0], stats[1], stats[2]
+    status = ext.out["status"].cpu().numpy()
+
+    # ---- end-to-end arm: host buffers through the public API -------------------
+    for w in range(W):
+        ext.step_host(batches[w])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        res = ext.step_host(batches[W + k])
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time, summed work) ----------------------------------
+    red = torch.tensor([t_total_ms, t_e2e, t_ext], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([n_ext, n_ctrl, n_roll], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_total_ms, t_e2e, t_ext_max = [float(x) for x in red.cpu()]
+    tot_ext, tot_ctrl, tot_roll = [float(x) for x in cnt.cpu()]
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        fp64_peak = sms * FP64_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+        M = len(rects)
+        flop = M_FLOP_ROLLOUT * n_roll + M_FLOP_PAIR * M * n_ctrl          # this rank's extend launches
+        achieved = flop / (t_ext * 1e-3) / 1e12
+        value = tot_ext / (t_total_ms * 1e-3)
+        line = {
+            "metric": "rrt_extensions_per_sec", "value": value, "unit": "extensions/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_total_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "cfg4: dense random-obstacle map, DWA steering",
+                       "obstacles": M, "queries_per_gpu": Q, "tree_nodes": args.tree_nodes,
+                       "rollouts_per_control_nominal": 4096,
+                       "rollouts_per_control_realised": tot_roll / max(tot_ctrl, 1),
+                       "control_steps_per_extension": tot_ctrl / max(tot_ext, 1),
+                       "use_clearance": False, "l2": "flushed between timed iterations (256 MiB write)",
+                       "status_last_step": {"timeout": int((status == 0).sum()), "collision": int((status == 1).sum()),
+                                            "reached": int((status == 2).sum())}},
+            "e2e": {"value": tot_ext / t_e2e, "unit": "extensions/s",
+                    "h2d_bytes_per_step": ext.h2d_bytes(), "d2h_bytes_per_step": ext.d2h_bytes()},
+            "gpu_launches": K * ext.launches_per_step,
+            "kernel_ms_per_step": {"nearest": t_near / K, "gather": t_gath / K, "extend_dwa": t_ext / K},
+            "roofline": {"kernel": "k_extend_dwa", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "peak_source": f"derived: {sms} SM x {FP64_LANES_PER_SM} FP64 FMA lanes x 2 x "
+                                        f"{sm_max:.0f} MHz (MEASURED_PEAKS.json holds only HBM and bf16 peaks)",
+                         "algorithmic_flop_per_launch": flop / K,
+                         "note": "algorithmic count = 406/rollout + 860/(pose,obstacle) pair (SURVEY 8d); the kernel "
+                                 "shares sincos chains across the grid and screens obstacles in FP32, so executed "
+                                 "FLOP are far fewer"},
+            "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args, rects, forest, batches[W])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def cpu_sample_run(rects, tree_states, samples, n, threads):
+    """The oracle's C restatement of nearest + DWA extension on the first n queries."""
+    from crl_kino_b200.workloads import DENSE_DWA
+    from oracle import oracle as orc
+    o = orc.Env()
+    o.set_obs(rects)
+    d = orc.Dwa(o, **DENSE_DWA)
+    xs = np.ascontiguousarray(tree_states[:n, :, 0])
+    ys = np.ascontiguousarray(tree_states[:n, :, 1])
+    t0 = time.perf_counter()
+    idx, _ = orc.nearest_batch(xs, ys, np.full(n, xs.shape[1], dtype=np.int32), samples[:n], threads=threads)
+    froms = tree_states[np.arange(n), idx]
+    r = d.extend_batch(froms, samples[:n], threads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, dt, int(r["n_steps"].sum())
+
+
+def cpu_baseline(args, rects, forest, samples):
+    from oracle import oracle as orc
+    cores = orc.cpu_count()
+    n = args.cpu_sample or min(args.queries, max(8 * cores, 64))
+    ts = forest.states[:n].cpu().numpy()
+    v, dt, steps = cpu_sample_run(rects, ts, samples, n, cores)
+    return {"value": v, "unit": "extensions/s", "cores": cores, "kind": "port",
+            "sample": f"first {n} queries of timed batch 0 (nearest + full DWA extension, {steps} control steps) "
+                      f"through oracle/crlk_oracle.c on {cores} threads in {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path (the Python
+    reference itself cannot travel to the GPU box) on all host cores."""
+    rank, _, world = dist_info()
+    if rank != 0:
+        return
+    from crl_kino_b200.workloads import dense_map, random_states
+    from oracle import oracle as orc
+    rects = dense_map(n_cells=args.cells)
+    o = orc.Env()
+    o.set_obs(rects)
+    cores = orc.cpu_count()
+    rng = np.random.default_rng(100)
+    n = args.cpu_sample or max(8 * cores, 64)
+    N = args.tree_nodes
+    K, W = args.steps, args.warmup
+    # same construction as the GPU arm, on the sample only
+    def free(nn):
+        out = []
+        while sum(len(x) for x in out) < nn:
+            c = random_states(rng, 4096)
+            clr = o.valid_state_batch(c)[1]
+            out.append(c[clr > 0.5])
+        return np.concatenate(out)[:nn]
+    nodes = free(n * N)
+    nodes[:, 3:] = 0
+    trees = nodes.reshape(n, N, 5)
+    xs, ys = np.ascontiguousarray(trees[:, :, 0]), np.ascontiguousarray(trees[:, :, 1])
+    batches = []
+    for b in range(K + W):
+        s = np.zeros((n, 5)); need = np.ones(n, dtype=bool)
+        while need.any():
+            c = random_states(rng, n, moving=True)
+            v = o.valid_state_batch(c, clearance=False)[0]
+            _, d = orc.nearest_batch(xs, ys, np.full(n, N, dtype=np.int32), c)
+            ok = need & v & (d >= 1.0) & (d < 20)
+            s[ok] = c[ok]; need[ok] = False
+        batches.append(s)
+    for w in range(min(W, 1)):
+        cpu_sample_run(rects, trees, batches[w], n, cores)
+    t0 = time.perf_counter()
+    tot = 0
+    for k in range(K):
+        cpu_sample_run(rects, trees, batches[W + k], n, cores)
+        tot += n
+    dt = time.perf_counter() - t0
+    v = tot / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "rrt_extensions_per_sec", "value": v, "unit": "extensions/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: dense random-obstacle map, DWA steering", "obstacles": len(rects),
+                   "queries_per_step": n, "tree_nodes": N},
+        "cpu_baseline": {"value": v, "unit": "extensions/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} queries per step (bounded sample of the 1024-query batch), nearest + full "
+                                   f"DWA extension through oracle/crlk_oracle.c on {cores} threads"},
+        "e2e": {"value": v, "unit": "extensions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -55,7 +55,8 @@ PROTOTYPES = {
     "crlk_dwa_max_rollouts": (C.c_int, [P, P]),
     "crlk_nearest": (C.c_int, [P, P, P, P, I64, P, I32, F64, P, I32, I32, P, P, P, P, P]),
     "crlk_nearest_scratch_bytes": (I64, [I32, I32]),
-    "crlk_extend_dwa": (C.c_int, [P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P]),
+    "crlk_extend_dwa": (C.c_int, [P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P]),
+    "crlk_gather_rows": (C.c_int, [P, I64, I32, P, I32, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),
     "crlk_policy_destroy": (C.c_int, [P]),
     "crlk_policy_forward": (C.c_int, [P, P, I32, P, F32, I32, P, P, P]),

@@ -918,7 +918,8 @@ __global__ void __launch_bounds__(DWA_THREADS)
 k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
              const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
              double *path, int *n_steps, int *status, int *node_step, int *n_nodes, int *ctrl_idx,
-             uint8_t *flags, const uint8_t *__restrict__ active, int *work_counter)
+             uint8_t *flags, const uint8_t *__restrict__ active, int *work_counter,
+             unsigned long long *stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DwaSmem sm;
@@ -946,9 +947,11 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
         __syncthreads();
         const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
         int nn = 0, st_code = CRLK_EXT_TIMEOUT, steps = 0, fl = 0;
+        unsigned long long rolls = 0;
         for (int k = 1; k <= x.n_max_extend; k++) {
             DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm);   // rrt.py:116
             fl |= r.near_tie ? 2 : 0;
+            rolls += (unsigned long long)r.R;
             __syncthreads();
             if (tid == 0) {
                 double s[5];
@@ -981,6 +984,11 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
         if (tid == 0) {
             n_steps[q] = steps; status[q] = st_code; n_nodes[q] = nn;
             if (flags) flags[q] = (uint8_t)fl;
+            if (stats) {
+                atomicAdd(&stats[0], 1ull);                          // extensions
+                atomicAdd(&stats[1], (unsigned long long)steps);     // control steps
+                atomicAdd(&stats[2], rolls);                         // rollouts scored
+            }
         }
     }
 }
@@ -1012,7 +1020,7 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
                                const double *from_states, const double *targets, int32_t Q,
                                double *path, int32_t *n_steps, int32_t *status, int32_t *node_step,
                                int32_t *n_nodes, int32_t *ctrl_idx, uint8_t *flags,
-                               const uint8_t *active, void *stream)
+                               const uint8_t *active, uint64_t *stats, void *stream)
 {
     CRLK_REQUIRE(env != nullptr, "env is NULL");
     DwaP d;
@@ -1039,7 +1047,7 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
     if (rc) return rc;
     k_extend_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
         env->p, d, x, env->d_rects, env->M, from_states, targets, Q, path, n_steps, status, node_step,
-        n_nodes, ctrl_idx, flags, active, counter);
+        n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -1228,6 +1236,30 @@ extern "C" int crlk_nearest(const double *x64, const double *y64, const float *x
     CRLK_LAUNCH_CHECK();
     k_nearest_final<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>((NNPartial *)scratch, splits,
                                                                        Q, idx, dist, near_tie);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------------------------------ plumbing
+
+__global__ void k_gather_rows(const double *__restrict__ src, long long q_stride, int row_len,
+                              const int *__restrict__ idx, int Q, double *dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q * row_len) return;
+    int q = i / row_len, c = i - q * row_len;
+    dst[i] = src[(size_t)q_stride * q + (size_t)idx[q] * row_len + c];
+}
+
+extern "C" int crlk_gather_rows(const double *src, int64_t q_stride, int32_t row_len,
+                                const int32_t *idx, int32_t Q, double *dst, void *stream)
+{
+    CRLK_REQUIRE(Q >= 0 && row_len >= 1, "shape");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(src && idx && dst, "NULL array");
+    int n = Q * row_len;
+    k_gather_rows<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, (long long)q_stride, row_len,
+                                                                   idx, Q, dst);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

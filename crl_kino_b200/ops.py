@@ -166,7 +166,7 @@ def nearest(x64, y64, n_nodes, targets, x32=None, y32=None, coord_bound=0.0, max
     return idx, dist, tie
 
 
-def extend_dwa(env, dp, xp, from_states, targets, active=None, want_ctrl=False, out=None):
+def extend_dwa(env, dp, xp, from_states, targets, active=None, want_ctrl=False, out=None, stats=None):
     from_states = as_dev(from_states).reshape(-1, 5)
     Q = from_states.shape[0]
     targets = as_dev(targets).reshape(Q, 5)
@@ -184,7 +184,16 @@ def extend_dwa(env, dp, xp, from_states, targets, active=None, want_ctrl=False, 
     check(lib().crlk_extend_dwa(env.h, C.byref(dp), C.byref(xp), _ptr(from_states), _ptr(targets), Q,
                                 _ptr(out["path"]), _ptr(out["n_steps"]), _ptr(out["status"]),
                                 _ptr(out["node_step"]), _ptr(out["n_nodes"]), _ptr(out.get("ctrl_idx")),
-                                _ptr(out["flags"]), _ptr(active), _stream()))
+                                _ptr(out["flags"]), _ptr(active), _ptr(stats), _stream()))
+    return out
+
+
+def gather_rows(src, idx, out=None):
+    """src: [Q, N, C] float64 CUDA, idx: int32 [Q] -> [Q, C] (src[q, idx[q]])."""
+    Q, N, Cc = src.shape
+    if out is None:
+        out = torch.empty(Q, Cc, dtype=torch.float64, device=src.device)
+    check(lib().crlk_gather_rows(_ptr(src), N * Cc, Cc, _ptr(idx), Q, _ptr(out), _stream()))
     return out
 
 

@@ -169,11 +169,19 @@ int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes);
  *   n_nodes    dev i32[Q]
  *   ctrl_idx   dev i32[Q x n_max_extend] (nullable) chosen rollout index per step
  *   flags      dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin
- *   active     dev u8[Q] (nullable) 0 => skip this pair (n_steps = 0, n_nodes = 0). */
+ *   active     dev u8[Q] (nullable) 0 => skip this pair (n_steps = 0, n_nodes = 0)
+ *   stats      dev u64[3] (nullable) ACCUMULATED (+=): extensions run, control steps
+ *              executed, rollouts scored -- the work counters behind bench.py's roofline. */
 int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
                     const double *from_states, const double *targets, int32_t Q, double *path,
                     int32_t *n_steps, int32_t *status, int32_t *node_step, int32_t *n_nodes,
-                    int32_t *ctrl_idx, uint8_t *flags, const uint8_t *active, void *stream);
+                    int32_t *ctrl_idx, uint8_t *flags, const uint8_t *active, uint64_t *stats,
+                    void *stream);
+
+/* dst[q, :] = src[q * q_stride + idx[q] * row_len : +row_len] -- picks the steer-from
+ * node of every query out of the per-query node tables (rrt.py:70). */
+int crlk_gather_rows(const double *src, int64_t q_stride, int32_t row_len, const int32_t *idx,
+                     int32_t Q, double *dst, void *stream);
 
 /* ---- learned steering: policy_forward (policy/rl_policy.py:83-109) ---- */
 
