@@ -12,7 +12,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "--expt-extended-lambda", "--expt-relaxed-constexpr",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 # (source, extra flags).  The float64 planner kernels must not contract a*b+c.
-UNITS = [("crlk_kernels.cu", ["--fmad=false"]),
+EXTRA_DEFS = ["-D" + d for d in os.environ.get("CRLK_DEFS", "").split() if d]
+UNITS = [("crlk_kernels.cu", ["--fmad=false"] + EXTRA_DEFS),
          ("crlk_nets.cu", [])]
 
 

@@ -174,6 +174,34 @@ __device__ __forceinline__ float aabb_center_d2(float4 o, float px, float py)
     return ex * ex + ey * ey;
 }
 
+// Visit every obstacle listed in the grid cells that the box [p - thr, p + thr]
+// touches, `nthreads` cooperating threads striding each cell's list.  An
+// obstacle spanning several visited cells is visited once per cell (harmless
+// for min / or reductions).  The loops are uniform across the cooperating
+// threads, so the visitor may use warp collectives when nthreads == 32.
+template <class F>
+__device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py, float thr, int t,
+                                           int nthreads, F f)
+{
+    float r = thr + 2e-3f;
+    float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
+    int cx0 = (int)fminf(fmaxf(floorf((px - r - os.gx0) * os.ginv), 0.f), hx);
+    int cx1 = (int)fminf(fmaxf(floorf((px + r - os.gx0) * os.ginv), 0.f), hx);
+    int cy0 = (int)fminf(fmaxf(floorf((py - r - os.gy0) * os.ginv), 0.f), hy);
+    int cy1 = (int)fminf(fmaxf(floorf((py + r - os.gy0) * os.ginv), 0.f), hy);
+    for (int cy = cy0; cy <= cy1; cy++) {
+        // the cells of one grid row are adjacent in the CSR, so a row is one range
+        int s = __ldg(&os.cell_start[cy * os.ncx + cx0]);
+        int e = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
+        for (int kb = s; kb < e; kb += nthreads) {
+            int k = kb + t;
+            bool in = k < e;
+            int o = in ? __ldg(&os.cell_items[k]) : -1;
+            f(o, in);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- reductions
 
 __device__ __forceinline__ double warp_min_d(double v)

@@ -14,6 +14,16 @@ struct EnvP {
     float rc;               // circumradius of the robot rectangle about the body origin
 };
 
+// Obstacle set on the device: rectangles plus a uniform grid of index lists
+// (CSR) used to screen only the cells around a pose.
+struct ObsSet {
+    const float4 *rects;      // [M] left, bottom, right, top
+    const int *cell_start;    // [ncx * ncy + 1]
+    const int *cell_items;    // obstacle ids, cell by cell
+    int M, ncx, ncy;
+    float gx0, gy0, ginv;     // grid origin and 1 / cell size
+};
+
 struct DwaP {
     double v_res, w_res, dt, predict_time;
     double g_goal, g_ob, g_speed;
@@ -34,6 +44,8 @@ struct CrlkEnv {
     CrlkEnvParams host;
     EnvP p;
     float4 *d_rects;  // M obstacles [l, b, r, t]
+    int *d_cell_start, *d_cell_items;
+    ObsSet os;
     int M;
 };
 

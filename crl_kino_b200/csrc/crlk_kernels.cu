@@ -69,6 +69,58 @@ static void fill_envp(const CrlkEnvParams *in, EnvP *p)
     p->rc = m * 1.0001f;
 }
 
+// Uniform grid over the obstacles' bounding box: cell (cx, cy) lists every
+// obstacle whose AABB touches it (CSR, row-major cells).
+static int build_grid(CrlkEnv *env, const float *r, int M)
+{
+    float x0 = 0.f, y0 = 0.f, x1 = 1.f, y1 = 1.f;
+    for (int i = 0; i < M; i++) {
+        if (i == 0) { x0 = r[0]; y0 = r[1]; x1 = r[2]; y1 = r[3]; }
+        x0 = fminf(x0, r[4 * i]); y0 = fminf(y0, r[4 * i + 1]);
+        x1 = fmaxf(x1, r[4 * i + 2]); y1 = fmaxf(y1, r[4 * i + 3]);
+    }
+    float ext = fmaxf(x1 - x0, y1 - y0);
+    float cell = fmaxf(2.0f, ext / 128.0f);
+    int ncx = (int)floorf((x1 - x0) / cell) + 1, ncy = (int)floorf((y1 - y0) / cell) + 1;
+    float ginv = 1.0f / cell;
+    auto cx = [&](float v) { return (int)fminf(fmaxf(floorf((v - x0) * ginv), 0.f), (float)(ncx - 1)); };
+    auto cy = [&](float v) { return (int)fminf(fmaxf(floorf((v - y0) * ginv), 0.f), (float)(ncy - 1)); };
+    int ncell = ncx * ncy;
+    int *start = (int *)calloc((size_t)ncell + 1, sizeof(int));
+    for (int i = 0; i < M; i++)
+        for (int yy = cy(r[4 * i + 1]); yy <= cy(r[4 * i + 3]); yy++)
+            for (int xx = cx(r[4 * i]); xx <= cx(r[4 * i + 2]); xx++) start[yy * ncx + xx + 1]++;
+    for (int c = 0; c < ncell; c++) start[c + 1] += start[c];
+    int total = start[ncell];
+    int *items = (int *)malloc(sizeof(int) * (size_t)(total + 1));
+    int *fill = (int *)calloc((size_t)ncell, sizeof(int));
+    for (int i = 0; i < M; i++)
+        for (int yy = cy(r[4 * i + 1]); yy <= cy(r[4 * i + 3]); yy++)
+            for (int xx = cx(r[4 * i]); xx <= cx(r[4 * i + 2]); xx++) {
+                int c = yy * ncx + xx;
+                items[start[c] + fill[c]++] = i;
+            }
+    if (env->d_cell_start) cudaFree(env->d_cell_start);
+    if (env->d_cell_items) cudaFree(env->d_cell_items);
+    env->d_cell_start = env->d_cell_items = nullptr;
+    cudaError_t e1 = cudaMalloc(&env->d_cell_start, sizeof(int) * ((size_t)ncell + 1));
+    cudaError_t e2 = cudaMalloc(&env->d_cell_items, sizeof(int) * (size_t)(total + 1));
+    if (e1 == cudaSuccess && e2 == cudaSuccess) {
+        e1 = cudaMemcpy(env->d_cell_start, start, sizeof(int) * ((size_t)ncell + 1), cudaMemcpyHostToDevice);
+        e2 = cudaMemcpy(env->d_cell_items, items, sizeof(int) * (size_t)(total + 1), cudaMemcpyHostToDevice);
+    }
+    free(start); free(items); free(fill);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        crlk_set_error("obstacle grid upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        return CRLK_E_CUDA;
+    }
+    env->os.rects = env->d_rects; env->os.cell_start = env->d_cell_start;
+    env->os.cell_items = env->d_cell_items;
+    env->os.M = M; env->os.ncx = ncx; env->os.ncy = ncy;
+    env->os.gx0 = x0; env->os.gy0 = y0; env->os.ginv = ginv;
+    return CRLK_OK;
+}
+
 extern "C" int crlk_env_set_obs(CrlkEnv *env, const float *rects_host, int32_t M)
 {
     CRLK_REQUIRE(env != nullptr, "env is NULL");
@@ -81,7 +133,7 @@ extern "C" int crlk_env_set_obs(CrlkEnv *env, const float *rects_host, int32_t M
     if (M > 0)
         CRLK_CUDA(cudaMemcpy(env->d_rects, rects_host, sizeof(float4) * (size_t)M,
                              cudaMemcpyHostToDevice));
-    return CRLK_OK;
+    return build_grid(env, rects_host, M);
 }
 
 extern "C" int crlk_env_create(const CrlkEnvParams *params, const float *rects_host, int32_t M,
@@ -106,6 +158,8 @@ extern "C" int crlk_env_destroy(CrlkEnv *env)
 {
     if (!env) return CRLK_OK;
     if (env->d_rects) cudaFree(env->d_rects);
+    if (env->d_cell_start) cudaFree(env->d_cell_start);
+    if (env->d_cell_items) cudaFree(env->d_cell_items);
     delete env;
     return CRLK_OK;
 }
@@ -134,16 +188,19 @@ __device__ __forceinline__ void warp_drain(const EnvP &e, const RobotPose &g, co
     }
 }
 
-// One warp per pose.  mode_clearance = 0: flag only (screen at 0.05);
-// 1: exact min distance (screen against the running best).
+// One warp per pose.  Flag only: screen the grid cells around the pose at the
+// collision radius.  With clearance: a full FP32 pass finds an upper bound of
+// the answer, then only cells within that bound are screened.
 __global__ void __launch_bounds__(256)
-k_valid_state(EnvP e, const float4 *__restrict__ rects, int M, const double *__restrict__ states,
-              int B, uint8_t *valid, double *clearance, uint8_t *near_boundary)
+k_valid_state(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8_t *valid,
+              double *clearance, uint8_t *near_boundary)
 {
     __shared__ int s_queue[8][WQ_CAP];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int pose = blockIdx.x * 8 + warp;
     if (pose >= B) return;
+    const float4 *__restrict__ rects = os.rects;
+    const int M = os.M;
     const double *st = states + 5 * (size_t)pose;
     RobotPose g;
     robot_pose_setup(e, st[0], st[1], st[2], g);
@@ -176,10 +233,8 @@ k_valid_state(EnvP e, const float4 *__restrict__ rects, int M, const double *__r
     }
     float thr2 = thr * thr;
     int count = 0;   // warp-uniform
-    for (int base = 0; base < M; base += 32) {
-        int o = base + lane;
-        bool keep = false;
-        if (o < M) keep = aabb_center_d2(__ldg(&rects[o]), px, py) <= thr2;
+    grid_visit(os, px, py, thr, lane, 32, [&](int o, bool in) {
+        bool keep = in && aabb_center_d2(__ldg(&rects[in ? o : 0]), px, py) <= thr2;
         unsigned mask = __ballot_sync(0xffffffffu, keep);
         if (mask) {
             int pos = count + __popc(mask & ((1u << lane) - 1u));
@@ -192,7 +247,7 @@ k_valid_state(EnvP e, const float4 *__restrict__ rects, int M, const double *__r
                 __syncwarp();
             }
         }
-    }
+    });
     __syncwarp();
     warp_drain(e, g, rects, queue, count, best, definite, marginal);
     best = warp_min_d(best);
@@ -212,7 +267,7 @@ extern "C" int crlk_valid_state(const CrlkEnv *env, const double *states, int32_
     CRLK_REQUIRE(B >= 0 && (B == 0 || states != nullptr), "states");
     if (B == 0) return CRLK_OK;
     k_valid_state<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        env->p, env->d_rects, env->M, states, B, valid, clearance, near_boundary);
+        env->p, env->os, states, B, valid, clearance, near_boundary);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -456,33 +511,41 @@ extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const do
 // ------------------------------------------------------------------- DWA (K1)
 
 #define DWA_THREADS 256
+#ifndef DWA_MIN_BLOCKS
+#define DWA_MIN_BLOCKS 3     // 85 registers per thread: 3 CTAs (24 warps) per SM (measured best of 2,3,4)
+#endif
 #define PW_BLOCK 128
 
 struct DwaSmem {
     double *c0, *c1;
     double *vtab, *vlast, *c2n;
     double *wcos, *wsin, *wth;
-    double *leaf;          // [3][lmax]
-    int *loff, *llen;      // [lmax]
-    double *red_v, *red_s; // [32]
-    int *red_i;            // [32]
-    double *scal;          // [16]
-    int *iscal;            // [8]
-    int *queue;            // [DWA_THREADS] scratch for the collision survivor list
-    int spos, rmax, lmax;
+    // numpy pairwise-sum recursion tree over R elements (rebuilt only when R changes)
+    int *nd_off, *nd_len, *nd_left;   // [nmax] element range; first child id (-1 = leaf)
+    int *leaf_ids;                    // [nmax] ids of the leaf nodes
+    double *nd_val;                   // [3][nmax] per-column node sums
+    int *lvl_start;                   // [PW_MAX_LEVELS + 1]
+    double *red_v, *red_s;            // [32]
+    int *red_i;                       // [32]
+    double *scal;                     // [16]
+    int *iscal;                       // [8]: 0 n_leaves, 1 opt idx, 2 near tie, 3 cached R, 4 n_levels, 5 n_nodes
+    int *queue;                       // [1024] scratch for the collision survivor list
+    int spos, rmax, nmax;
 };
+
+#define PW_MAX_LEVELS 24
 
 __host__ __device__ inline int dwa_spos(const DwaP &d)
 {
     return d.use_clearance ? d.n_sub * d.n_outer : d.n_sub;
 }
 __host__ __device__ inline int dwa_rmax(const DwaP &d) { return d.nv_max * d.nw_max; }
-__host__ __device__ inline int dwa_lmax(const DwaP &d) { return dwa_rmax(d) / 32 + 8; }
+__host__ __device__ inline int dwa_nmax(const DwaP &d) { return dwa_rmax(d) / 32 + 16; }
 
 __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, DwaSmem *s)
 {
     size_t off = 0;
-    int spos = dwa_spos(d), rmax = dwa_rmax(d), lmax = dwa_lmax(d);
+    int spos = dwa_spos(d), rmax = dwa_rmax(d), nmax = dwa_nmax(d);
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
     size_t o_c0 = take(sizeof(double) * rmax);
     size_t o_c1 = take(d.use_clearance ? sizeof(double) * rmax : 0);
@@ -492,9 +555,12 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_wcos = take(sizeof(double) * d.nw_max * spos);
     size_t o_wsin = take(sizeof(double) * d.nw_max * spos);
     size_t o_wth = take(sizeof(double) * d.nw_max * d.n_outer);
-    size_t o_leaf = take(sizeof(double) * 3 * lmax);
-    size_t o_loff = take(sizeof(int) * lmax);
-    size_t o_llen = take(sizeof(int) * lmax);
+    size_t o_noff = take(sizeof(int) * nmax);
+    size_t o_nlen = take(sizeof(int) * nmax);
+    size_t o_nleft = take(sizeof(int) * nmax);
+    size_t o_lids = take(sizeof(int) * nmax);
+    size_t o_nval = take(sizeof(double) * 3 * nmax);
+    size_t o_lvl = take(sizeof(int) * (PW_MAX_LEVELS + 1));
     size_t o_rv = take(sizeof(double) * 32);
     size_t o_rs = take(sizeof(double) * 32);
     size_t o_ri = take(sizeof(int) * 32);
@@ -507,13 +573,14 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->c2n = (double *)(base + o_c2n);
         s->wcos = (double *)(base + o_wcos); s->wsin = (double *)(base + o_wsin);
         s->wth = (double *)(base + o_wth);
-        s->leaf = (double *)(base + o_leaf);
-        s->loff = (int *)(base + o_loff); s->llen = (int *)(base + o_llen);
+        s->nd_off = (int *)(base + o_noff); s->nd_len = (int *)(base + o_nlen);
+        s->nd_left = (int *)(base + o_nleft); s->leaf_ids = (int *)(base + o_lids);
+        s->nd_val = (double *)(base + o_nval); s->lvl_start = (int *)(base + o_lvl);
         s->red_v = (double *)(base + o_rv); s->red_s = (double *)(base + o_rs);
         s->red_i = (int *)(base + o_ri);
         s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
         s->queue = (int *)(base + o_q);
-        s->spos = spos; s->rmax = rmax; s->lmax = lmax;
+        s->spos = spos; s->rmax = rmax; s->nmax = nmax;
     }
     return off;
 }
@@ -550,36 +617,75 @@ int crlk_make_dwa(const CrlkEnv *env, const CrlkDwaParams *in, DwaP *d)
     return CRLK_OK;
 }
 
-// Leaves of numpy's pairwise-sum recursion over n elements, left to right.
-__device__ int pw_enumerate(int n, int *loff, int *llen)
+// numpy's pairwise summation (umath DOUBLE_pairwise_sum) splits n > 128 elements
+// into (n2, n - n2), n2 = (n / 2) rounded down to a multiple of 8, and sums
+// blocks of <= 128 with 8 interleaved accumulators.  The recursion tree depends
+// only on n, so one warp builds it breadth-first (children of a node are
+// adjacent, levels are contiguous) and it is cached until n changes.
+__device__ void pw_build_tree_warp(int n, const DwaSmem &sm)
 {
-    int so[32], sn[32];
-    int sp = 0, cnt = 0;
-    so[0] = 0; sn[0] = n; sp = 1;
-    while (sp) {
-        sp--;
-        int o = so[sp], m = sn[sp];
-        if (m <= PW_BLOCK) {
-            loff[cnt] = o; llen[cnt] = m; cnt++;
-        } else {
-            int n2 = m / 2;
-            n2 -= n2 % 8;
-            so[sp] = o + n2; sn[sp] = m - n2; sp++;
-            so[sp] = o;      sn[sp] = n2;     sp++;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { sm.nd_off[0] = 0; sm.nd_len[0] = n; sm.lvl_start[0] = 0; sm.lvl_start[1] = 1; }
+    __syncwarp();
+    int s = 0, e = 1, depth = 0, n_leaves = 0;
+    for (;;) {
+        int next = e;
+        for (int base = s; base < e; base += 32) {
+            int node = base + lane;
+            int len = (node < e) ? sm.nd_len[node] : 0;
+            bool split = len > PW_BLOCK;
+            bool leaf = (node < e) && !split;
+            unsigned ms = __ballot_sync(0xffffffffu, split);
+            unsigned ml = __ballot_sync(0xffffffffu, leaf);
+            unsigned lt = (1u << lane) - 1u;
+            if (split) {
+                int pos = next + 2 * __popc(ms & lt);
+                int off = sm.nd_off[node];
+                int n2 = len / 2;
+                n2 -= n2 % 8;
+                sm.nd_left[node] = pos;
+                sm.nd_off[pos] = off;          sm.nd_len[pos] = n2;
+                sm.nd_off[pos + 1] = off + n2; sm.nd_len[pos + 1] = len - n2;
+            } else if (leaf) {
+                sm.nd_left[node] = -1;
+                sm.leaf_ids[n_leaves + __popc(ml & lt)] = node;
+            }
+            next += 2 * __popc(ms);
+            n_leaves += __popc(ml);
         }
+        __syncwarp();
+        depth++;
+        if (next == e || depth >= PW_MAX_LEVELS) break;
+        s = e; e = next;
+        if (lane == 0) sm.lvl_start[depth + 1] = e;
+        __syncwarp();
     }
-    return cnt;
+    if (lane == 0) { sm.iscal[0] = n_leaves; sm.iscal[3] = n; sm.iscal[4] = depth; sm.iscal[5] = e; }
 }
 
-// Combine leaf sums in the recursion's own association order.
-__device__ double pw_combine(int n, const double *leaf, int &cur)
+// One <= 128-element block by 8 cooperating lanes (sub = lane & 7): lane k owns
+// accumulator r[k]; the combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and the
+// sequential remainder follow numpy's order exactly.  Result valid where sub == 0.
+template <class F>
+__device__ __forceinline__ double np_leaf_sum8(F f, int off, int n, int sub)
 {
-    if (n <= PW_BLOCK) return leaf[cur++];
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    double a = pw_combine(n2, leaf, cur);
-    double b = pw_combine(n - n2, leaf, cur);
-    return a + b;
+    double res;
+    if (n < 8) {
+        res = 0.0;
+        if (sub == 0)
+            for (int i = 0; i < n; i++) res += f(off + i);
+        return res;
+    }
+    const int lim = n - (n % 8);
+    double r = f(off + sub);
+    for (int i = 8 + sub; i < lim; i += 8) r += f(off + i);
+    const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);   // the 8 cooperating lanes
+    double t1 = r + __shfl_down_sync(gm, r, 1, 8);
+    double t2 = t1 + __shfl_down_sync(gm, t1, 2, 8);
+    res = t2 + __shfl_down_sync(gm, t2, 4, 8);
+    if (sub == 0)
+        for (int i = lim; i < n; i++) res += f(off + i);
+    return res;
 }
 
 struct DwaResult {
@@ -589,7 +695,7 @@ struct DwaResult {
 };
 
 // get_clearance for one pose by one thread (used only when use_clearance = 1).
-__device__ double clearance_thread(const EnvP &e, const float4 *__restrict__ rects, int M, double x,
+__device__ __noinline__ double clearance_thread(const EnvP &e, const float4 *__restrict__ rects, int M, double x,
                                    double y, double th)
 {
     RobotPose g;
@@ -662,7 +768,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
             if ((k + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (k + 1) / d.n_sub - 1] = th;
         }
     }
-    if (tid == 0) sm.iscal[0] = pw_enumerate(R, sm.loff, sm.llen);
+    if (warp == 3 && sm.iscal[3] != R) pw_build_tree_warp(R, sm);   // warps 3-4 have no chain work
     // clearance of the shared first row (dwa.py:65-67, i = 0)
     double clr0 = CRLK_CLEARANCE_CAP;
     if (d.use_clearance) clr0 = pymax(clearance_thread(e, rects, M, st[0], st[1], st[2]), 0.001);
@@ -701,32 +807,38 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
     }
     __syncthreads();
 
-    // column sums in numpy's pairwise order (dwa.py:76-78)
-    const int L = sm.iscal[0];
-    if (warp < 3) {
-        for (int l = lane; l < L; l += 32) {
-            int off = sm.loff[l], n = sm.llen[l];
-            double s;
-            if (warp == 0) {
-                const double *c0 = sm.c0;
-                s = np_leaf_sum([&](int q) { return c0[q]; }, off, n);
-            } else if (warp == 1) {
-                if (d.use_clearance) {
-                    const double *c1 = sm.c1;
-                    s = np_leaf_sum([&](int q) { return c1[q]; }, off, n);
-                } else {
-                    s = np_leaf_sum([&](int) { return 1.0 / 100.0; }, off, n);
-                }
+    // column sums in numpy's pairwise order (dwa.py:76-78): every leaf block of
+    // every column by 8 lanes, then the tree levels bottom-up (one warp per column)
+    {
+        const int L = sm.iscal[0];
+        const int sub = tid & 7;
+        const double *c0 = sm.c0, *c1 = sm.c1, *vl = sm.vlast;
+        for (int task = tid >> 3; task < 3 * L; task += T >> 3) {
+            int col = task / L, node = sm.leaf_ids[task - col * L];
+            int off = sm.nd_off[node], n = sm.nd_len[node];
+            double sres;
+            if (col == 0) {
+                sres = np_leaf_sum8([&](int q) { return c0[q]; }, off, n, sub);
+            } else if (col == 1) {
+                if (d.use_clearance) sres = np_leaf_sum8([&](int q) { return c1[q]; }, off, n, sub);
+                else sres = np_leaf_sum8([&](int) { return 1.0 / 100.0; }, off, n, sub);
             } else {
-                const double *vl = sm.vlast;
-                s = np_leaf_sum([&](int q) { return v_hi - vl[q / nw]; }, off, n);
+                sres = np_leaf_sum8([&](int q) { return v_hi - vl[q / nw]; }, off, n, sub);
             }
-            sm.leaf[warp * sm.lmax + l] = s;
+            if (sub == 0) sm.nd_val[col * sm.nmax + node] = sres;
         }
-        __syncwarp();
-        if (lane == 0) {
-            int cur = 0;
-            sm.scal[warp] = pw_combine(R, sm.leaf + warp * sm.lmax, cur);
+        __syncthreads();
+        if (warp < 3) {
+            double *val = sm.nd_val + warp * sm.nmax;
+            for (int lv = sm.iscal[4] - 1; lv >= 0; lv--) {
+                int e = sm.lvl_start[lv + 1];
+                for (int node = sm.lvl_start[lv] + lane; node < e; node += 32) {
+                    int l = sm.nd_left[node];
+                    if (l >= 0) val[node] = val[l] + val[l + 1];
+                }
+                __syncwarp();
+            }
+            if (lane == 0) sm.scal[warp] = val[0];
         }
     }
     __syncthreads();
@@ -786,7 +898,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
     return res;
 }
 
-__global__ void __launch_bounds__(DWA_THREADS)
+__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
 k_dwa_control(EnvP e, DwaP d, const float4 *__restrict__ rects, int M,
               const double *__restrict__ states, const double *__restrict__ goals, int goal_stride,
               int B, double *opt_v, int *opt_idx, double *opt_cost, double *opt_traj,
@@ -796,6 +908,7 @@ k_dwa_control(EnvP e, DwaP d, const float4 *__restrict__ rects, int M,
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5];
+    if (threadIdx.x == 0) sm.iscal[3] = -1;   // no pairwise-sum tree cached yet
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
@@ -873,10 +986,11 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
 // all M obstacles, survivors queued in shared memory, exact FP64 tests spread
 // over the threads.  Returns bit0 = collision, bit1 = the decision is within
 // 1e-6 of the 0.05 threshold (reported, not claimed).
-__device__ int collision_block(const EnvP &e, const float4 *__restrict__ rects, int M, double x,
-                               double y, double th, int *s_queue /*1024*/, int *s_ctl /*4*/)
+__device__ int collision_block(const EnvP &e, const ObsSet &os, double x, double y, double th,
+                               int *s_queue /*1024*/, int *s_ctl /*4*/)
 {
     const int tid = threadIdx.x, T = blockDim.x;
+    const float4 *__restrict__ rects = os.rects;
     RobotPose g;
     robot_pose_setup(e, x, y, th, g);
     float px = (float)x, py = (float)y;
@@ -886,7 +1000,8 @@ __device__ int collision_block(const EnvP &e, const float4 *__restrict__ rects, 
     if (tid < 4) s_ctl[tid] = 0;
     __syncthreads();
     bool coll = false, definite = false, marginal = false;
-    for (int o = tid; o < M; o += T) {
+    grid_visit(os, px, py, thr, tid, T, [&](int o, bool in) {
+        if (!in) return;
         float4 r = __ldg(&rects[o]);
         if (aabb_center_d2(r, px, py) <= thr2) {
             int pos = atomicAdd(&s_ctl[0], 1);
@@ -897,7 +1012,7 @@ __device__ int collision_block(const EnvP &e, const float4 *__restrict__ rects, 
                 definite |= d; marginal |= m;
             }
         }
-    }
+    });
     __syncthreads();
     int cnt = min(s_ctl[0], 1024);
     for (int k = tid; k < cnt; k += T) {
@@ -914,8 +1029,8 @@ __device__ int collision_block(const EnvP &e, const float4 *__restrict__ rects, 
     return res;
 }
 
-__global__ void __launch_bounds__(DWA_THREADS)
-k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
+__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
+k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
              const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
              double *path, int *n_steps, int *status, int *node_step, int *n_nodes, int *ctrl_idx,
              uint8_t *flags, const uint8_t *__restrict__ active, int *work_counter,
@@ -929,6 +1044,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
     __shared__ int s_q;
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
+    if (tid == 0) sm.iscal[3] = -1;   // no pairwise-sum tree cached yet
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
         __syncthreads();
@@ -949,7 +1065,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
         int nn = 0, st_code = CRLK_EXT_TIMEOUT, steps = 0, fl = 0;
         unsigned long long rolls = 0;
         for (int k = 1; k <= x.n_max_extend; k++) {
-            DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm);   // rrt.py:116
+            DwaResult r = dwa_control_block(e, d, os.rects, os.M, s_state, gx, gy, sm);   // rrt.py:116
             fl |= r.near_tie ? 2 : 0;
             rolls += (unsigned long long)r.R;
             __syncthreads();
@@ -966,7 +1082,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, const float4 *__restrict__ rects, int M,
             __syncthreads();
             steps = k;
             // rrt.py:121: valid_state_check on the new state
-            int col = collision_block(e, rects, M, s_state[0], s_state[1], s_state[2], sm.queue, s_ctl);
+            int col = collision_block(e, os, s_state[0], s_state[1], s_state[2], sm.queue, s_ctl);
             if (col & 2) fl |= 1;
             col &= 1;
             if (col == 1) { st_code = CRLK_EXT_COLLISION; break; }
@@ -1046,7 +1162,7 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
     rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
     if (rc) return rc;
     k_extend_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
-        env->p, d, x, env->d_rects, env->M, from_states, targets, Q, path, n_steps, status, node_step,
+        env->p, d, x, env->os, from_states, targets, Q, path, n_steps, status, node_step,
         n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;

@@ -414,7 +414,7 @@ __global__ void k_rl_init(const double *__restrict__ from_states, const uint8_t 
 // One warp per query: apply the action (differential_gym.py:139), then the
 // planner's checks (rrt_rl.py:48-57).
 __global__ void __launch_bounds__(256)
-k_rl_step(EnvP e, ExtP x, const float4 *__restrict__ rects, int M, const double *__restrict__ targets,
+k_rl_step(EnvP e, ExtP x, ObsSet os, const double *__restrict__ targets,
           const float *__restrict__ act, int k, int Q, double *state, int *done, int *nn, double *path,
           int *n_steps, int *status, int *node_step, int *n_nodes, float *actions, uint8_t *flags)
 {
@@ -436,12 +436,11 @@ k_rl_step(EnvP e, ExtP x, const float4 *__restrict__ rects, int M, const double 
     float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
     float thr2 = thr * thr;
     int *queue = s_queue[warp];
+    const float4 *__restrict__ rects = os.rects;
     bool coll = false, definite = false, marginal = false;
     int count = 0;
-    for (int base = 0; base < M; base += 32) {
-        int o = base + lane;
-        bool keep = false;
-        if (o < M) keep = aabb_center_d2(__ldg(&rects[o]), px, py) <= thr2;
+    grid_visit(os, px, py, thr, lane, 32, [&](int o, bool in) {
+        bool keep = in && aabb_center_d2(__ldg(&rects[in ? o : 0]), px, py) <= thr2;
         unsigned mask = __ballot_sync(0xffffffffu, keep);
         if (mask) {
             int pos = count + __popc(mask & ((1u << lane) - 1u));
@@ -459,7 +458,7 @@ k_rl_step(EnvP e, ExtP x, const float4 *__restrict__ rects, int M, const double 
                 __syncwarp();
             }
         }
-    }
+    });
     __syncwarp();
     for (int b0 = 0; b0 < count; b0 += 32)
         if (b0 + lane < count) {
@@ -526,7 +525,7 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
         rc = policy_forward_impl(p, w.obs, 736, noise ? noise + (size_t)(k - 1) * 2 : nullptr,
                                  (long long)x.n_max_extend * 2, eps, Q, w.act, w.mlp, st);
         if (rc) return rc;
-        k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->d_rects, env->M, targets, w.act, k, Q,
+        k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->os, targets, w.act, k, Q,
                                               w.state, w.done, w.nn, path, n_steps, status, node_step,
                                               n_nodes, actions, flags);
         CRLK_LAUNCH_CHECK();
