@@ -725,9 +725,10 @@ __device__ __noinline__ double clearance_thread(const EnvP &e, const float4 *__r
 
 // DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
 // doubles) and the goal must be block-uniform.  Every thread returns the result.
+template <class Epi>
 __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float4 *__restrict__ rects,
                                        int M, const double *st, double gx, double gy,
-                                       const DwaSmem &sm)
+                                       const DwaSmem &sm, Epi epilogue)
 {
     const int tid = threadIdx.x, T = DWA_THREADS;
     const int lane = tid & 31, warp = tid >> 5;
@@ -775,20 +776,49 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
     __syncthreads();
 
     // rollouts: heading cost from trajectory row 1 (dwa.py:58-62)
-    for (int r = tid; r < R; r += T) {
-        int i = r / nw, j = r - i * nw;
-        double x = st[0], y = st[1];
+    const int di = T / nw, dj = T - di * nw;     // r += T  <=>  (i, j) += (di, dj) with carry
+    int ri = tid / nw, rj = tid - ri * nw;
+    auto heading_cost = [&](int i, int j, double &x, double &y) {
         const double *vt = sm.vtab + i * spos;
         const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
+        x = st[0]; y = st[1];
         for (int k = 0; k < d.n_sub; k++) {
             x = x + vt[k] * wc[k] * dt;
             y = y + vt[k] * ws[k] * dt;
         }
         double ang = atan2(gy - y, gx - x);
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
-        c0 = pymin(c0, CRLK_TWO_PI - c0);
-        sm.c0[r] = c0;
-        if (d.use_clearance) {
+        return pymin(c0, CRLK_TWO_PI - c0);
+    };
+    if (!d.use_clearance) {
+        // two independent rollouts per iteration: the FP64 dependency chains overlap
+        int r = tid;
+        for (; r + T < R; r += 2 * T) {
+            const int i0 = ri, j0 = rj;
+            ri += di; rj += dj;
+            if (rj >= nw) { rj -= nw; ri++; }
+            const int i1 = ri, j1 = rj;
+            ri += di; rj += dj;
+            if (rj >= nw) { rj -= nw; ri++; }
+            double xa, ya, xb, yb;
+            double ca = heading_cost(i0, j0, xa, ya);
+            double cb = heading_cost(i1, j1, xb, yb);
+            sm.c0[r] = ca;
+            sm.c0[r + T] = cb;
+        }
+        if (r < R) {
+            double xa, ya;
+            sm.c0[r] = heading_cost(ri, rj, xa, ya);
+        }
+    } else {
+        for (int r = tid; r < R; r += T) {
+            const int i = ri, j = rj;
+            ri += di; rj += dj;
+            if (rj >= nw) { rj -= nw; ri++; }
+            double x, y;
+            sm.c0[r] = heading_cost(i, j, x, y);
+            const double *vt = sm.vtab + i * spos;
+            const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
             double min_dis = pymin(clr0, 100.0);
             for (int row = 1; row <= d.n_outer; row++) {
                 if (row > 1)
@@ -813,8 +843,14 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
         const int L = sm.iscal[0];
         const int sub = tid & 7;
         const double *c0 = sm.c0, *c1 = sm.c1, *vl = sm.vlast;
-        for (int task = tid >> 3; task < 3 * L; task += T >> 3) {
+        // q / nw for q < 2^14, nw < 2^7 as one multiply-high
+        const unsigned magic = 0xffffffffu / (unsigned)nw + 1u;
+        // the constant obstacle column (dwa.py:64-69 disabled) sums to a function of R alone
+        const bool skip_c1 = !d.use_clearance && sm.iscal[6] == R;
+        const int ncol = skip_c1 ? 2 : 3;
+        for (int task = tid >> 3; task < ncol * L; task += T >> 3) {
             int col = task / L, node = sm.leaf_ids[task - col * L];
+            if (skip_c1 && col == 1) col = 2;
             int off = sm.nd_off[node], n = sm.nd_len[node];
             double sres;
             if (col == 0) {
@@ -823,7 +859,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
                 if (d.use_clearance) sres = np_leaf_sum8([&](int q) { return c1[q]; }, off, n, sub);
                 else sres = np_leaf_sum8([&](int) { return 1.0 / 100.0; }, off, n, sub);
             } else {
-                sres = np_leaf_sum8([&](int q) { return v_hi - vl[q / nw]; }, off, n, sub);
+                sres = np_leaf_sum8([&](int q) { return v_hi - vl[__umulhi((unsigned)q, magic)]; }, off, n, sub);
             }
             if (sub == 0) sm.nd_val[col * sm.nmax + node] = sres;
         }
@@ -838,58 +874,109 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
                 }
                 __syncwarp();
             }
-            if (lane == 0) sm.scal[warp] = val[0];
+            if (lane == 0) {
+                if (warp == 1 && !d.use_clearance) {
+                    if (sm.iscal[6] == R) sm.scal[1] = sm.scal[9];           // cached
+                    else { sm.scal[1] = val[0]; sm.scal[9] = val[0]; sm.iscal[7] = R; }
+                } else {
+                    sm.scal[warp] = val[0];
+                }
+            }
         }
     }
     __syncthreads();
+    if (tid == 0 && !d.use_clearance) sm.iscal[6] = sm.iscal[7];
     const double S0 = sm.scal[0], S1 = sm.scal[1], S2 = sm.scal[2];
-    for (int i = tid; i < nv; i += T) {
-        double c2 = v_hi - sm.vlast[i];
-        sm.c2n[i] = (S2 != 0.0) ? c2 / S2 : c2;
-    }
-    __syncthreads();
-
-    // weighted sum and first argmin (dwa.py:79-82), plus the runner-up for near_tie
-    double best = CUDART_INF, second = CUDART_INF;
-    int bi = 0x7fffffff;
+    // weighted sum and first argmin (dwa.py:79-82).  Screen: the normalising
+    // divisions replaced by reciprocal multiplies (a few ulp off); every rollout
+    // within 1e-12 relative of the screened minimum is then re-scored with the
+    // reference's exact operations, so the winner is the exact first minimum.
+    const double inv0 = (S0 != 0.0) ? 1.0 / S0 : 1.0;
+    const double inv1 = (S1 != 0.0) ? 1.0 / S1 : 1.0;
+    const double inv2 = (S2 != 0.0) ? 1.0 / S2 : 1.0;
     const double c1n_const = (S1 != 0.0) ? (1.0 / 100.0) / S1 : (1.0 / 100.0);
-    for (int r = tid; r < R; r += T) {
-        int i = r / nw;
+    auto approx_cost = [&](int r, int i) {
+        double c1a = d.use_clearance ? sm.c1[r] * inv1 : c1n_const;
+        return d.g_goal * (sm.c0[r] * inv0) + d.g_ob * c1a + d.g_speed * ((v_hi - sm.vlast[i]) * inv2);
+    };
+    auto exact_cost = [&](int r, int i) {
         double c0n = (S0 != 0.0) ? sm.c0[r] / S0 : sm.c0[r];
         double c1n = c1n_const;
         if (d.use_clearance) c1n = (S1 != 0.0) ? sm.c1[r] / S1 : sm.c1[r];
-        double c = d.g_goal * c0n + d.g_ob * c1n + d.g_speed * sm.c2n[i];
-        if (c < best) { second = best; best = c; bi = r; }
-        else if (c < second) second = c;
+        double c2 = v_hi - sm.vlast[i];
+        double c2n = (S2 != 0.0) ? c2 / S2 : c2;
+        return d.g_goal * c0n + d.g_ob * c1n + d.g_speed * c2n;
+    };
+    double abest = CUDART_INF, asecond = CUDART_INF;
+    int abi = 0x7fffffff, abv = 0;
+    ri = tid / nw; rj = tid - ri * nw;
+    for (int r = tid; r < R; r += T) {
+        const int i = ri;
+        ri += di; rj += dj;
+        if (rj >= nw) { rj -= nw; ri++; }
+        double c = approx_cost(r, i);
+        if (c < abest) { asecond = abest; abest = c; abi = r; abv = i; }
+        else if (c < asecond) asecond = c;
     }
-    // warp level: merge (best, idx, second)
+    {   // block minimum of the screened costs and the runner-up (near_tie report)
+        double wb = abest, ws2 = asecond;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        double os = __shfl_xor_sync(0xffffffffu, second, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        second = fmin(fmin(second, os), fmax(best, ob));
-        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, wb, o);
+            double os = __shfl_xor_sync(0xffffffffu, ws2, o);
+            ws2 = fmin(fmin(ws2, os), fmax(wb, ob));
+            wb = fmin(wb, ob);
+        }
+        if (lane == 0) { sm.red_v[warp] = wb; sm.red_s[warp] = ws2; }
     }
-    if (lane == 0) { sm.red_v[warp] = best; sm.red_s[warp] = second; sm.red_i[warp] = bi; }
+    __syncthreads();
+    double m_a = sm.red_v[0], s_a = sm.red_s[0];
+#pragma unroll
+    for (int w = 1; w < T / 32; w++) {
+        double ob = sm.red_v[w], os = sm.red_s[w];
+        s_a = fmin(fmin(s_a, os), fmax(m_a, ob));
+        m_a = fmin(m_a, ob);
+    }
+    const double lim = m_a + fabs(m_a) * 1e-12;
+    double best = CUDART_INF;
+    int bi = 0x7fffffff;
+    if (abest <= lim) {
+        if (asecond <= lim) {           // several candidates in this thread: rescan them all
+            ri = tid / nw; rj = tid - ri * nw;
+            for (int r = tid; r < R; r += T) {
+                const int i = ri;
+                ri += di; rj += dj;
+                if (rj >= nw) { rj -= nw; ri++; }
+                if (approx_cost(r, i) <= lim) {
+                    double c = exact_cost(r, i);
+                    if (c < best) { best = c; bi = r; }
+                }
+            }
+        } else {
+            best = exact_cost(abi, abv);
+            bi = abi;
+        }
+    }
+    __syncthreads();          // red_v / red_s are reused below
+    warp_argmin(best, bi);
+    if (lane == 0) { sm.red_v[warp] = best; sm.red_i[warp] = bi; }
     __syncthreads();
     if (tid == 0) {
-        double b = sm.red_v[0], s2 = sm.red_s[0];
+        double b = sm.red_v[0];
         int ix = sm.red_i[0];
         for (int w = 1; w < T / 32; w++) {
-            double ob = sm.red_v[w], os = sm.red_s[w];
+            double ob = sm.red_v[w];
             int oi = sm.red_i[w];
-            double loser = fmax(b, ob);
             if (ob < b || (ob == b && oi < ix)) { b = ob; ix = oi; }
-            s2 = fmin(fmin(s2, os), loser);
         }
         int i = ix / nw, j = ix - i * nw;
         sm.scal[4] = arange_at(v_lo, v1, vd, i);
         sm.scal[5] = arange_at(w_lo, w1, wd, j);
         sm.scal[6] = b;
         sm.iscal[1] = ix;
-        double gap = s2 - b;
-        sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(b)) ? 1 : 0;
+        double gap = s_a - m_a;
+        sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(m_a)) ? 1 : 0;
+        epilogue(sm.scal[4], sm.scal[5], ix);    // thread 0 only, before the closing barrier
     }
     __syncthreads();
     DwaResult res;
@@ -908,13 +995,13 @@ k_dwa_control(EnvP e, DwaP d, const float4 *__restrict__ rects, int M,
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5];
-    if (threadIdx.x == 0) sm.iscal[3] = -1;   // no pairwise-sum tree cached yet
+    if (threadIdx.x == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
         __syncthreads();
         double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
-        DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm);
+        DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm, [](double, double, int) {});
         if (threadIdx.x == 0) {
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
@@ -1039,12 +1126,12 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
-    __shared__ double s_state[5];
+    __shared__ double s_state[5], s_next[5];
     __shared__ int s_ctl[8];
     __shared__ int s_q;
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
-    if (tid == 0) sm.iscal[3] = -1;   // no pairwise-sum tree cached yet
+    if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
         __syncthreads();
@@ -1065,20 +1152,22 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
         int nn = 0, st_code = CRLK_EXT_TIMEOUT, steps = 0, fl = 0;
         unsigned long long rolls = 0;
         for (int k = 1; k <= x.n_max_extend; k++) {
-            DwaResult r = dwa_control_block(e, d, os.rects, os.M, s_state, gx, gy, sm);   // rrt.py:116
+            // rrt.py:116-118: control, then thread 0 advances the state inside the
+            // control block's closing section (no extra barrier round trip)
+            DwaResult r = dwa_control_block(e, d, os.rects, os.M, s_state, gx, gy, sm,
+                [&](double cv, double cw, int ix) {
+                    double s[5];
+                    for (int c = 0; c < 5; c++) s[c] = s_state[c];
+                    motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
+                    for (int c = 0; c < 5; c++) {
+                        s_next[c] = s[c];
+                        path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
+                    }
+                    if (ctrl_idx) ctrl_idx[(size_t)q * x.n_max_extend + (k - 1)] = ix;
+                });
             fl |= r.near_tie ? 2 : 0;
             rolls += (unsigned long long)r.R;
-            __syncthreads();
-            if (tid == 0) {
-                double s[5];
-                for (int c = 0; c < 5; c++) s[c] = s_state[c];
-                motion_velocity_dev(e, s, r.v, r.w, x.n_sub_step);                  // rrt.py:118
-                for (int c = 0; c < 5; c++) {
-                    s_state[c] = s[c];
-                    path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
-                }
-                if (ctrl_idx) ctrl_idx[(size_t)q * x.n_max_extend + (k - 1)] = r.idx;
-            }
+            if (tid < 5) s_state[tid] = s_next[tid];
             __syncthreads();
             steps = k;
             // rrt.py:121: valid_state_check on the new state
