@@ -58,6 +58,7 @@ struct CrlkPolicy {
     float *d_b[8];
     float low[2], high[2], scale[2], bias[2];
     int max_dim;
+    struct CrlkPolicyTc *tc;   // tensor-core path of the hidden layers (NULL if the widths do not tile)
 };
 
 struct CrlkEstimator {
@@ -99,3 +100,12 @@ int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x);
     } while (0)
 
 int crlk_require_device(void);
+
+// tensor-core MLP (crlk_mlp_tc.cu)
+struct CrlkPolicyTc;
+int crlk_tc_supported(const int *dims, int n_layers);
+int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_host, CrlkPolicyTc **out);
+void crlk_tc_destroy(CrlkPolicyTc *t);
+size_t crlk_tc_workspace_bytes(const CrlkPolicyTc *t, int B);
+int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, int B, void *workspace,
+                           const float *const *d_bias, const float **out, int *ld_out, cudaStream_t st);

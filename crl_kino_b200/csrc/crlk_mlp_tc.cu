@@ -1,0 +1,418 @@
+// libcrlk.so -- actor MLP hidden layers on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA; sm_100a only).
+//
+// The reference MLP is float32 (torch sgemm).  A single bf16 or tf32 pass is
+// ~1e-3 off, too coarse for the 1e-4 trajectory contract after 50 closed-loop
+// steps, so every float32 operand is split into three bf16 planes
+//     x = x1 + x2 + x3,  x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2)
+// and  A.W^T  is accumulated in float32 (TMEM) over the six plane products
+//     A1W1 + A1W2 + A2W1 + A2W2 + A1W3 + A3W1      (dropped terms <= 2^-24 |a||w|),
+// i.e. one bf16 GEMM with a 6x longer K loop whose TMA loads walk the planes.
+// The epilogue adds the bias, applies ReLU and writes the next layer's three
+// bf16 planes directly (and/or float32 for the head kernel).
+//
+// Tile: 128 (batch rows) x 128 (features) x 64 (k), UMMA 128x128x16, 4 smem
+// stages of 32 KB, 128 TMEM columns.  Warp roles: 0 = TMA producer, 1 = MMA
+// issuer (one thread), 2 = TMEM allocator, 4-7 = epilogue (one TMEM lane
+// quadrant each).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "crlk_internal.h"
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_BK 64
+#define TC_STAGES 4
+#define TC_STAGE_BYTES (TC_BM * TC_BK * 2)     // 16 KB per operand tile
+#define TC_THREADS 256
+#define TC_SMEM_BYTES (2 * TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_NPAIR 6
+
+__device__ __constant__ int c_pair_a[TC_NPAIR] = {0, 0, 1, 1, 0, 2};
+__device__ __constant__ int c_pair_w[TC_NPAIR] = {0, 1, 0, 1, 2, 0};
+
+// ---------------------------------------------------------------- PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, 128-byte swizzled operand tile (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused with swizzle) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n)
+{
+    uint32_t d = 0;
+    d |= 1u << 4;                    // c_format = F32
+    d |= 1u << 7;                    // a_format = BF16
+    d |= 1u << 10;                   // b_format = BF16
+    d |= (uint32_t)(n >> 3) << 17;   // n_dim
+    d |= (uint32_t)(m >> 4) << 24;   // m_dim
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 &a, __nv_bfloat16 &b, __nv_bfloat16 &c)
+{
+    a = __float2bfloat16_rn(x);
+    float r1 = x - __bfloat162float(a);
+    b = __float2bfloat16_rn(r1);
+    float r2 = r1 - __bfloat162float(b);
+    c = __float2bfloat16_rn(r2);
+}
+
+// ------------------------------------------------------------------ the GEMM
+
+// planes_out: [3][Mpad][ld_out] bf16 (nullable), c32: [B][ldc] float (nullable).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+              int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
+              __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;    // SWIZZLE_128B needs 1024 B alignment
+    const uint32_t sA = base, sB = base + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t bars = sB + TC_STAGES * TC_STAGE_BYTES;           // full[S], empty[S], tmem_full, tmem slot
+    const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull = bars + 16 * TC_STAGES;
+    const uint32_t tslot = tfull + 8;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + 2 * TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+    const int iters = TC_NPAIR * kblocks;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(TC_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer
+        for (int it = 0; it < iters; it++) {
+            int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+            int pair = it / kblocks, kb = it - pair * kblocks;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            mbar_expect_tx(full0 + 8 * s, 2 * TC_STAGE_BYTES);
+            tma_load_2d(sA + s * TC_STAGE_BYTES, &tmA, kb * TC_BK, c_pair_a[pair] * Mpad + m0, full0 + 8 * s);
+            tma_load_2d(sB + s * TC_STAGE_BYTES, &tmW, kb * TC_BK, c_pair_w[pair] * N + n0, full0 + 8 * s);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer (single thread)
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+        for (int it = 0; it < iters; it++) {
+            int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint64_t da = umma_desc_sw128(sA + s * TC_STAGE_BYTES);
+            uint64_t db = umma_desc_sw128(sB + s * TC_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; k++)      // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+                umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+            umma_commit(empty0 + 8 * s);              // frees the smem stage when these MMAs retire
+        }
+        umma_commit(tfull);                           // accumulator complete
+    } else if (warp >= 4) {
+        // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) = rows m0 + 32q + lane
+        const int q = warp & 3;
+        const int m = m0 + 32 * q + lane;
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; c++) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+            if (m < B) {
+                const int n = n0 + 32 * c;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = fmaxf(__uint_as_float(r[j]) + __ldg(&bias[n + j]), 0.f);
+                if (c32) {
+                    float4 *dst = reinterpret_cast<float4 *>(c32 + (size_t)m * ldc + n);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (planes_out) {
+                    uint32_t p0[16], p1[16], p2[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        __nv_bfloat16 a0, b0, c0, a1, b1, c1;
+                        split3(v[2 * j], a0, b0, c0);
+                        split3(v[2 * j + 1], a1, b1, c1);
+                        p0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
+                        p1[j] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                        p2[j] = (uint32_t)__bfloat16_as_ushort(c0) | ((uint32_t)__bfloat16_as_ushort(c1) << 16);
+                    }
+                    const size_t plane = (size_t)Mpad * ld_out;
+                    uint4 *d0 = reinterpret_cast<uint4 *>(planes_out + (size_t)m * ld_out + n);
+                    uint4 *d1 = reinterpret_cast<uint4 *>(planes_out + plane + (size_t)m * ld_out + n);
+                    uint4 *d2 = reinterpret_cast<uint4 *>(planes_out + 2 * plane + (size_t)m * ld_out + n);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        d0[j] = make_uint4(p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+                        d1[j] = make_uint4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+                        d2[j] = make_uint4(p2[4 * j], p2[4 * j + 1], p2[4 * j + 2], p2[4 * j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_BN));
+    }
+}
+
+// float32 [B, ld_in] -> three bf16 planes [3][Mpad][ld_out] (columns >= K zero filled)
+__global__ void k_split_planes(const float *__restrict__ in, int ld_in, int K, int B, int Mpad,
+                               __nv_bfloat16 *__restrict__ out, int ld_out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)Mpad * ld_out;
+    if (i >= total) return;
+    int m = (int)(i / ld_out), k = (int)(i - (size_t)m * ld_out);
+    float x = (m < B && k < K && k < ld_in) ? in[(size_t)m * ld_in + k] : 0.f;
+    __nv_bfloat16 a, b, c;
+    split3(x, a, b, c);
+    out[i] = a;
+    out[total + i] = b;
+    out[2 * total + i] = c;
+}
+
+// ------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (row pitch ld elements), box = 64 columns x 128 rows, 128 B swizzle.
+static int make_map(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, uint64_t ld)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { crlk_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CRLK_E_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    cuuint32_t box[2] = {TC_BK, TC_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { crlk_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CRLK_E_CUDA; }
+    return CRLK_OK;
+}
+
+static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
+
+struct TcLayer {
+    __nv_bfloat16 *d_w;   // [3][N][Kp]
+    CUtensorMap map_w;
+    int N, K, Kp;
+};
+
+struct CrlkPolicyTc {
+    int n_hidden;
+    TcLayer layer[8];
+    int max_width;        // widest activation (elements), multiple of 64
+};
+
+static void host_split3(float x, uint16_t &a, uint16_t &b, uint16_t &c)
+{
+    auto rn = [](float f) -> uint16_t {
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+        u += 0x7fffu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto up = [](uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; };
+    a = rn(x);
+    float r1 = x - up(a);
+    b = rn(r1);
+    float r2 = r1 - up(b);
+    c = rn(r2);
+}
+
+// Can the hidden layers of this actor run on the tensor-core path?
+int crlk_tc_supported(const int *dims, int n_layers)
+{
+    for (int i = 0; i < n_layers - 1; i++)
+        if (dims[i + 1] % TC_BN != 0) return 0;
+    return 1;
+}
+
+int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_host, CrlkPolicyTc **out)
+{
+    CrlkPolicyTc *t = new CrlkPolicyTc();
+    memset(t, 0, sizeof *t);
+    t->n_hidden = n_layers - 1;
+    t->max_width = 0;
+    for (int i = 0; i < t->n_hidden; i++) {
+        TcLayer &L = t->layer[i];
+        L.N = dims[i + 1]; L.K = dims[i]; L.Kp = rup(dims[i], TC_BK);
+        if (L.Kp > t->max_width) t->max_width = L.Kp;
+        if (L.N > t->max_width) t->max_width = L.N;
+        size_t plane = (size_t)L.N * L.Kp;
+        uint16_t *h = (uint16_t *)calloc(3 * plane, sizeof(uint16_t));
+        for (int n = 0; n < L.N; n++)
+            for (int k = 0; k < L.K; k++) {
+                uint16_t a, b, c;
+                host_split3(weights_host[i][(size_t)n * L.K + k], a, b, c);
+                h[(size_t)n * L.Kp + k] = a;
+                h[plane + (size_t)n * L.Kp + k] = b;
+                h[2 * plane + (size_t)n * L.Kp + k] = c;
+            }
+        CRLK_CUDA(cudaMalloc(&L.d_w, 3 * plane * sizeof(uint16_t)));
+        CRLK_CUDA(cudaMemcpy(L.d_w, h, 3 * plane * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        free(h);
+        int rc = make_map(&L.map_w, L.d_w, 3ull * L.N, L.Kp, L.Kp);
+        if (rc) return rc;
+    }
+    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    *out = t;
+    return CRLK_OK;
+}
+
+void crlk_tc_destroy(CrlkPolicyTc *t)
+{
+    if (!t) return;
+    for (int i = 0; i < t->n_hidden; i++)
+        if (t->layer[i].d_w) cudaFree(t->layer[i].d_w);
+    delete t;
+}
+
+size_t crlk_tc_workspace_bytes(const CrlkPolicyTc *t, int B)
+{
+    size_t Mpad = (size_t)rup(B, TC_BM);
+    size_t planes = 3 * Mpad * t->max_width * sizeof(uint16_t);
+    size_t last = Mpad * t->layer[t->n_hidden - 1].N * sizeof(float);
+    return 2 * planes + last + 1024;
+}
+
+// Hidden layers: obs (float32) -> float32 activations of the last hidden layer.
+// Returns the pointer / leading dimension of that activation through out/ld_out.
+int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, int B, void *workspace,
+                           const float *const *d_bias, const float **out, int *ld_out, cudaStream_t st)
+{
+    const int Mpad = rup(B, TC_BM);
+    uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    size_t planes_bytes = 3 * (size_t)Mpad * t->max_width * sizeof(uint16_t);
+    __nv_bfloat16 *pl[2] = {(__nv_bfloat16 *)ws, (__nv_bfloat16 *)(ws + planes_bytes)};
+    float *last = (float *)(ws + 2 * planes_bytes);
+    // layer-0 operand planes from the float32 observation
+    {
+        const TcLayer &L = t->layer[0];
+        size_t total = (size_t)Mpad * L.Kp;
+        k_split_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, ld_obs, L.K, B, Mpad, pl[0], L.Kp);
+        CRLK_LAUNCH_CHECK();
+    }
+    for (int i = 0; i < t->n_hidden; i++) {
+        const TcLayer &L = t->layer[i];
+        CUtensorMap mapA;
+        int rc = make_map(&mapA, pl[i & 1], 3ull * Mpad, L.Kp, L.Kp);
+        if (rc) return rc;
+        bool is_last = (i == t->n_hidden - 1);
+        dim3 grid(L.N / TC_BN, Mpad / TC_BM);
+        k_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
+            mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
+            is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
+        CRLK_LAUNCH_CHECK();
+    }
+    *out = last;
+    *ld_out = t->layer[t->n_hidden - 1].N;
+    return CRLK_OK;
+}

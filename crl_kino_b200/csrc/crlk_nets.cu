@@ -1,6 +1,7 @@
 // libcrlk.so -- learned steering: actor MLP, estimator/classifier CNN and the
 // RL extend loop (float32; FMA contraction allowed, tolerance-based parity).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "crlk_device.cuh"
 
@@ -45,6 +46,11 @@ extern "C" int crlk_policy_create(int32_t n_layers, const int32_t *dims,
         p->bias[k] = (low[k] + high[k]) / 2.0f;
         p->scale[k] = (high[k] - low[k]) / 2.0f;
     }
+    p->tc = nullptr;
+    if (crlk_tc_supported(p->dims, n_layers)) {
+        int rc2 = crlk_tc_create(p->dims, n_layers, weights_host, &p->tc);
+        if (rc2) return rc2;
+    }
     *out = p;
     return CRLK_OK;
 }
@@ -56,6 +62,7 @@ extern "C" int crlk_policy_destroy(CrlkPolicy *p)
         if (p->d_w[i]) cudaFree(p->d_w[i]);
         if (p->d_b[i]) cudaFree(p->d_b[i]);
     }
+    crlk_tc_destroy(p->tc);
     delete p;
     return CRLK_OK;
 }
@@ -63,7 +70,9 @@ extern "C" int crlk_policy_destroy(CrlkPolicy *p)
 extern "C" int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B)
 {
     if (!p || B <= 0) return 0;
-    return (int64_t)sizeof(float) * 2 * (int64_t)round_up(B, 64) * p->max_dim + 256;
+    int64_t simt = (int64_t)sizeof(float) * 2 * (int64_t)round_up(B, 64) * p->max_dim + 256;
+    int64_t tc = p->tc ? (int64_t)crlk_tc_workspace_bytes(p->tc, B) : 0;
+    return simt > tc ? simt : tc;
 }
 
 // C[B, N] = relu(A[B, lda] . W[N, K]^T + b), K % 16 == 0, rows of A/W 16-byte aligned.
@@ -152,22 +161,29 @@ static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs
                                cudaStream_t st)
 {
     const int L = p->n_layers;
-    float *buf[2];
-    size_t half = (size_t)round_up(B, 64) * p->max_dim;
-    buf[0] = (float *)workspace;
-    buf[1] = buf[0] + half;
     const float *in = obs;
     int ld_in = ld_obs;
-    for (int i = 0; i < L - 1; i++) {
-        int N = p->dims[i + 1];
-        int ldc = p->kpad[i + 1];
-        float *outb = buf[i & 1];
-        dim3 grid((N + GM_BN - 1) / GM_BN, (B + GM_BM - 1) / GM_BM);
-        k_linear_relu<<<grid, 256, 0, st>>>(in, ld_in, p->d_w[i], p->kpad[i], p->d_b[i], outb, ldc, B, N,
-                                           nullptr);
-        CRLK_LAUNCH_CHECK();
-        in = outb;
-        ld_in = ldc;
+    static const bool force_simt = getenv("CRLK_MLP_SIMT") != nullptr;   // A/B switch for the tests
+    if (p->tc && !force_simt) {
+        // hidden layers on the tensor cores (tcgen05, bf16 x 3 split, float32 accumulate)
+        int rc = crlk_tc_hidden_forward(p->tc, obs, ld_obs, B, workspace, p->d_b, &in, &ld_in, st);
+        if (rc) return rc;
+    } else {
+        float *buf[2];
+        size_t half = (size_t)round_up(B, 64) * p->max_dim;
+        buf[0] = (float *)workspace;
+        buf[1] = buf[0] + half;
+        for (int i = 0; i < L - 1; i++) {
+            int N = p->dims[i + 1];
+            int ldc = p->kpad[i + 1];
+            float *outb = buf[i & 1];
+            dim3 grid((N + GM_BN - 1) / GM_BN, (B + GM_BM - 1) / GM_BM);
+            k_linear_relu<<<grid, 256, 0, st>>>(in, ld_in, p->d_w[i], p->kpad[i], p->d_b[i], outb, ldc, B, N,
+                                               nullptr);
+            CRLK_LAUNCH_CHECK();
+            in = outb;
+            ld_in = ldc;
+        }
     }
     HeadP hp;
     for (int k = 0; k < 2; k++) {
