@@ -24,6 +24,19 @@ class DwaParams(C.Structure):
                 ("skip", C.c_int32), ("use_clearance", C.c_int32)]
 
 
+class ForestView(C.Structure):
+    _fields_ = [("x64", C.c_void_p), ("y64", C.c_void_p), ("x32", C.c_void_p), ("y32", C.c_void_p),
+                ("states", C.c_void_p), ("parent", C.c_void_p), ("n_nodes", C.c_void_p),
+                ("stride", C.c_int64), ("pool", C.c_void_p), ("seg_off", C.c_void_p),
+                ("seg_len", C.c_void_p), ("seg_flag", C.c_void_p), ("pool_used", C.c_void_p),
+                ("pool_cap", C.c_int64)]
+
+
+class ExtendView(C.Structure):
+    _fields_ = [("path", C.c_void_p), ("n_steps", C.c_void_p), ("status", C.c_void_p),
+                ("node_step", C.c_void_p), ("n_nodes", C.c_void_p)]
+
+
 class ExtendParams(C.Structure):
     _fields_ = [("n_max_extend", C.c_int32), ("n_tree", C.c_int32), ("step_dt", C.c_double),
                 ("reach_radius", C.c_double)]
@@ -57,6 +70,8 @@ PROTOTYPES = {
     "crlk_nearest_scratch_bytes": (I64, [I32, I32]),
     "crlk_extend_dwa": (C.c_int, [P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P]),
     "crlk_gather_rows": (C.c_int, [P, I64, I32, P, I32, P, P]),
+    "crlk_rrt_select": (C.c_int, [P, P, I32, I32, F64, F64, P, P, P, P]),
+    "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),
     "crlk_policy_destroy": (C.c_int, [P]),
     "crlk_policy_forward": (C.c_int, [P, P, I32, P, F32, I32, P, P, P]),

@@ -14,6 +14,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "--expt-extended-lambda", "--expt-re
 # (source, extra flags).  The float64 planner kernels must not contract a*b+c.
 EXTRA_DEFS = ["-D" + d for d in os.environ.get("CRLK_DEFS", "").split() if d]
 UNITS = [("crlk_kernels.cu", ["--fmad=false"] + EXTRA_DEFS),
+         ("crlk_planner.cu", ["--fmad=false"]),
          ("crlk_nets.cu", []),
          ("crlk_mlp_tc.cu", [])]
 

@@ -114,3 +114,164 @@ class BatchedExtender:
 
     def d2h_bytes(self):
         return sum(h.numel() * h.element_size() for h in self._h_out.values())
+
+
+class BatchedRRT:
+    """Q independent RRT.planning() runs (rrt.py:51-89) advanced in lock step,
+    trees resident in HBM.  One round = one sample per unfinished query:
+    validity check + nearest node + acceptance (rrt.py:64-69), one extension
+    toward the sample (rrt.py:72), node append + goal test (rrt.py:74-77), and
+    the steer-to-goal retry (rrt.py:78-83).  Sampling stays on the host as
+    pre-drawn per-query streams (the reference's RNG order cannot be reproduced
+    across queries); every query consumes its own stream in order, so its tree
+    is the one the sequential planner would build from the same stream.
+
+    steering: 'dwa' (RRT) or 'rl' (RRT_RL with `policy`, optional noise stream).
+    """
+
+    def __init__(self, env, starts, goals, max_iter=500, dwa=None, policy=None, eps=0.0,
+                 keep_paths=True, node_capacity=None, with_f32=True):
+        import ctypes as C
+        from .._lib import ExtendView, ForestView
+        self.env = env
+        self.Q = Q = len(starts)
+        self.max_iter = max_iter
+        self.policy = policy
+        self.eps = eps
+        if dwa is None and policy is None:
+            from ..policy.dwa import DWA
+            dwa = DWA(env)
+            dwa.set_dwa(dt=0.2, v_res=0.02)          # rrt.py:39-40
+        self.dwa = dwa
+        self.xp = ops.extend_params()
+        self.per = self.xp.n_max_extend // self.xp.n_tree + 1
+        d = ops.dev()
+        cap = node_capacity or (2 * (self.per - 1) * max_iter + 1)
+        self.forest = f = Forest(Q, cap, d, with_f32=with_f32)
+        self.starts = ops.as_dev(starts).reshape(Q, 5)
+        self.goals = ops.as_dev(goals).reshape(Q, 5)
+        v, _, _ = ops.valid_state(env.handle, torch.cat([self.starts, self.goals]))
+        assert bool(v.all().item()), "The start or goal states are not valid"      # rrt.py:93
+        f.fill(self.starts.reshape(Q, 1, 5))
+        self.keep_paths = keep_paths
+        self.pool_cap = self.xp.n_max_extend * 2 * max_iter if keep_paths else 0
+        if keep_paths:
+            self.pool = torch.zeros(Q, self.pool_cap, 5, dtype=torch.float64, device=d)
+            self.seg_off = torch.zeros(Q, cap, dtype=torch.int32, device=d)
+            self.seg_len = torch.zeros(Q, cap, dtype=torch.int32, device=d)
+            self.seg_flag = torch.zeros(Q, cap, dtype=torch.uint8, device=d)
+            self.pool_used = torch.zeros(Q, dtype=torch.int32, device=d)
+        i32 = dict(dtype=torch.int32, device=d)
+        u8 = dict(dtype=torch.uint8, device=d)
+        self.iters = torch.zeros(Q, **i32)
+        self.done = torch.zeros(Q, **u8)
+        self.reached = torch.zeros(Q, **u8)
+        self.active = torch.zeros(Q, **u8)
+        self.retry_active = torch.zeros(Q, **u8)
+        self.retry_from = torch.zeros(Q, 5, dtype=torch.float64, device=d)
+        self.retry_parent = torch.zeros(Q, **i32)
+        self.overflow = torch.zeros(1, **i32)
+        self.cursor = torch.zeros(Q, **i32)
+        self.sample = torch.zeros(Q, 5, dtype=torch.float64, device=d)
+        self.from_states = torch.zeros(Q, 5, dtype=torch.float64, device=d)
+        self.stats = torch.zeros(4, dtype=torch.int64, device=d)
+        self.out = [None, None]
+        self.rounds = 0
+        self.coord_bound = env.coord_bound()
+        self.first_has_start = 0 if policy is None else 1
+        fv = ForestView(f.x.data_ptr(), f.y.data_ptr(), f.x32.data_ptr() if f.x32 is not None else None,
+                        f.y32.data_ptr() if f.y32 is not None else None, f.states.data_ptr(),
+                        f.parent.data_ptr(), f.n_nodes.data_ptr(), cap,
+                        self.pool.data_ptr() if keep_paths else None,
+                        self.seg_off.data_ptr() if keep_paths else None,
+                        self.seg_len.data_ptr() if keep_paths else None,
+                        self.seg_flag.data_ptr() if keep_paths else None,
+                        self.pool_used.data_ptr() if keep_paths else None, self.pool_cap)
+        self._fv = fv
+        self._C = C
+        self._ExtendView = ExtendView
+        self.noise = None
+
+    # ---- one extension pass ------------------------------------------------
+    def _extend(self, slot, from_states, targets, active):
+        if self.policy is None:
+            self.out[slot] = ops.extend_dwa(self.env.handle, self.dwa.params(), self.xp, from_states, targets,
+                                            active=active, out=self.out[slot], stats=self.stats)
+        else:
+            self.out[slot] = ops.extend_rl(self.env.handle, self.policy.actor.handle, self.xp, from_states,
+                                           targets, self.noise, self.eps, active=active)
+        return self.out[slot]
+
+    def _append(self, out, parent_idx, active, primary):
+        from .._lib import check, lib
+        C = self._C
+        ev = self._ExtendView(out["path"].data_ptr(), out["n_steps"].data_ptr(), out["status"].data_ptr(),
+                              out["node_step"].data_ptr(), out["n_nodes"].data_ptr())
+        p = lambda t: C.c_void_p(t.data_ptr())
+        check(lib().crlk_rrt_append(C.byref(self._fv), C.byref(ev), p(parent_idx), p(active), p(self.goals),
+                                    self.Q, self.xp.n_max_extend, self.xp.n_tree, self.first_has_start,
+                                    1 if primary else 0, self.max_iter, 1.0, 5.0, p(self.iters), p(self.done),
+                                    p(self.reached), p(self.retry_active), p(self.retry_from),
+                                    p(self.retry_parent), p(self.overflow), ops._stream()))
+
+    def round(self, samples):
+        """Advance every unfinished query by one sample (samples: CUDA float64 [Q, 5])."""
+        from .._lib import check, lib
+        C = self._C
+        f = self.forest
+        p = lambda t: C.c_void_p(t.data_ptr())
+        valid, _, _ = ops.valid_state(self.env.handle, samples)                       # rrt.py:66
+        idx, dist, _ = ops.nearest(f.x, f.y, f.n_nodes, samples, x32=f.x32, y32=f.y32,
+                                   coord_bound=self.coord_bound)                       # rrt.py:68
+        check(lib().crlk_rrt_select(p(valid), p(dist), self.Q, self.max_iter, 1.0, 20.0, p(self.done),
+                                    p(self.iters), p(self.active), ops._stream()))      # rrt.py:69
+        ops.gather_rows(f.states, idx, out=self.from_states)                          # rrt.py:70
+        out = self._extend(0, self.from_states, samples, self.active)                 # rrt.py:72
+        self._append(out, idx, self.active, True)                                     # rrt.py:74-79
+        out2 = self._extend(1, self.retry_from, self.goals, self.retry_active)        # rrt.py:80
+        self._append(out2, self.retry_parent, self.retry_active, False)               # rrt.py:81-83
+        self.rounds += 1
+
+    def plan(self, streams, check_every=8, max_rounds=None):
+        """streams: float64 [Q, S, 5] pre-drawn samples per query (host or device).
+        Runs rounds until every query is done or its stream is exhausted."""
+        streams = ops.as_dev(streams)
+        S = streams.shape[1]
+        max_rounds = min(S, max_rounds or S)
+        step = torch.zeros(self.Q, dtype=torch.int32, device=streams.device)
+        for r in range(max_rounds):
+            step.fill_(r)
+            ops.gather_rows(streams, step, out=self.sample)
+            self.round(self.sample)
+            if (r + 1) % check_every == 0 and bool(self.done.all().item()):
+                break
+        torch.cuda.synchronize()
+        if int(self.overflow.item()):
+            raise RuntimeError(f"{int(self.overflow.item())} trees ran out of node/path capacity")
+        self.samples_used = r + 1
+        return self.reached.cpu().numpy().astype(bool)
+
+    # ---- results ---------------------------------------------------------------
+    def tree(self, q):
+        """(states [n,5], parents [n]) of query q as numpy arrays."""
+        n = int(self.forest.n_nodes[q].item())
+        return self.forest.states[q, :n].cpu().numpy(), self.forest.parent[q, :n].cpu().numpy()
+
+    def final_course(self, q, goal_ind=-1):
+        """generate_final_course (rrt.py:137-144) for query q."""
+        assert self.keep_paths, "paths were not kept"
+        states, parents = self.tree(q)
+        n = len(states)
+        off = self.seg_off[q, :n].cpu().numpy()
+        ln = self.seg_len[q, :n].cpu().numpy()
+        flag = self.seg_flag[q, :n].cpu().numpy()
+        used = int(self.pool_used[q].item())
+        pool = self.pool[q, :used].cpu().numpy()
+        node = goal_ind % n
+        path = []
+        while parents[node] >= 0:
+            seg = [pool[off[node] + i] for i in range(ln[node])]
+            full = ([states[parents[node]]] if flag[node] else []) + seg     # Node.path
+            path = full[1:] + path
+            node = parents[node]
+        return [states[node]] + path

@@ -220,6 +220,51 @@ int crlk_estimator_destroy(CrlkEstimator *e);
 int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, int32_t ld_obs, int32_t B,
                            float *est, float *prob, void *stream);
 
+/* ---- planner bookkeeping on the device: RRT.planning (planner/rrt.py:51-89) ---- */
+
+/* Q trees in SoA form (device pointers; tree q owns elements [q*stride, (q+1)*stride)).
+ * The optional path pool keeps, per node, the executed states between its parent
+ * and itself (Node.path, rrt.py:120) for generate_final_course (rrt.py:137-144). */
+typedef struct {
+    double *x64, *y64;       /* [Q x stride] */
+    float *x32, *y32;        /* [Q x stride] float32 copies scanned by crlk_nearest (nullable) */
+    double *states;          /* [Q x stride x 5] */
+    int32_t *parent;         /* [Q x stride] */
+    int32_t *n_nodes;        /* [Q] */
+    int64_t stride;          /* node capacity per tree */
+    double *pool;            /* [Q x pool_cap x 5] (nullable: paths are not kept) */
+    int32_t *seg_off, *seg_len;   /* [Q x stride] segment of each node inside its tree's pool */
+    uint8_t *seg_flag;       /* [Q x stride] 1 = Node.path starts with the parent's state */
+    int32_t *pool_used;      /* [Q] */
+    int64_t pool_cap;
+} CrlkForestView;
+
+/* outputs of crlk_extend_dwa / crlk_extend_rl, as consumed by crlk_rrt_append */
+typedef struct {
+    const double *path;
+    const int32_t *n_steps, *status, *node_step, *n_nodes;
+} CrlkExtendView;
+
+/* Sample acceptance of rrt.py:64-69 for one candidate per query:
+ * active[q] = !done && iters < max_iter && valid && d_min <= dist < d_max;
+ * accepted queries count one iteration (iters[q] += 1). */
+int crlk_rrt_select(const uint8_t *valid, const double *dist, int32_t Q, int32_t max_iter, double d_min,
+                    double d_max, const uint8_t *done, int32_t *iters, uint8_t *active, void *stream);
+
+/* Append the nodes of one extension per active query (rrt.py:125-134), run the
+ * goal test on the tree's last node (rrt.py:75, :81; radius goal_radius) and --
+ * when primary != 0 -- choose the new node nearest to the goal for the retry
+ * extension (rrt.py:78-80: cost < retry_radius).  first_has_start: 0 for the DWA
+ * steer (the first segment's Node.path lacks the start state, rrt.py:102-104),
+ * 1 for the RL steer (rrt_rl.py:27).  overflow (dev i32[1]) counts trees that
+ * ran out of node or pool capacity (those queries are stopped and reported). */
+int crlk_rrt_append(const CrlkForestView *forest, const CrlkExtendView *ext, const int32_t *parent_idx,
+                    const uint8_t *active, const double *goals, int32_t Q, int32_t n_max_extend,
+                    int32_t n_tree, int32_t first_has_start, int32_t primary, int32_t max_iter,
+                    double goal_radius, double retry_radius, const int32_t *iters, uint8_t *done,
+                    uint8_t *reached, uint8_t *retry_active, double *retry_from, int32_t *retry_parent,
+                    int32_t *overflow, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
