@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--cells", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="extensions in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the planning / nearest / MLP side measurements")
+    ap.add_argument("--plan-iters", type=int, default=100, help="max_iter of the planning-queries/s leg")
     return ap.parse_args()
 
 
@@ -58,7 +60,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -120,6 +122,118 @@ def build_workload(args, env, rank):
             batches[b, ok] = cand[b, ok]
             need[b, ok] = False
     return forest, batches
+
+
+def timed(fn, n, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def planning_leg(args, env, dwa, rank):
+    """Planning queries/s: Q full RRT.planning runs (max_iter = --plan-iters) in lock step."""
+    import torch
+    from crl_kino_b200.planner.batched import BatchedRRT
+    from crl_kino_b200.workloads import query_pairs, sample_stream
+    Q = args.queries
+
+    def clearance(c):
+        return env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
+    starts, goals = query_pairs(clearance, Q, seed=7 + rank)
+    sb = env.get_bounds()["state_bounds"]
+    S = args.plan_iters * 4 + 32
+    rng = np.random.default_rng(300 + rank)
+    streams = rng.uniform(sb[:, 0], sb[:, 1], (Q, S, 5))
+    pick = rng.integers(0, 101, (Q, S)) <= 5                      # goal bias of rrt.py:147
+    streams[pick] = np.repeat(goals[:, None, :], S, 1)[pick]
+    dstreams = torch.as_tensor(streams).cuda()
+    p = BatchedRRT(env, starts, goals, max_iter=args.plan_iters, dwa=dwa, keep_paths=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reached = p.plan(dstreams, check_every=16)
+    dt = time.perf_counter() - t0
+    st = p.stats.cpu().numpy()
+    return {"queries": Q, "seconds": dt, "queries_per_sec": Q / dt, "max_iter": args.plan_iters,
+            "rounds": p.samples_used, "reached_frac": float(reached.mean()),
+            "extensions": int(st[0]), "extensions_per_sec": float(st[0]) / dt,
+            "mean_nodes": float(p.forest.n_nodes.double().mean().item()),
+            "inputs": (starts, goals, streams)}
+
+
+def _cpu_plan_one(a):
+    rects, start, goal, stream, iters = a
+    from crl_kino_b200.workloads import DENSE_DWA
+    from oracle import oracle as orc
+    o = orc.Env()
+    o.set_obs(rects)
+    p = orc.PlannerPort(o, max_iter=iters, dwa_kwargs=DENSE_DWA)
+    p.set_start_and_goal(start, goal)
+    p.planning(iter(stream))
+    return p.n_extend_calls, bool(p.reach_exactly)
+
+
+def cpu_planning(rects, inputs, iters, n, cores):
+    import multiprocessing as mp
+    starts, goals, streams = inputs
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_plan_one, [(rects, starts[q], goals[q], streams[q], iters) for q in range(n)])
+    dt = time.perf_counter() - t0
+    return {"queries_per_sec": n / dt, "queries": n, "seconds": dt, "cores": cores, "kind": "port",
+            "extensions": int(sum(r[0] for r in res))}
+
+
+def nearest_roofline(peaks):
+    """K3 at cfg5 tree size: 100,000-node trees, float32 SoA scan (8 B per node)."""
+    import torch
+    from crl_kino_b200 import ops
+    Q, N = 1024, 100000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.rand(Q, N, generator=g, device="cuda", dtype=torch.float64) * 40 - 20)
+    y = (torch.rand(Q, N, generator=g, device="cuda", dtype=torch.float64) * 40 - 20)
+    x32, y32 = x.float(), y.float()
+    n = torch.full((Q,), N, dtype=torch.int32, device="cuda")
+    t = (torch.rand(Q, 2, generator=g, device="cuda", dtype=torch.float64) * 40 - 20)
+    ms = timed(lambda: ops.nearest(x, y, n, t, x32=x32, y32=y32, coord_bound=22.0), 10)
+    algo = 8.0 * Q * N
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = algo / (ms * 1e-3) / 1e9
+    return {"kernel": "k_nearest", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "ms": ms,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "workload": f"{Q} trees x {N} nodes (819 MB of float32 coordinates, > L2), one target each",
+            "nodes_per_sec": Q * N / (ms * 1e-3)}
+
+
+def mlp_roofline(peaks):
+    """K4: actor MLP 733-1024-512-512-512-2 at B = 8192 on tcgen05 (bf16 x 3 split)."""
+    import torch
+    from crl_kino_b200 import ops
+    from crl_kino_b200.env import DifferentialDriveGym
+    from crl_kino_b200.policy.rl_policy import load_policy
+    B = 8192
+    pol = load_policy(DifferentialDriveGym(), [1024, 512, 512, 512], None, seed=0)
+    obs = torch.zeros(B, ops.OBS_LD, dtype=torch.float32, device="cuda")
+    obs[:, :733] = torch.rand(B, 733, device="cuda")
+    h = pol.actor.handle
+    ms = timed(lambda: ops.policy_forward(h, obs), 20)
+    algo = 3600384.0 * B
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    ach = algo / (ms * 1e-3) / 1e12
+    return {"kernel": "k_gemm_bf16x3 (+ split, head)", "bound": "tensor", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms": ms,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
+            "note": "algorithmic float32 FLOP (3,600,384 per sample); the kernel issues 6 bf16 MMAs per "
+                    "float32 product pair (bf16 x 3 operand split) to keep float32-level accuracy, so the "
+                    "tensor pipe does 6x this work", "policy_samples_per_sec": B / (ms * 1e-3)}
 
 
 def run_ours(args):
@@ -186,14 +300,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
 
+    plan = None
+    if not args.no_extra:
+        plan = planning_leg(args, env, dwa, rank)
+
     # ---- reduce over ranks (max time, summed work) ----------------------------------
-    red = torch.tensor([t_total_ms, t_e2e, t_ext], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([n_ext, n_ctrl, n_roll], dtype=torch.float64, device="cuda")
+    red = torch.tensor([t_total_ms, t_e2e, t_ext, plan["seconds"] if plan else 0.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([n_ext, n_ctrl, n_roll, plan["queries"] if plan else 0.0, plan["extensions"] if plan else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_total_ms, t_e2e, t_ext_max = [float(x) for x in red.cpu()]
-    tot_ext, tot_ctrl, tot_roll = [float(x) for x in cnt.cpu()]
+    t_total_ms, t_e2e, t_ext_max, t_plan = [float(x) for x in red.cpu()]
+    tot_ext, tot_ctrl, tot_roll, tot_q, tot_pext = [float(x) for x in cnt.cpu()]
 
     line = None
     if rank == 0:
@@ -236,8 +354,21 @@ def run_ours(args):
                                  "FLOP are far fewer"},
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if plan is not None:
+            line["planning"] = {"queries_per_sec": tot_q / t_plan, "unit": "queries/s", "queries": int(tot_q),
+                                "max_iter": plan["max_iter"], "rounds": plan["rounds"],
+                                "reached_frac_rank0": plan["reached_frac"], "mean_nodes_rank0": plan["mean_nodes"],
+                                "extensions_per_sec": tot_pext / t_plan,
+                                "note": "Q full RRT.planning runs in lock step (BatchedRRT), trees and sample "
+                                        "streams resident in HBM; wall clock incl. host round control"}
+            line["rooflines_other_kernels"] = [nearest_roofline(peaks), mlp_roofline(peaks)]
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, rects, forest, batches[W])
+            if plan is not None:
+                from oracle import oracle as orc
+                cores = orc.cpu_count()
+                line["planning"]["cpu_baseline"] = cpu_planning(rects, plan["inputs"], plan["max_iter"],
+                                                                min(args.queries, cores), cores)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -265,7 +396,7 @@ def cpu_sample_run(rects, tree_states, samples, n, threads):
 def cpu_baseline(args, rects, forest, samples):
     from oracle import oracle as orc
     cores = orc.cpu_count()
-    n = args.cpu_sample or min(args.queries, max(8 * cores, 64))
+    n = args.cpu_sample or min(args.queries, max(64 * cores, 256))
     ts = forest.states[:n].cpu().numpy()
     v, dt, steps = cpu_sample_run(rects, ts, samples, n, cores)
     return {"value": v, "unit": "extensions/s", "cores": cores, "kind": "port",
@@ -286,7 +417,7 @@ def run_reference(args):
     o.set_obs(rects)
     cores = orc.cpu_count()
     rng = np.random.default_rng(100)
-    n = args.cpu_sample or max(8 * cores, 64)
+    n = args.cpu_sample or min(args.queries, max(16 * cores, 128))
     N = args.tree_nodes
     K, W = args.steps, args.warmup
     # same construction as the GPU arm, on the sample only
