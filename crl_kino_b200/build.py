@@ -16,7 +16,7 @@ EXTRA_DEFS = ["-D" + d for d in os.environ.get("CRLK_DEFS", "").split() if d]
 UNITS = [("crlk_kernels.cu", ["--fmad=false"] + EXTRA_DEFS),
          ("crlk_planner.cu", ["--fmad=false"]),
          ("crlk_nets.cu", []),
-         ("crlk_mlp_tc.cu", [])]
+         ("crlk_mlp_tc.cu", EXTRA_DEFS)]
 
 
 def _nvcc():

@@ -100,6 +100,8 @@ int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x);
     } while (0)
 
 int crlk_require_device(void);
+int crlk_local_obs_masked(const CrlkEnv *env, const double *states, const double *goals, int32_t goal_stride,
+                          int32_t B, float *obs32, int32_t ld32, const int *skip, void *stream);
 
 // tensor-core MLP (crlk_mlp_tc.cu)
 struct CrlkPolicyTc;

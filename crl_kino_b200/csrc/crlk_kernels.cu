@@ -56,6 +56,10 @@ int crlk_count_loop_le(double limit, double step)
 
 // ------------------------------------------------------------------- handles
 
+#ifndef CRLK_GRID_CELL
+#define CRLK_GRID_CELL 0.5f   // obstacle grid pitch in metres (tuned on the cfg4 map, see profiles/)
+#endif
+
 static void fill_envp(const CrlkEnvParams *in, EnvP *p)
 {
     p->max_v = in->max_v; p->min_v = in->min_v; p->max_w = in->max_w;
@@ -80,7 +84,7 @@ static int build_grid(CrlkEnv *env, const float *r, int M)
         x1 = fmaxf(x1, r[4 * i + 2]); y1 = fmaxf(y1, r[4 * i + 3]);
     }
     float ext = fmaxf(x1 - x0, y1 - y0);
-    float cell = fmaxf(2.0f, ext / 128.0f);
+    float cell = fmaxf(CRLK_GRID_CELL, ext / 256.0f);
     int ncx = (int)floorf((x1 - x0) / cell) + 1, ncy = (int)floorf((y1 - y0) / cell) + 1;
     float ginv = 1.0f / cell;
     auto cx = [&](float v) { return (int)fminf(fmaxf(floorf((v - x0) * ginv), 0.f), (float)(ncx - 1)); };
@@ -389,82 +393,65 @@ __device__ __forceinline__ double arange_at(double a0, double a1, double d, int 
     return (i == 0) ? a0 : (i == 1) ? a1 : a0 + (double)i * d;
 }
 
-// One CTA per observation: FP32 screen of the obstacle set against the local
-// window's bounding circle, then exact closed-interval tests (rigid.py:158-166).
+// One CTA per observation, three sample points per thread.  Each point is a
+// point query against the obstacle grid: only the lists of the cell(s) holding
+// the point are tested (closed intervals, rigid.py:158-166).  A point inside an
+// obstacle always falls in a cell of that obstacle's range because the cell
+// function is monotone, so the result equals the scan over all obstacles.
 __global__ void __launch_bounds__(256)
-k_local_obs(ObsGrid og, const float4 *__restrict__ rects, int M, const double *__restrict__ states,
+k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
             const double *__restrict__ goals, int goal_stride, int B, double *obs64, float *obs32,
-            int ld32, uint8_t *near_boundary)
+            int ld32, uint8_t *near_boundary, const int *__restrict__ skip)
 {
-    __shared__ float4 s_tile[OBS_TILE];
-    __shared__ int s_cnt;
     __shared__ int s_near;
     int b = blockIdx.x;
     if (b >= B) return;
+    if (skip && skip[b]) return;
     const double *st = states + 5 * (size_t)b;
     double x = st[0], y = st[1], th = st[2];
     double sn, cs;
     sincos(th, &sn, &cs);
-    // window centre in the body frame and its radius (+ slack)
-    double cbx = 0.5 * (og.ba0 + arange_at(og.ba0, og.ba1, og.bad, OBS_SIDE - 1));
-    double cby = 0.5 * (og.lr0 + arange_at(og.lr0, og.lr1, og.lrd, OBS_SIDE - 1));
-    double hx = arange_at(og.ba0, og.ba1, og.bad, OBS_SIDE - 1) - cbx;
-    double hy = arange_at(og.lr0, og.lr1, og.lrd, OBS_SIDE - 1) - cby;
-    float wcx = (float)((cs * cbx + (-sn) * cby) + x);
-    float wcy = (float)((sn * cbx + cs * cby) + y);
-    float rad = (float)sqrt(hx * hx + hy * hy) * 1.001f + 1e-3f;
-    float rad2 = rad * rad;
-
-    // this thread's sample points (3 per thread at 256 threads)
-    double pxs[3], pys[3];
-    bool occ[3] = {false, false, false};
+    if (threadIdx.x == 0) s_near = 0;
+    __syncthreads();
+    const float4 *__restrict__ rects = os.rects;
+    const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
     bool nearp = false;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         int p = threadIdx.x + k * 256;
+        if (p >= OBS_NPTS) break;
         int ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;
         double bx = arange_at(og.ba0, og.ba1, og.bad, ib);
         double by = arange_at(og.lr0, og.lr1, og.lrd, il);
-        pxs[k] = (cs * bx + (-sn) * by) + x;     // differential_gym.py:83 (wTb @ [bx, by, 1])
-        pys[k] = (sn * bx + cs * by) + y;
-    }
-    if (threadIdx.x == 0) s_near = 0;
-    for (int base = 0; base < M; base += OBS_TILE) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
-        for (int o = base + threadIdx.x; o < min(M, base + OBS_TILE); o += 256) {
-            float4 r = __ldg(&rects[o]);
-            if (aabb_center_d2(r, wcx, wcy) <= rad2) s_tile[atomicAdd(&s_cnt, 1)] = r;
-        }
-        __syncthreads();
-        int cnt = s_cnt;
-        for (int i = 0; i < cnt; i++) {
-            float4 r = s_tile[i];
-            double l = r.x, bo = r.y, rr = r.z, t = r.w;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                double px = pxs[k], py = pys[k];
-                bool in = (px >= l && px <= rr && py >= bo && py <= t);
-                occ[k] |= in;
-                bool in_big = (px >= l - OBS_NEAR_EPS && px <= rr + OBS_NEAR_EPS &&
-                               py >= bo - OBS_NEAR_EPS && py <= t + OBS_NEAR_EPS);
-                bool in_small = (px >= l + OBS_NEAR_EPS && px <= rr - OBS_NEAR_EPS &&
-                                 py >= bo + OBS_NEAR_EPS && py <= t - OBS_NEAR_EPS);
-                nearp |= (in_big && !in_small) && (threadIdx.x + k * 256 < OBS_NPTS);
+        double px = (cs * bx + (-sn) * by) + x;     // differential_gym.py:83 (wTb @ [bx, by, 1])
+        double py = (sn * bx + cs * by) + y;
+        // cells of the point (a 1e-6 halo so that the near-boundary report sees neighbours)
+        float fx0 = floorf(((float)px - 1e-6f - os.gx0) * os.ginv), fx1 = floorf(((float)px + 1e-6f - os.gx0) * os.ginv);
+        float fy0 = floorf(((float)py - 1e-6f - os.gy0) * os.ginv), fy1 = floorf(((float)py + 1e-6f - os.gy0) * os.ginv);
+        bool occ = false;
+        if (fx1 >= 0.f && fx0 <= hx && fy1 >= 0.f && fy0 <= hy) {     // else outside every obstacle
+            int cx0 = (int)fmaxf(fx0, 0.f), cx1 = (int)fminf(fx1, hx);
+            int cy0 = (int)fmaxf(fy0, 0.f), cy1 = (int)fminf(fy1, hy);
+            for (int cy = cy0; cy <= cy1; cy++) {
+                int s0 = __ldg(&os.cell_start[cy * os.ncx + cx0]);
+                int e0 = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
+                for (int i = s0; i < e0; i++) {
+                    float4 r = __ldg(&rects[__ldg(&os.cell_items[i])]);
+                    double l = r.x, bo = r.y, rr = r.z, t = r.w;
+                    occ |= (px >= l && px <= rr && py >= bo && py <= t);
+                    bool in_big = (px >= l - OBS_NEAR_EPS && px <= rr + OBS_NEAR_EPS &&
+                                   py >= bo - OBS_NEAR_EPS && py <= t + OBS_NEAR_EPS);
+                    bool in_small = (px >= l + OBS_NEAR_EPS && px <= rr - OBS_NEAR_EPS &&
+                                     py >= bo + OBS_NEAR_EPS && py <= t - OBS_NEAR_EPS);
+                    nearp |= in_big && !in_small;
+                }
             }
         }
+        double v = occ ? 0.0 : 1.0;
+        if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
+        if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
     }
     if (nearp) s_near = 1;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        int p = threadIdx.x + k * 256;
-        if (p < OBS_NPTS) {
-            double v = occ[k] ? 0.0 : 1.0;
-            if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
-            if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
-        }
-    }
     if (threadIdx.x == 0) {
         const double *g = goals + (size_t)goal_stride * b;
         double qx = g[0] - x, qy = g[1] - y;     // differential_gym.py:186-187 as R^T (g - t)
@@ -501,9 +488,21 @@ extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const do
     CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
     CRLK_REQUIRE(obs32 == nullptr || ld32 >= 4 + OBS_NPTS, "ld32 < 733");
     if (B == 0) return CRLK_OK;
-    k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->d_rects, env->M, states,
-                                                    goals, goal_stride, B, obs64, obs32, ld32,
-                                                    near_boundary);
+    k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                    goal_stride, B, obs64, obs32, ld32, near_boundary,
+                                                    nullptr);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// Same, skipping rows whose skip[b] != 0 (finished extensions of the RL steer loop).
+int crlk_local_obs_masked(const CrlkEnv *env, const double *states, const double *goals,
+                          int32_t goal_stride, int32_t B, float *obs32, int32_t ld32, const int *skip,
+                          void *stream)
+{
+    if (B == 0) return CRLK_OK;
+    k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                    goal_stride, B, nullptr, obs32, ld32, nullptr, skip);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

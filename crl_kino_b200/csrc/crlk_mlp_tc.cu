@@ -23,7 +23,12 @@
 #define TC_BM 128
 #define TC_BN 128
 #define TC_BK 64
-#define TC_STAGES 4
+#ifndef TC_STAGES
+#define TC_STAGES 3
+#endif
+#ifndef TC_MIN_BLOCKS
+#define TC_MIN_BLOCKS 2
+#endif
 #define TC_STAGE_BYTES (TC_BM * TC_BK * 2)     // 16 KB per operand tile
 #define TC_THREADS 256
 #define TC_SMEM_BYTES (2 * TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
@@ -134,7 +139,7 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16 &a, __nv_bfloat16 
 // ------------------------------------------------------------------ the GEMM
 
 // planes_out: [3][Mpad][ld_out] bf16 (nullable), c32: [B][ldc] float (nullable).
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TC_MIN_BLOCKS)
 k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
               int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
               __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc)

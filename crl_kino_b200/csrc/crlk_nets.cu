@@ -535,7 +535,7 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
     CRLK_LAUNCH_CHECK();
     for (int k = 1; k <= x.n_max_extend; k++) {
         // observation of the current state (rrt_rl.py:34 / differential_gym.py:141)
-        rc = crlk_local_obs(env, w.state, targets, 5, Q, nullptr, w.obs, 736, nullptr, stream);
+        rc = crlk_local_obs_masked(env, w.state, targets, 5, Q, w.obs, 736, w.done, stream);
         if (rc) return rc;
         // action = policy(obs) (rrt_rl.py:41)
         rc = policy_forward_impl(p, w.obs, 736, noise ? noise + (size_t)(k - 1) * 2 : nullptr,
