@@ -3,6 +3,7 @@
 // the reference's scalar Python/numpy code; fused operations are explicit.
 #include <math_constants.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "crlk_device.cuh"
 
@@ -1330,9 +1331,7 @@ k_nearest(const double *__restrict__ x64, const double *__restrict__ y64,
         };
         int hi4 = lo + ((hi - lo) & ~3);
         if (vec_ok) {
-            for (int i = lo + threadIdx.x * 4; i < hi4; i += NN_THREADS * 4) {
-                float4 vx = __ldcs(reinterpret_cast<const float4 *>(xs + i));
-                float4 vy = __ldcs(reinterpret_cast<const float4 *>(ys + i));
+            auto score4 = [&](float4 vx, float4 vy, int i) {
                 float dx0 = vx.x - ftx, dy0 = vy.x - fty, dx1 = vx.y - ftx, dy1 = vy.y - fty;
                 float dx2 = vx.z - ftx, dy2 = vy.z - fty, dx3 = vx.w - ftx, dy3 = vy.w - fty;
                 float e0 = dx0 * dx0 + dy0 * dy0, e1 = dx1 * dx1 + dy1 * dy1;
@@ -1342,6 +1341,28 @@ k_nearest(const double *__restrict__ x64, const double *__restrict__ y64,
                 if (em <= m2 * 1.001f + band_abs) {
                     visit(e0, i); visit(e1, i + 1); visit(e2, i + 2); visit(e3, i + 3);
                 }
+            };
+            const int stride4 = NN_THREADS * 4;
+            int i = lo + threadIdx.x * 4;
+            // four independent 16-byte loads per array in flight per thread
+            for (; i + 3 * stride4 < hi4; i += 4 * stride4) {
+                float4 x0 = __ldcs(reinterpret_cast<const float4 *>(xs + i));
+                float4 y0 = __ldcs(reinterpret_cast<const float4 *>(ys + i));
+                float4 x1 = __ldcs(reinterpret_cast<const float4 *>(xs + i + stride4));
+                float4 y1 = __ldcs(reinterpret_cast<const float4 *>(ys + i + stride4));
+                float4 x2 = __ldcs(reinterpret_cast<const float4 *>(xs + i + 2 * stride4));
+                float4 y2 = __ldcs(reinterpret_cast<const float4 *>(ys + i + 2 * stride4));
+                float4 x3 = __ldcs(reinterpret_cast<const float4 *>(xs + i + 3 * stride4));
+                float4 y3 = __ldcs(reinterpret_cast<const float4 *>(ys + i + 3 * stride4));
+                score4(x0, y0, i);
+                score4(x1, y1, i + stride4);
+                score4(x2, y2, i + 2 * stride4);
+                score4(x3, y3, i + 3 * stride4);
+            }
+            for (; i < hi4; i += stride4) {
+                float4 vx = __ldcs(reinterpret_cast<const float4 *>(xs + i));
+                float4 vy = __ldcs(reinterpret_cast<const float4 *>(ys + i));
+                score4(vx, vy, i);
             }
         } else {
             hi4 = lo;
@@ -1402,7 +1423,8 @@ __global__ void k_nearest_final(const NNPartial *__restrict__ partial, int split
 
 static int nn_splits(int Q, int max_nodes)
 {
-    int want = (2 * 148 + Q - 1) / Q;                  // fill the machine twice over
+    static const int waves = getenv("CRLK_NN_WAVES") ? atoi(getenv("CRLK_NN_WAVES")) : 1;   // measured best: 1
+    int want = (waves * 148 * 8 + Q - 1) / Q;          // several waves of 8 resident CTAs per SM
     int cap = (max_nodes + 8191) / 8192;               // at least 8k nodes per CTA
     int s = want < cap ? want : cap;
     return s < 1 ? 1 : s;
