@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"])
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU (0 = 1024 for cfg4, 65536 / gpus for cfg5)")
     ap.add_argument("--tree-nodes", type=int, default=1024)
     ap.add_argument("--cells", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="extensions in the CPU sample (0 = auto)")
@@ -240,6 +241,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     rank, local_rank, world = dist_info()
+    if args.workload == "cfg5":
+        return run_cfg5(args)
+    args.queries = args.queries or 1024
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -376,6 +380,124 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+def run_cfg5(args):
+    """cfg5: 65,536 independent queries sharded over the GPUs, 100,000-node trees, batched policy
+    steering.  One step = nearest node of one sample per query + one RL extension (<= 50 policy
+    steps) from that node toward the query's goal (the sample itself lies within the 1 m reach
+    radius of such a dense tree, which would end every extension after one step)."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_info()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from crl_kino_b200 import ops
+    from crl_kino_b200.env import DifferentialDriveEnv, DifferentialDriveGym
+    from crl_kino_b200.planner.batched import BatchedExtender, Forest
+    from crl_kino_b200.planner.sharding import shard_range
+    from crl_kino_b200.policy.rl_policy import load_policy
+    from crl_kino_b200.workloads import dense_map, free_states
+
+    N = 100000
+    total_q = 65536
+    lo, hi = shard_range(total_q, rank, world)
+    Q = args.queries or (hi - lo)
+    free_b, _ = torch.cuda.mem_get_info()
+    fit = int(0.8 * free_b / (N * 64 + 50 * 5 * 8 + 3 * 736 * 4 * 2))
+    capped = Q > fit
+    Q = min(Q, fit)
+    rects = dense_map(n_cells=args.cells)
+    env = DifferentialDriveEnv(1.0, -0.1, np.pi, 1.0, np.pi)
+    env.set_obs(rects)
+    pol = load_policy(DifferentialDriveGym(), [1024, 512, 512, 512], None, seed=0)
+    rng = np.random.default_rng(3 + rank)
+
+    def clearance(c):
+        return env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
+    pool = free_states(clearance, rng, 1 << 21, 0.0, batch=1 << 19)
+    pool[:, 3:] = 0.0
+    dpool = ops.as_dev(pool)
+    forest = Forest(Q, N)
+    g = torch.Generator(device="cuda").manual_seed(11 + rank)
+    for q0 in range(0, Q, 128):
+        q1 = min(Q, q0 + 128)
+        idx = torch.randint(0, dpool.shape[0], (q1 - q0, N), generator=g, device="cuda")
+        st = dpool[idx]
+        forest.states[q0:q1] = st
+        forest.x[q0:q1] = st[:, :, 0]; forest.y[q0:q1] = st[:, :, 1]
+        forest.x32[q0:q1] = st[:, :, 0].float(); forest.y32[q0:q1] = st[:, :, 1].float()
+        del st, idx
+    forest.n_nodes[:] = N
+    K, W = args.steps, args.warmup
+    samples = [ops.as_dev(free_states(clearance, rng, Q, 0.0, moving=False)) for _ in range(K + W)]
+    goals = ops.as_dev(free_states(clearance, rng, Q, 0.5))
+    ext = BatchedExtender(env, forest, policy=pol, eps=0.0)
+    ext.extend_targets = goals
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for w in range(W):
+        ext.step(samples[w])
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    n_steps_tot = 0
+    for k in range(K):
+        out = ext.step(samples[W + k], events=evs[k])
+    barrier()
+    clocks = sampler.stop()
+    t_near = sum(e[0].elapsed_time(e[1]) for e in evs)
+    t_ext = sum(e[2].elapsed_time(e[3]) for e in evs)
+    t_total = sum(e[0].elapsed_time(e[3]) for e in evs)
+    mean_steps = float(out["n_steps"].double().mean().item())
+    hs = [s.cpu().numpy() for s in samples]
+    for w in range(W):
+        ext.step_host(hs[w])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        ext.step_host(hs[W + k])
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    red = torch.tensor([t_total, t_e2e, t_near, t_ext], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(Q * K)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_total, t_e2e, t_near, t_ext = [float(x) for x in red.cpu()]
+    tot = float(cnt.item())
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        near_gbs = 8.0 * Q * N * K / (t_near * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "rrt_extensions_per_sec", "value": tot / (t_total * 1e-3), "unit": "extensions/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_total / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 policy / f64 dynamics", "data": "synthetic",
+            "config": {"workload": "cfg5: large trees, batched policy steering", "queries_total": int(tot / K),
+                       "queries_per_gpu": Q, "capped_by_memory": bool(capped), "tree_nodes": N,
+                       "obstacles": len(rects), "policy": "seeded random-init actor 733-1024-512-512-512-2, eps 0",
+                       "mean_policy_steps_per_extension": mean_steps,
+                       "l2": "per-step tree scan (>= 800 MB) exceeds L2"},
+            "e2e": {"value": tot / t_e2e, "unit": "extensions/s", "h2d_bytes_per_step": ext.h2d_bytes(),
+                    "d2h_bytes_per_step": ext.d2h_bytes()},
+            "gpu_launches": K * ext.launches_per_step,
+            "kernel_ms_per_step": {"nearest": t_near / K, "extend_rl": t_ext / K},
+            "roofline": {"kernel": "k_nearest", "bound": "hbm", "achieved": near_gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": near_gbs / hbm, "traffic": None},
+            "clocks": clocks}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cpu_sample_run(rects, tree_states, samples, n, threads):
     """The oracle's C restatement of nearest + DWA extension on the first n queries."""
     from crl_kino_b200.workloads import DENSE_DWA
@@ -405,6 +527,7 @@ def cpu_baseline(args, rects, forest, samples):
 
 
 def run_reference(args):
+    args.queries = args.queries or 1024
     """--impl reference: the CPU restatement of the reference path (the Python
     reference itself cannot travel to the GPU box) on all host cores."""
     rank, _, world = dist_info()

@@ -72,6 +72,7 @@ class BatchedExtender:
                            n_nodes=torch.empty(Q, dtype=torch.int32).pin_memory(),
                            nearest_idx=torch.empty(Q, dtype=torch.int32).pin_memory(),
                            flags=torch.empty(Q, dtype=torch.uint8).pin_memory())
+        self.extend_targets = None    # extend toward these instead of the samples (cfg5)
         self.launches_per_step = 4 if policy is None else 3 + self.xp.n_max_extend * (2 + len(policy.actor.weights)) + 1
 
     def step(self, samples, events=None):
@@ -92,8 +93,9 @@ class BatchedExtender:
             self.out = ops.extend_dwa(self.env.handle, self.dwa.params(), self.xp, self.from_states, samples,
                                       out=self.out, stats=self.stats)
         else:
+            tg = samples if self.extend_targets is None else self.extend_targets
             self.out = ops.extend_rl(self.env.handle, self.policy.actor.handle, self.xp, self.from_states,
-                                     samples, None, self.eps)
+                                     tg, None, self.eps)
         mark(3)
         self.out["nearest_idx"], self.out["nearest_dist"] = idx, dist
         return self.out
