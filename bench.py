@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--cells", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="extensions in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--use-clearance", action="store_true",
+                    help="enable the per-rollout clearance term (dwa.py:64-69); GPU legs only")
     ap.add_argument("--no-extra", action="store_true", help="skip the planning / nearest / MLP side measurements")
     ap.add_argument("--plan-iters", type=int, default=100, help="max_iter of the planning-queries/s leg")
     return ap.parse_args()
@@ -258,6 +260,10 @@ def run_ours(args):
     env.set_obs(rects)
     dwa = DWA(env)
     dwa.set_dwa(**DENSE_DWA)
+    if args.use_clearance:
+        dwa.set_dwa(use_clearance=True)
+        args.no_cpu = True          # the CPU restatement needs ~80 s per control step in this mode
+        args.no_extra = True
     forest, batches = build_workload(args, env, rank)
     ext = BatchedExtender(env, forest, dwa=dwa)
     dev_batches = ops.as_dev(batches)
@@ -341,7 +347,7 @@ def run_ours(args):
                        "rollouts_per_control_nominal": 4096,
                        "rollouts_per_control_realised": tot_roll / max(tot_ctrl, 1),
                        "control_steps_per_extension": tot_ctrl / max(tot_ext, 1),
-                       "use_clearance": False, "l2": "flushed between timed iterations (256 MiB write)",
+                       "use_clearance": bool(args.use_clearance), "l2": "flushed between timed iterations (256 MiB write)",
                        "status_last_step": {"timeout": int((status == 0).sum()), "collision": int((status == 1).sum()),
                                             "reached": int((status == 2).sum())}},
             "e2e": {"value": tot_ext / t_e2e, "unit": "extensions/s",

@@ -202,6 +202,53 @@ __device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py,
     }
 }
 
+// get_clearance (differential_env.py:126-132) for one pose by ONE thread: a
+// growing box of grid cells around the pose is screened in FP32 against the
+// best exact distance found so far; the search stops as soon as the box covers
+// every obstacle that could still beat it (centre distance < best + rc).
+// Returns min(100, min distance), or -1 on collision -- the same value as the
+// scan over all obstacles.
+static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const ObsSet &os, double x, double y,
+                                                     double th, bool *definite_out, bool *marginal_out)
+{
+    RobotPose g;
+    robot_pose_setup(e, x, y, th, g);
+    const float px = (float)x, py = (float)y;
+    const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
+    double best = CRLK_CLEARANCE_CAP;
+    bool definite = false, marginal = false;
+    float r = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
+    for (;;) {
+        float rr = r + 2e-3f;
+        int cx0 = (int)fminf(fmaxf(floorf((px - rr - os.gx0) * os.ginv), 0.f), hx);
+        int cx1 = (int)fminf(fmaxf(floorf((px + rr - os.gx0) * os.ginv), 0.f), hx);
+        int cy0 = (int)fminf(fmaxf(floorf((py - rr - os.gy0) * os.ginv), 0.f), hy);
+        int cy1 = (int)fminf(fmaxf(floorf((py + rr - os.gy0) * os.ginv), 0.f), hy);
+        for (int cy = cy0; cy <= cy1; cy++) {
+            int s = __ldg(&os.cell_start[cy * os.ncx + cx0]);
+            int en = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
+            for (int k = s; k < en; k++) {
+                float4 o = __ldg(&os.rects[__ldg(&os.cell_items[k])]);
+                float lim = (float)fmax(best, 0.0) * 1.0001f + e.rc + CRLK_CULL_MARGIN;
+                if (aabb_center_d2(o, px, py) <= lim * lim) {
+                    bool dd, mm;
+                    double dis = dis2obs_exact(e, g, o, dd, mm);
+                    definite |= dd; marginal |= mm;
+                    best = fmin(best, dis);
+                }
+            }
+        }
+        if (best < 0.0) break;
+        float need = (float)best * 1.0001f + e.rc + CRLK_CULL_MARGIN;
+        bool whole = (cx0 == 0 && cy0 == 0 && cx1 == os.ncx - 1 && cy1 == os.ncy - 1);
+        if (need <= r || whole) break;
+        r = fminf(need, 2.0f * r);
+    }
+    if (definite_out) *definite_out = definite;
+    if (marginal_out) *marginal_out = marginal;
+    return (best < 0.0) ? -1.0 : best;
+}
+
 // ---------------------------------------------------------------- reductions
 
 __device__ __forceinline__ double warp_min_d(double v)

@@ -265,14 +265,33 @@ k_valid_state(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8
     }
 }
 
+// Clearance mode: one thread per pose, grid ring search.
+__global__ void __launch_bounds__(128)
+k_clearance(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8_t *valid, double *clearance,
+            uint8_t *near_boundary)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double *st = states + 5 * (size_t)i;
+    bool d, m;
+    double c = clearance_grid_thread(e, os, st[0], st[1], st[2], &d, &m);
+    if (valid) valid[i] = (c < 0.0) ? 0 : 1;
+    clearance[i] = c;
+    if (near_boundary) near_boundary[i] = (m && !d) ? 1 : 0;
+}
+
 extern "C" int crlk_valid_state(const CrlkEnv *env, const double *states, int32_t B, uint8_t *valid,
                                 double *clearance, uint8_t *near_boundary, void *stream)
 {
     CRLK_REQUIRE(env != nullptr, "env is NULL");
     CRLK_REQUIRE(B >= 0 && (B == 0 || states != nullptr), "states");
     if (B == 0) return CRLK_OK;
-    k_valid_state<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        env->p, env->os, states, B, valid, clearance, near_boundary);
+    if (clearance)
+        k_clearance<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, env->os, states, B, valid,
+                                                                      clearance, near_boundary);
+    else
+        k_valid_state<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(env->p, env->os, states, B, valid,
+                                                                    clearance, near_boundary);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -695,39 +714,17 @@ struct DwaResult {
 };
 
 // get_clearance for one pose by one thread (used only when use_clearance = 1).
-__device__ __noinline__ double clearance_thread(const EnvP &e, const float4 *__restrict__ rects, int M, double x,
-                                   double y, double th)
+__device__ __forceinline__ double clearance_thread(const EnvP &e, const ObsSet &os, double x, double y,
+                                                   double th)
 {
-    RobotPose g;
-    robot_pose_setup(e, x, y, th, g);
-    float px = (float)x, py = (float)y;
-    float lmin = CUDART_INF_F;
-    int limin = -1;
-    for (int o = 0; o < M; o++) {
-        float d2 = aabb_center_d2(__ldg(&rects[o]), px, py);
-        if (d2 < lmin) { lmin = d2; limin = o; }
-    }
-    double best = CRLK_CLEARANCE_CAP;
-    bool d, m;
-    if (limin >= 0) best = fmin(best, dis2obs_exact(e, g, __ldg(&rects[limin]), d, m));
-    if (best < 0.0) return -1.0;
-    float thr = (float)best * 1.0001f + e.rc + CRLK_CULL_MARGIN;
-    float thr2 = thr * thr;
-    for (int o = 0; o < M; o++) {
-        float4 r = __ldg(&rects[o]);
-        if (aabb_center_d2(r, px, py) <= thr2) {
-            best = fmin(best, dis2obs_exact(e, g, r, d, m));
-            if (best < 0.0) return -1.0;
-        }
-    }
-    return best;
+    return clearance_grid_thread(e, os, x, y, th, nullptr, nullptr);
 }
 
 // DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
 // doubles) and the goal must be block-uniform.  Every thread returns the result.
 template <class Epi>
-__device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float4 *__restrict__ rects,
-                                       int M, const double *st, double gx, double gy,
+__device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSet &os,
+                                       const double *st, double gx, double gy,
                                        const DwaSmem &sm, Epi epilogue)
 {
     const int tid = threadIdx.x, T = DWA_THREADS;
@@ -772,7 +769,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
     if (warp == 3 && sm.iscal[3] != R) pw_build_tree_warp(R, sm);   // warps 3-4 have no chain work
     // clearance of the shared first row (dwa.py:65-67, i = 0)
     double clr0 = CRLK_CLEARANCE_CAP;
-    if (d.use_clearance) clr0 = pymax(clearance_thread(e, rects, M, st[0], st[1], st[2]), 0.001);
+    if (d.use_clearance) clr0 = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
     __syncthreads();
 
     // rollouts: heading cost from trajectory row 1 (dwa.py:58-62)
@@ -827,7 +824,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
                         y = y + vt[k] * ws[k] * dt;
                     }
                 if (row % d.skip == 0) {
-                    double dis = pymax(clearance_thread(e, rects, M, x, y, sm.wth[j * d.n_outer + row - 1]),
+                    double dis = pymax(clearance_thread(e, os, x, y, sm.wth[j * d.n_outer + row - 1]),
                                        0.001);
                     min_dis = pymin(dis, min_dis);
                 }
@@ -986,7 +983,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const float
 }
 
 __global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
-k_dwa_control(EnvP e, DwaP d, const float4 *__restrict__ rects, int M,
+k_dwa_control(EnvP e, DwaP d, ObsSet os,
               const double *__restrict__ states, const double *__restrict__ goals, int goal_stride,
               int B, double *opt_v, int *opt_idx, double *opt_cost, double *opt_traj,
               int *n_rollouts, uint8_t *near_tie)
@@ -1001,7 +998,7 @@ k_dwa_control(EnvP e, DwaP d, const float4 *__restrict__ rects, int M,
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
         __syncthreads();
         double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
-        DwaResult r = dwa_control_block(e, d, rects, M, s_state, gx, gy, sm, [](double, double, int) {});
+        DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm, [](double, double, int) {});
         if (threadIdx.x == 0) {
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
@@ -1061,7 +1058,7 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
     rc = set_smem_attr((const void *)k_dwa_control, smem);
     if (rc) return rc;
     k_dwa_control<<<B, DWA_THREADS, smem, (cudaStream_t)stream>>>(
-        env->p, d, env->d_rects, env->M, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
+        env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
         opt_traj, n_rollouts, near_tie);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
@@ -1154,7 +1151,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
         for (int k = 1; k <= x.n_max_extend; k++) {
             // rrt.py:116-118: control, then thread 0 advances the state inside the
             // control block's closing section (no extra barrier round trip)
-            DwaResult r = dwa_control_block(e, d, os.rects, os.M, s_state, gx, gy, sm,
+            DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm,
                 [&](double cv, double cw, int ix) {
                     double s[5];
                     for (int c = 0; c < 5; c++) s[c] = s_state[c];
