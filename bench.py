@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 M_FLOP_ROLLOUT = 406.0      # FP ops per DWA rollout
 M_FLOP_PAIR = 860.0         # FP ops per (pose, obstacle) pair, brute force
 FP64_LANES_PER_SM = 64      # B200: 64 FP64 FMA lanes per SM
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures
+# summarised in profiles/r1d_*_ncu_summary.txt (default workload sizes only)
+NCU_TRAFFIC_EXTEND_DWA = 1.689856e6 + 7.159808e6      # k_extend_dwa, 1024 queries, cfg4 map
+NCU_TRAFFIC_NEAREST = 820.148992e6 + 4.725248e6       # k_nearest, 1024 trees x 100,000 nodes
 
 
 def parse():
@@ -210,7 +214,7 @@ def nearest_roofline(peaks):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = algo / (ms * 1e-3) / 1e9
     return {"kernel": "k_nearest", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": None, "ms": ms,
+            "frac": ach / peak, "traffic": NCU_TRAFFIC_NEAREST, "algorithmic_bytes_per_launch": algo, "ms": ms,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "workload": f"{Q} trees x {N} nodes (819 MB of float32 coordinates, > L2), one target each",
             "nodes_per_sec": Q * N / (ms * 1e-3)}
@@ -233,6 +237,7 @@ def mlp_roofline(peaks):
     ach = algo / (ms * 1e-3) / 1e12
     return {"kernel": "k_gemm_bf16x3 (+ split, head)", "bound": "tensor", "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms": ms,
+            "ncu": "profiles/r1d_gemm_ncu_summary.txt: tensor pipe 46.5 % active in the layer-0 GEMM",
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "note": "algorithmic float32 FLOP (3,600,384 per sample); the kernel issues 6 bf16 MMAs per "
                     "float32 product pair (bf16 x 3 operand split) to keep float32-level accuracy, so the "
@@ -355,7 +360,9 @@ def run_ours(args):
             "gpu_launches": K * ext.launches_per_step,
             "kernel_ms_per_step": {"nearest": t_near / K, "gather": t_gath / K, "extend_dwa": t_ext / K},
             "roofline": {"kernel": "k_extend_dwa", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": NCU_TRAFFIC_EXTEND_DWA if (Q == 1024 and args.cells == 10000 and not args.use_clearance) else None,
+                         "ncu": "profiles/r1d_extend_ncu_summary.txt: fp64 pipe 23.4 %, issue slots 52.7 %, 80 regs, 3 CTAs/SM",
                          "peak_source": f"derived: {sms} SM x {FP64_LANES_PER_SM} FP64 FMA lanes x 2 x "
                                         f"{sm_max:.0f} MHz (MEASURED_PEAKS.json holds only HBM and bf16 peaks)",
                          "algorithmic_flop_per_launch": flop / K,
