@@ -538,7 +538,7 @@ int crlk_local_obs_masked(const CrlkEnv *env, const double *states, const double
 struct DwaSmem {
     double *c0, *c1;
     double *vtab, *vlast, *c2n;
-    double *wcos, *wsin, *wth;
+    double *wcos, *wsin, *wth, *wom;
     // numpy pairwise-sum recursion tree over R elements (rebuilt only when R changes)
     int *nd_off, *nd_len, *nd_left;   // [nmax] element range; first child id (-1 = leaf)
     int *leaf_ids;                    // [nmax] ids of the leaf nodes
@@ -574,6 +574,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_wcos = take(sizeof(double) * d.nw_max * spos);
     size_t o_wsin = take(sizeof(double) * d.nw_max * spos);
     size_t o_wth = take(sizeof(double) * d.nw_max * d.n_outer);
+    size_t o_wom = take(sizeof(double) * d.nw_max);
     size_t o_noff = take(sizeof(int) * nmax);
     size_t o_nlen = take(sizeof(int) * nmax);
     size_t o_nleft = take(sizeof(int) * nmax);
@@ -592,6 +593,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->c2n = (double *)(base + o_c2n);
         s->wcos = (double *)(base + o_wcos); s->wsin = (double *)(base + o_wsin);
         s->wth = (double *)(base + o_wth);
+        s->wom = (double *)(base + o_wom);
         s->nd_off = (int *)(base + o_noff); s->nd_len = (int *)(base + o_nlen);
         s->nd_left = (int *)(base + o_nleft); s->leaf_ids = (int *)(base + o_lids);
         s->nd_val = (double *)(base + o_nval); s->lvl_start = (int *)(base + o_lvl);
@@ -707,6 +709,21 @@ __device__ __forceinline__ double np_leaf_sum8(F f, int off, int n, int sub)
     return res;
 }
 
+#ifdef CRLK_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
+#define PHASE_START() long long _t0 = clock64()
+extern "C" int crlk_debug_phase_cycles(unsigned long long *out16, int reset)
+{
+    cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
+    return 0;
+}
+#else
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_START() do { } while (0)
+#endif
+
 struct DwaResult {
     double v, w, cost;
     int idx, R;
@@ -742,14 +759,21 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     const int R = nv * nw;
     const int S = d.n_sub * d.n_outer, spos = sm.spos;
 
+    PHASE_START();
     __syncthreads();   // previous users of the shared tables are done
+    PHASE_MARK(0);
     // velocity chains (one per v command) and heading chains (one per w command)
     for (int i = tid; i < nv; i += T) {
         double cv = arange_at(v_lo, v1, vd, i);
         double cur = st[3];
         for (int k = 0; k < S; k++) {
-            cur = vel_substep(cur, cv, e.max_acc_v, e.min_v, e.max_v, dt);
+            double nxt = vel_substep(cur, cv, e.max_acc_v, e.min_v, e.max_v, dt);
+            // f(cur) == cur is a fixed point of the (deterministic) sub-step: every later
+            // sub-step returns the same value, so the chain can stop (bit-identical result)
+            bool fixed = (nxt == cur);
+            cur = nxt;
             if (k < spos) sm.vtab[i * spos + k] = cur;
+            else if (fixed) break;
         }
         sm.vlast[i] = cur;
     }
@@ -764,6 +788,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             sm.wcos[j * spos + k] = cs;
             sm.wsin[j * spos + k] = sn;
             if ((k + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (k + 1) / d.n_sub - 1] = th;
+            if (k + 1 == d.n_sub) sm.wom[j] = cur;      // omega after the first dt step
         }
     }
     if (warp == 3 && sm.iscal[3] != R) pw_build_tree_warp(R, sm);   // warps 3-4 have no chain work
@@ -771,6 +796,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     double clr0 = CRLK_CLEARANCE_CAP;
     if (d.use_clearance) clr0 = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
     __syncthreads();
+    PHASE_MARK(1);
 
     // rollouts: heading cost from trajectory row 1 (dwa.py:58-62)
     const int di = T / nw, dj = T - di * nw;     // r += T  <=>  (i, j) += (di, dj) with carry
@@ -833,6 +859,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         }
     }
     __syncthreads();
+    PHASE_MARK(2);
 
     // column sums in numpy's pairwise order (dwa.py:76-78): every leaf block of
     // every column by 8 lanes, then the tree levels bottom-up (one warp per column)
@@ -861,6 +888,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             if (sub == 0) sm.nd_val[col * sm.nmax + node] = sres;
         }
         __syncthreads();
+        PHASE_MARK(3);
         if (warp < 3) {
             double *val = sm.nd_val + warp * sm.nmax;
             for (int lv = sm.iscal[4] - 1; lv >= 0; lv--) {
@@ -882,6 +910,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         }
     }
     __syncthreads();
+    PHASE_MARK(4);
     if (tid == 0 && !d.use_clearance) sm.iscal[6] = sm.iscal[7];
     const double S0 = sm.scal[0], S1 = sm.scal[1], S2 = sm.scal[2];
     // weighted sum and first argmin (dwa.py:79-82).  Screen: the normalising
@@ -927,6 +956,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         if (lane == 0) { sm.red_v[warp] = wb; sm.red_s[warp] = ws2; }
     }
     __syncthreads();
+    PHASE_MARK(5);
     double m_a = sm.red_v[0], s_a = sm.red_s[0];
 #pragma unroll
     for (int w = 1; w < T / 32; w++) {
@@ -958,6 +988,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     warp_argmin(best, bi);
     if (lane == 0) { sm.red_v[warp] = best; sm.red_i[warp] = bi; }
     __syncthreads();
+    PHASE_MARK(6);
     if (tid == 0) {
         double b = sm.red_v[0];
         int ix = sm.red_i[0];
@@ -973,9 +1004,23 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         sm.iscal[1] = ix;
         double gap = s_a - m_a;
         sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(m_a)) ? 1 : 0;
-        epilogue(sm.scal[4], sm.scal[5], ix);    // thread 0 only, before the closing barrier
+        // trajectory row 1 of the winner (= motion_velocity(state, opt_v, d.dt), same operations)
+        double row1[5];
+        {
+            const double *vt = sm.vtab + i * spos;
+            const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
+            double x = st[0], y = st[1];
+            for (int k = 0; k < d.n_sub; k++) {
+                x = x + vt[k] * wc[k] * dt;
+                y = y + vt[k] * ws[k] * dt;
+            }
+            row1[0] = x; row1[1] = y; row1[2] = sm.wth[j * d.n_outer];
+            row1[3] = vt[d.n_sub - 1]; row1[4] = sm.wom[j];
+        }
+        epilogue(sm.scal[4], sm.scal[5], ix, row1);    // thread 0 only, before the closing barrier
     }
     __syncthreads();
+    PHASE_MARK(7);
     DwaResult res;
     res.v = sm.scal[4]; res.w = sm.scal[5]; res.cost = sm.scal[6];
     res.idx = sm.iscal[1]; res.near_tie = sm.iscal[2]; res.R = R;
@@ -998,7 +1043,7 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
         __syncthreads();
         double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
-        DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm, [](double, double, int) {});
+        DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm, [](double, double, int, const double *) {});
         if (threadIdx.x == 0) {
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
@@ -1152,10 +1197,15 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
             // rrt.py:116-118: control, then thread 0 advances the state inside the
             // control block's closing section (no extra barrier round trip)
             DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm,
-                [&](double cv, double cw, int ix) {
+                [&](double cv, double cw, int ix, const double *row1) {
                     double s[5];
-                    for (int c = 0; c < 5; c++) s[c] = s_state[c];
-                    motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
+                    if (x.n_sub_step == d.n_sub) {
+                        // executing the control for step_dt == dwa.dt IS the winner's trajectory row 1
+                        for (int c = 0; c < 5; c++) s[c] = row1[c];
+                    } else {
+                        for (int c = 0; c < 5; c++) s[c] = s_state[c];
+                        motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
+                    }
                     for (int c = 0; c < 5; c++) {
                         s_next[c] = s[c];
                         path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
@@ -1168,7 +1218,9 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
             __syncthreads();
             steps = k;
             // rrt.py:121: valid_state_check on the new state
+            PHASE_START();
             int col = collision_block(e, os, s_state[0], s_state[1], s_state[2], sm.queue, s_ctl);
+            PHASE_MARK(8);
             if (col & 2) fl |= 1;
             col &= 1;
             if (col == 1) { st_code = CRLK_EXT_COLLISION; break; }
