@@ -1116,7 +1116,7 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
 // over the threads.  Returns bit0 = collision, bit1 = the decision is within
 // 1e-6 of the 0.05 threshold (reported, not claimed).
 __device__ int collision_block(const EnvP &e, const ObsSet &os, double x, double y, double th,
-                               int *s_queue /*1024*/, int *s_ctl /*4*/)
+                               int *s_queue /*unused*/, int *s_ctl /*unused*/)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     const float4 *__restrict__ rects = os.rects;
@@ -1125,37 +1125,23 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, double x, double
     float px = (float)x, py = (float)y;
     float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
     float thr2 = thr * thr;
-    __syncthreads();
-    if (tid < 4) s_ctl[tid] = 0;
-    __syncthreads();
     bool coll = false, definite = false, marginal = false;
+    // each thread screens its share of the cell lists and tests its survivors at once
+    // (a pose touches a few hundred listed obstacles at most: <= 1-2 per thread)
     grid_visit(os, px, py, thr, tid, T, [&](int o, bool in) {
         if (!in) return;
         float4 r = __ldg(&rects[o]);
         if (aabb_center_d2(r, px, py) <= thr2) {
-            int pos = atomicAdd(&s_ctl[0], 1);
-            if (pos < 1024) s_queue[pos] = o;
-            else {   // queue overflow: evaluate in place
-                bool d, m;
-                coll |= dis2obs_exact(e, g, r, d, m) < 0.0;
-                definite |= d; marginal |= m;
-            }
+            bool d, m;
+            coll |= dis2obs_exact(e, g, r, d, m) < 0.0;
+            definite |= d; marginal |= m;
         }
     });
-    __syncthreads();
-    int cnt = min(s_ctl[0], 1024);
-    for (int k = tid; k < cnt; k += T) {
-        bool d, m;
-        coll |= dis2obs_exact(e, g, __ldg(&rects[s_queue[k]]), d, m) < 0.0;
-        definite |= d; marginal |= m;
-    }
-    if (coll) atomicOr(&s_ctl[1], 1);
-    if (definite) atomicOr(&s_ctl[2], 1);
-    if (marginal) atomicOr(&s_ctl[3], 1);
-    __syncthreads();
-    int res = (s_ctl[1] ? 1 : 0) | ((s_ctl[3] && !s_ctl[2]) ? 2 : 0);
-    __syncthreads();
-    return res;
+    // barrier-fused reductions
+    int any_coll = __syncthreads_or(coll);
+    int any_def = __syncthreads_or(definite);
+    int any_mar = __syncthreads_or(marginal);
+    return (any_coll ? 1 : 0) | ((any_mar && !any_def) ? 2 : 0);
 }
 
 __global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
