@@ -70,13 +70,15 @@ PROTOTYPES = {
     "crlk_nearest_scratch_bytes": (I64, [I32, I32]),
     "crlk_extend_dwa": (C.c_int, [P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P]),
     "crlk_gather_rows": (C.c_int, [P, I64, I32, P, I32, P, P]),
+    "crlk_estimator_choose_parent": (C.c_int, [P, P, P, I64, P, I32, P, I32, P, P, P, P]),
+    "crlk_estimator_cp_workspace_bytes": (I64, [I32, I32]),
     "crlk_rrt_select": (C.c_int, [P, P, I32, I32, F64, F64, P, P, P, P]),
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),
     "crlk_policy_destroy": (C.c_int, [P]),
     "crlk_policy_forward": (C.c_int, [P, P, I32, P, F32, I32, P, P, P]),
     "crlk_policy_workspace_bytes": (I64, [P, I32]),
-    "crlk_extend_rl": (C.c_int, [P, P, P, P, P, I32, P, F32, P, P, P, P, P, P, P, P, P, P]),
+    "crlk_extend_rl": (C.c_int, [P, P, P, P, P, I32, P, I32, P, F32, P, P, P, P, P, P, P, P, P, P]),
     "crlk_extend_rl_workspace_bytes": (I64, [P, I32]),
     "crlk_estimator_create": (C.c_int, [P, P, P]),
     "crlk_estimator_destroy": (C.c_int, [P]),

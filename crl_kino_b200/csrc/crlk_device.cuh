@@ -249,6 +249,70 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
     return (best < 0.0) ? -1.0 : best;
 }
 
+// ------------------------------------------------ local occupancy map (R9)
+
+#define OBS_NPTS 729
+#define OBS_SIDE 27
+#define OBS_NEAR_EPS 1e-9
+
+struct ObsGrid {      // np.arange(-2, 6, 0.3) / np.arange(-4, 4, 0.3) (differential_gym.py:67-71)
+    double ba0, ba1, bad;   // start, start+step, delta
+    double lr0, lr1, lrd;
+};
+
+static inline ObsGrid make_obs_grid()
+{
+    ObsGrid g;
+    g.ba0 = -2.0; g.ba1 = -2.0 + 0.3; g.bad = g.ba1 - g.ba0;
+    g.lr0 = -4.0; g.lr1 = -4.0 + 0.3; g.lrd = g.lr1 - g.lr0;
+    return g;
+}
+
+__device__ __forceinline__ double arange_at(double a0, double a1, double d, int i)
+{
+    return (i == 0) ? a0 : (i == 1) ? a1 : a0 + (double)i * d;
+}
+
+// wTb @ [bx, by, 1] with every operation rounded separately (no FMA contraction,
+// whatever the translation unit's -fmad setting): identical bits in every kernel.
+__device__ __forceinline__ void body_to_world(double cs, double sn, double x, double y, double bx, double by,
+                                              double &px, double &py)
+{
+    px = __dadd_rn(__dadd_rn(__dmul_rn(cs, bx), __dmul_rn(-sn, by)), x);
+    py = __dadd_rn(__dadd_rn(__dmul_rn(sn, bx), __dmul_rn(cs, by)), y);
+}
+
+// valid_point_check for one point as a query against the obstacle grid (closed
+// intervals, rigid.py:158-166).  A point inside an obstacle always falls in a
+// cell of that obstacle's range (the cell function is monotone), so this equals
+// the scan over all obstacles.  `near` is OR-ed with "within 1e-9 of a face".
+__device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, double py, bool &near)
+{
+    const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
+    float fx0 = floorf(((float)px - 1e-6f - os.gx0) * os.ginv), fx1 = floorf(((float)px + 1e-6f - os.gx0) * os.ginv);
+    float fy0 = floorf(((float)py - 1e-6f - os.gy0) * os.ginv), fy1 = floorf(((float)py + 1e-6f - os.gy0) * os.ginv);
+    bool occ = false;
+    if (fx1 >= 0.f && fx0 <= hx && fy1 >= 0.f && fy0 <= hy) {     // else outside every obstacle
+        int cx0 = (int)fmaxf(fx0, 0.f), cx1 = (int)fminf(fx1, hx);
+        int cy0 = (int)fmaxf(fy0, 0.f), cy1 = (int)fminf(fy1, hy);
+        for (int cy = cy0; cy <= cy1; cy++) {
+            int s0 = __ldg(&os.cell_start[cy * os.ncx + cx0]);
+            int e0 = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
+            for (int i = s0; i < e0; i++) {
+                float4 r = __ldg(&os.rects[__ldg(&os.cell_items[i])]);
+                double l = r.x, bo = r.y, rr = r.z, t = r.w;
+                occ |= (px >= l && px <= rr && py >= bo && py <= t);
+                bool in_big = (px >= l - OBS_NEAR_EPS && px <= rr + OBS_NEAR_EPS &&
+                               py >= bo - OBS_NEAR_EPS && py <= t + OBS_NEAR_EPS);
+                bool in_small = (px >= l + OBS_NEAR_EPS && px <= rr - OBS_NEAR_EPS &&
+                                 py >= bo + OBS_NEAR_EPS && py <= t - OBS_NEAR_EPS);
+                near |= in_big && !in_small;
+            }
+        }
+    }
+    return occ;
+}
+
 // ---------------------------------------------------------------- reductions
 
 __device__ __forceinline__ double warp_min_d(double v)

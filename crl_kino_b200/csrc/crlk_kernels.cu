@@ -398,20 +398,6 @@ extern "C" int crlk_dynamic_window(const CrlkEnv *env, const double *states, dou
 
 // -------------------------------------------------------- local observation (R9)
 
-#define OBS_NPTS 729
-#define OBS_SIDE 27
-#define OBS_TILE 1024
-#define OBS_NEAR_EPS 1e-9
-
-struct ObsGrid {      // np.arange(-2, 6, 0.3) / np.arange(-4, 4, 0.3) (differential_gym.py:67-71)
-    double ba0, ba1, bad;   // start, start+step, delta
-    double lr0, lr1, lrd;
-};
-
-__device__ __forceinline__ double arange_at(double a0, double a1, double d, int i)
-{
-    return (i == 0) ? a0 : (i == 1) ? a1 : a0 + (double)i * d;
-}
 
 // One CTA per observation, three sample points per thread.  Each point is a
 // point query against the obstacle grid: only the lists of the cell(s) holding
@@ -433,8 +419,6 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
     sincos(th, &sn, &cs);
     if (threadIdx.x == 0) s_near = 0;
     __syncthreads();
-    const float4 *__restrict__ rects = os.rects;
-    const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
     bool nearp = false;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -443,30 +427,9 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
         int ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;
         double bx = arange_at(og.ba0, og.ba1, og.bad, ib);
         double by = arange_at(og.lr0, og.lr1, og.lrd, il);
-        double px = (cs * bx + (-sn) * by) + x;     // differential_gym.py:83 (wTb @ [bx, by, 1])
-        double py = (sn * bx + cs * by) + y;
-        // cells of the point (a 1e-6 halo so that the near-boundary report sees neighbours)
-        float fx0 = floorf(((float)px - 1e-6f - os.gx0) * os.ginv), fx1 = floorf(((float)px + 1e-6f - os.gx0) * os.ginv);
-        float fy0 = floorf(((float)py - 1e-6f - os.gy0) * os.ginv), fy1 = floorf(((float)py + 1e-6f - os.gy0) * os.ginv);
-        bool occ = false;
-        if (fx1 >= 0.f && fx0 <= hx && fy1 >= 0.f && fy0 <= hy) {     // else outside every obstacle
-            int cx0 = (int)fmaxf(fx0, 0.f), cx1 = (int)fminf(fx1, hx);
-            int cy0 = (int)fmaxf(fy0, 0.f), cy1 = (int)fminf(fy1, hy);
-            for (int cy = cy0; cy <= cy1; cy++) {
-                int s0 = __ldg(&os.cell_start[cy * os.ncx + cx0]);
-                int e0 = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
-                for (int i = s0; i < e0; i++) {
-                    float4 r = __ldg(&rects[__ldg(&os.cell_items[i])]);
-                    double l = r.x, bo = r.y, rr = r.z, t = r.w;
-                    occ |= (px >= l && px <= rr && py >= bo && py <= t);
-                    bool in_big = (px >= l - OBS_NEAR_EPS && px <= rr + OBS_NEAR_EPS &&
-                                   py >= bo - OBS_NEAR_EPS && py <= t + OBS_NEAR_EPS);
-                    bool in_small = (px >= l + OBS_NEAR_EPS && px <= rr - OBS_NEAR_EPS &&
-                                     py >= bo + OBS_NEAR_EPS && py <= t - OBS_NEAR_EPS);
-                    nearp |= in_big && !in_small;
-                }
-            }
-        }
+        double px, py;
+        body_to_world(cs, sn, x, y, bx, by, px, py);     // differential_gym.py:83 (wTb @ [bx, by, 1])
+        bool occ = local_map_occupied(os, px, py, nearp);
         double v = occ ? 0.0 : 1.0;
         if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
         if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
@@ -489,14 +452,6 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
     }
     __syncthreads();
     if (threadIdx.x == 0 && near_boundary) near_boundary[b] = (uint8_t)s_near;
-}
-
-static ObsGrid make_obs_grid()
-{
-    ObsGrid g;
-    g.ba0 = -2.0; g.ba1 = -2.0 + 0.3; g.bad = g.ba1 - g.ba0;
-    g.lr0 = -4.0; g.lr1 = -4.0 + 0.3; g.lrd = g.lr1 - g.lr0;
-    return g;
 }
 
 extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals,

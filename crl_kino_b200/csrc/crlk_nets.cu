@@ -130,7 +130,8 @@ struct HeadP { float low[2], high[2], scale[2], bias[2]; };
 __global__ void __launch_bounds__(256)
 k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W, int K,
               const float *__restrict__ bias, const float *__restrict__ noise, long long noise_stride,
-              float eps, HeadP hp, int B, float *__restrict__ act)
+              const int *__restrict__ noise_cursor, int noise_off, float eps, HeadP hp, int B,
+              float *__restrict__ act)
 {
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -149,7 +150,10 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
     if (lane < 2) {
         float z = (lane == 0 ? s0 : s1) + __ldg(&bias[lane]);
         z = tanhf(z);
-        if (noise) z = z + noise[(size_t)row * noise_stride + lane] * eps;
+        if (noise) {
+            long long off = (long long)noise_off + (noise_cursor ? noise_cursor[row] : 0);
+            z = z + noise[(size_t)row * noise_stride + off * 2 + lane] * eps;
+        }
         z = z * hp.scale[lane] + hp.bias[lane];
         z = fminf(fmaxf(z, hp.low[lane]), hp.high[lane]);
         act[2 * (size_t)row + lane] = z;
@@ -157,8 +161,8 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
 }
 
 static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs, const float *noise,
-                               long long noise_stride, float eps, int B, float *act, void *workspace,
-                               cudaStream_t st)
+                               long long noise_stride, const int *noise_cursor, int noise_off, float eps, int B,
+                               float *act, void *workspace, cudaStream_t st)
 {
     const int L = p->n_layers;
     const float *in = obs;
@@ -190,7 +194,7 @@ static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs
         hp.low[k] = p->low[k]; hp.high[k] = p->high[k]; hp.scale[k] = p->scale[k]; hp.bias[k] = p->bias[k];
     }
     k_policy_head<<<(B + 7) / 8, 256, 0, st>>>(in, ld_in, p->d_w[L - 1], p->kpad[L - 1], p->d_b[L - 1],
-                                              noise, noise_stride, eps, hp, B, act);
+                                              noise, noise_stride, noise_cursor, noise_off, eps, hp, B, act);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -206,7 +210,7 @@ extern "C" int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_
     CRLK_REQUIRE(ld_obs >= p->kpad[0] && ld_obs % 4 == 0,
                  "ld_obs must be >= the input width rounded up to 16, zero padded");
     CRLK_REQUIRE(((uintptr_t)obs & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "16-byte alignment");
-    return policy_forward_impl(p, obs, ld_obs, noise, 2, eps, B, act, workspace, (cudaStream_t)stream);
+    return policy_forward_impl(p, obs, ld_obs, noise, 2, nullptr, 0, eps, B, act, workspace, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------- estimator CNNs (R11)
@@ -295,29 +299,10 @@ __device__ __forceinline__ void conv_relu_pool(const float *__restrict__ w, cons
     }
 }
 
-// One CTA per (sample, net): estimator/network.py:39-69 and :97-127.
-__global__ void __launch_bounds__(CNN_THREADS)
-k_estimator(const float *__restrict__ params, const float *__restrict__ obs, int ld_obs, int B,
-            float *__restrict__ est, float *__restrict__ prob)
+
+// conv4 (32 -> 64, 3x3, pad 1) + ReLU + global average pool over the 3 x 3 map
+__device__ __forceinline__ void conv4_avgpool(const float *__restrict__ P, const float *s_c, float *s_d)
 {
-    __shared__ float s_in[27 * 27];
-    __shared__ float s_a[8 * 13 * 13];
-    __shared__ float s_b[16 * 6 * 6];
-    __shared__ float s_c[32 * 3 * 3];
-    __shared__ float s_d[64];
-    const int b = blockIdx.x, net = blockIdx.y;
-    if (b >= B) return;
-    const float *P = params + (size_t)net * CNN_PARAMS;
-    const float *o = obs + (size_t)b * ld_obs;
-    for (int i = threadIdx.x; i < 729; i += CNN_THREADS) s_in[i] = o[4 + i];
-    __syncthreads();
-    conv_relu_pool<1, 8, 27>(P + O_W1, P + O_B1, s_in, s_a);
-    __syncthreads();
-    conv_relu_pool<8, 16, 13>(P + O_W2, P + O_B2, s_a, s_b);
-    __syncthreads();
-    conv_relu_pool<16, 32, 6>(P + O_W3, P + O_B3, s_b, s_c);
-    __syncthreads();
-    // conv4 + ReLU + global average pool over 3 x 3
     for (int co = threadIdx.x; co < 64; co += CNN_THREADS) {
         float sum = 0.f;
         for (int y = 0; y < 3; y++)
@@ -342,21 +327,53 @@ k_estimator(const float *__restrict__ params, const float *__restrict__ obs, int
             }
         s_d[co] = sum / 9.0f;
     }
+}
+
+// Linear(67 -> 1) over [features(64), ext(3)] by the first warp; result in lane 0.
+__device__ __forceinline__ float cnn_head(const float *__restrict__ P, const float *s_d, float e0, float e1,
+                                          float e2)
+{
+    int lane = threadIdx.x;
+    float acc = 0.f;
+    for (int k = lane; k < 64; k += 32) acc = fmaf(s_d[k], __ldg(&P[O_WL + k]), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    acc = fmaf(e0, __ldg(&P[O_WL + 64]), acc);
+    acc = fmaf(e1, __ldg(&P[O_WL + 65]), acc);
+    acc = fmaf(e2, __ldg(&P[O_WL + 66]), acc);
+    return acc + __ldg(&P[O_BL]);
+}
+
+// One CTA per (sample, net): estimator/network.py:39-69 and :97-127.
+__global__ void __launch_bounds__(CNN_THREADS)
+k_estimator(const float *__restrict__ params, const float *__restrict__ obs, int ld_obs, int B,
+            float *__restrict__ est, float *__restrict__ prob)
+{
+    __shared__ float s_in[27 * 27];
+    __shared__ float s_a[8 * 13 * 13];
+    __shared__ float s_b[16 * 6 * 6];
+    __shared__ float s_c[32 * 3 * 3];
+    __shared__ float s_d[64];
+    const int b = blockIdx.x, net = blockIdx.y;
+    if (b >= B) return;
+    const float *P = params + (size_t)net * CNN_PARAMS;
+    const float *o = obs + (size_t)b * ld_obs;
+    for (int i = threadIdx.x; i < 729; i += CNN_THREADS) s_in[i] = o[4 + i];
+    __syncthreads();
+    conv_relu_pool<1, 8, 27>(P + O_W1, P + O_B1, s_in, s_a);
+    __syncthreads();
+    conv_relu_pool<8, 16, 13>(P + O_W2, P + O_B2, s_a, s_b);
+    __syncthreads();
+    conv_relu_pool<16, 32, 6>(P + O_W3, P + O_B3, s_b, s_c);
+    __syncthreads();
+    conv4_avgpool(P, s_c, s_d);
     __syncthreads();
     if (threadIdx.x < 32) {
-        int lane = threadIdx.x;
-        float acc = 0.f;
-        for (int k = lane; k < 64; k += 32) acc = fmaf(s_d[k], __ldg(&P[O_WL + k]), acc);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) {
-            // ext = [||goal_body||, v, omega] (rrt_rl_estimator.py:59-62), float32
-            float gx = o[0], gy = o[1];
-            float e0 = sqrtf(gx * gx + gy * gy);
-            acc = fmaf(e0, __ldg(&P[O_WL + 64]), acc);
-            acc = fmaf(o[2], __ldg(&P[O_WL + 65]), acc);
-            acc = fmaf(o[3], __ldg(&P[O_WL + 66]), acc);
-            acc += __ldg(&P[O_BL]);
+        // ext = [||goal_body||, v, omega] (rrt_rl_estimator.py:59-62), float32
+        float gx = o[0], gy = o[1];
+        float e0 = sqrtf(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+        float acc = cnn_head(P, s_d, e0, o[2], o[3]);
+        if (threadIdx.x == 0) {
             if (net == 0) est[b] = acc;
             else prob[b] = 1.0f / (1.0f + expf(-acc));
         }
@@ -373,6 +390,159 @@ extern "C" int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, 
     CRLK_REQUIRE(ld_obs >= 733, "ld_obs < 733");
     dim3 grid(B, 2);
     k_estimator<<<grid, CNN_THREADS, 0, (cudaStream_t)stream>>>(e->d_params, obs, ld_obs, B, est, prob);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+
+// ---- RRT_RL_Estimator.choose_parent on the device (rrt_rl_estimator.py:26-79) ----
+
+// per node: Euclidean distance to the query's target and the [1, 20) filter (:29-31)
+__global__ void k_cp_dist(const double *__restrict__ states, long long stride, const int *__restrict__ n_nodes,
+                          int max_nodes, const double *__restrict__ targets, int Q, double *dist, int *skip)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Q * max_nodes) return;
+    int q = (int)(i / max_nodes), n = (int)(i - (long long)q * max_nodes);
+    if (n >= n_nodes[q]) { skip[i] = 1; dist[i] = CUDART_INF; return; }
+    const double *s = states + ((size_t)stride * q + n) * 5;
+    double dx = s[0] - targets[5 * (size_t)q], dy = s[1] - targets[5 * (size_t)q + 1];
+    double dd = sqrt(fma(dy, dy, __dmul_rn(dx, dx)));            // np.linalg.norm
+    dist[i] = dd;
+    skip[i] = (dd >= 1.0 && dd < 20.0) ? 0 : 1;
+}
+
+// One CTA per candidate node: local observation (differential_gym.py:180-190)
+// straight into shared memory, then both CNNs (estimator/network.py).
+__global__ void __launch_bounds__(CNN_THREADS)
+k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const double *__restrict__ states,
+                  long long stride, int max_nodes, const double *__restrict__ targets,
+                  const int *__restrict__ skip, long long rows, float *__restrict__ est, float *__restrict__ prob)
+{
+    __shared__ float s_in[27 * 27];
+    __shared__ float s_a[8 * 13 * 13];
+    __shared__ float s_b[16 * 6 * 6];
+    __shared__ float s_c[32 * 3 * 3];
+    __shared__ float s_d[64];
+    __shared__ float s_ext[4];
+    const long long row = blockIdx.x;
+    if (row >= rows || skip[row]) return;
+    const int q = (int)(row / max_nodes), nidx = (int)(row - (long long)q * max_nodes);
+    const double *st = states + ((size_t)stride * q + nidx) * 5;
+    const double x = st[0], y = st[1];
+    double sn, cs;
+    sincos(st[2], &sn, &cs);
+    bool nearp = false;
+    for (int p = threadIdx.x; p < OBS_NPTS; p += CNN_THREADS) {
+        int ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;
+        double px, py;
+        body_to_world(cs, sn, x, y, arange_at(og.ba0, og.ba1, og.bad, ib), arange_at(og.lr0, og.lr1, og.lrd, il),
+                      px, py);
+        s_in[p] = local_map_occupied(os, px, py, nearp) ? 0.f : 1.f;
+    }
+    if (threadIdx.x == 0) {
+        double qx = __dadd_rn(targets[5 * (size_t)q], -x), qy = __dadd_rn(targets[5 * (size_t)q + 1], -y);
+        float gbx = (float)__dadd_rn(__dmul_rn(cs, qx), __dmul_rn(sn, qy));
+        float gby = (float)__dadd_rn(__dmul_rn(-sn, qx), __dmul_rn(cs, qy));
+        s_ext[0] = sqrtf(__fadd_rn(__fmul_rn(gbx, gbx), __fmul_rn(gby, gby)));   // torch.norm in float32 (:59)
+        s_ext[1] = (float)st[3];
+        s_ext[2] = (float)st[4];
+    }
+    __syncthreads();
+    for (int net = 0; net < 2; net++) {
+        const float *P = params + (size_t)net * CNN_PARAMS;
+        conv_relu_pool<1, 8, 27>(P + O_W1, P + O_B1, s_in, s_a);
+        __syncthreads();
+        conv_relu_pool<8, 16, 13>(P + O_W2, P + O_B2, s_a, s_b);
+        __syncthreads();
+        conv_relu_pool<16, 32, 6>(P + O_W3, P + O_B3, s_b, s_c);
+        __syncthreads();
+        conv4_avgpool(P, s_c, s_d);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float acc = cnn_head(P, s_d, s_ext[0], s_ext[1], s_ext[2]);
+            if (threadIdx.x == 0) {
+                if (net == 0) est[row] = acc;
+                else prob[row] = 1.0f / (1.0f + expf(-acc));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// per query: cost = (est + 1) * 15 + 100 * (1 - round(prob)) on the filtered nodes (float32
+// arithmetic, :70-74), the plain distance elsewhere; first minimum (:76); (0, 100) if no
+// node passed the filter (:33-34).
+__global__ void __launch_bounds__(256)
+k_cp_final(const double *__restrict__ dist, const int *__restrict__ skip, const float *__restrict__ est,
+           const float *__restrict__ prob, const int *__restrict__ n_nodes, int max_nodes, int Q, int *idx,
+           double *cost)
+{
+    __shared__ double sv[8];
+    __shared__ int si[8], sany[8];
+    const int q = blockIdx.x;
+    if (q >= Q) return;
+    const int n = n_nodes[q];
+    double best = CUDART_INF;
+    int bi = 0x7fffffff, any = 0;
+    for (int k = threadIdx.x; k < n; k += 256) {
+        size_t i = (size_t)q * max_nodes + k;
+        double c = dist[i];
+        if (!skip[i]) {
+            float fail = 1.0f - rintf(prob[i]);
+            c = (double)__fmul_rn(__fadd_rn(est[i], 1.0f), 15.0f);
+            c = c + (double)__fmul_rn(100.0f, fail);
+            any = 1;
+        }
+        if (c < best || (c == best && k < bi)) { best = c; bi = k; }
+    }
+    warp_argmin(best, bi);
+    any = __any_sync(0xffffffffu, any);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sv[warp] = best; si[warp] = bi; sany[warp] = any; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+            if (sv[w] < best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+            any |= sany[w];
+        }
+        if (!any) { idx[q] = 0; cost[q] = 100.0; }
+        else { idx[q] = bi; cost[q] = best; }
+    }
+}
+
+extern "C" int64_t crlk_estimator_cp_workspace_bytes(int32_t Q, int32_t max_nodes)
+{
+    if (Q <= 0 || max_nodes <= 0) return 0;
+    int64_t rows = (int64_t)Q * max_nodes;
+    return rows * (8 + 4 + 4 + 4) + 1024;
+}
+
+extern "C" int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstimator *e, const double *states,
+                                            int64_t stride, const int32_t *n_nodes, int32_t max_nodes,
+                                            const double *targets, int32_t Q, int32_t *idx, double *cost,
+                                            void *workspace, void *stream)
+{
+    CRLK_REQUIRE(env && e, "env/estimator is NULL");
+    CRLK_REQUIRE(Q >= 0 && max_nodes >= 1 && stride >= max_nodes, "shape");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(states && n_nodes && targets && idx && cost && workspace, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)Q * max_nodes;
+    CRLK_REQUIRE(rows < 2147483647LL, "too many candidate nodes for one call");
+    unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    double *dist = (double *)ws;
+    int *skip = (int *)(ws + rows * 8);
+    float *est = (float *)(ws + rows * 12);
+    float *prob = (float *)(ws + rows * 16);
+    k_cp_dist<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(states, (long long)stride, n_nodes, max_nodes,
+                                                            targets, Q, dist, skip);
+    CRLK_LAUNCH_CHECK();
+    k_estimator_nodes<<<(unsigned)rows, CNN_THREADS, 0, st>>>(make_obs_grid(), env->os, e->d_params, states,
+                                                             (long long)stride, max_nodes, targets, skip, rows,
+                                                             est, prob);
+    CRLK_LAUNCH_CHECK();
+    k_cp_final<<<Q, 256, 0, st>>>(dist, skip, est, prob, n_nodes, max_nodes, Q, idx, cost);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -511,11 +681,20 @@ k_rl_step(EnvP e, ExtP x, ObsSet os, const double *__restrict__ targets,
     }
 }
 
+// every executed step consumed one noise draw (net.py:147-150)
+__global__ void k_advance_cursor(int *cursor, const int *__restrict__ n_steps, const uint8_t *__restrict__ active,
+                                 int Q)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q && (!active || active[q])) cursor[q] += n_steps[q];
+}
+
 extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
                               const double *from_states, const double *targets, int32_t Q,
-                              const float *noise, float eps, double *path, int32_t *n_steps,
-                              int32_t *status, int32_t *node_step, int32_t *n_nodes, float *actions,
-                              uint8_t *flags, const uint8_t *active, void *workspace, void *stream)
+                              const float *noise, int32_t noise_rows, int32_t *noise_cursor, float eps,
+                              double *path, int32_t *n_steps, int32_t *status, int32_t *node_step,
+                              int32_t *n_nodes, float *actions, uint8_t *flags, const uint8_t *active,
+                              void *workspace, void *stream)
 {
     CRLK_REQUIRE(env && p, "env/policy is NULL");
     CRLK_REQUIRE(p->dims[0] == 733, "the actor must take the 733-vector observation");
@@ -527,6 +706,7 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
     CRLK_REQUIRE(from_states && targets && path && n_steps && status && node_step && n_nodes && workspace,
                  "NULL array");
     CRLK_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    CRLK_REQUIRE(!noise || noise_rows >= (noise_cursor ? 1 : x.n_max_extend), "noise_rows too small");
     cudaStream_t st = (cudaStream_t)stream;
     RlWs w;
     rl_carve(p, Q, (unsigned char *)workspace, &w);
@@ -538,12 +718,16 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
         rc = crlk_local_obs_masked(env, w.state, targets, 5, Q, w.obs, 736, w.done, stream);
         if (rc) return rc;
         // action = policy(obs) (rrt_rl.py:41)
-        rc = policy_forward_impl(p, w.obs, 736, noise ? noise + (size_t)(k - 1) * 2 : nullptr,
-                                 (long long)x.n_max_extend * 2, eps, Q, w.act, w.mlp, st);
+        rc = policy_forward_impl(p, w.obs, 736, noise, (long long)noise_rows * 2, noise_cursor, k - 1, eps, Q,
+                                 w.act, w.mlp, st);
         if (rc) return rc;
         k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->os, targets, w.act, k, Q,
                                               w.state, w.done, w.nn, path, n_steps, status, node_step,
                                               n_nodes, actions, flags);
+        CRLK_LAUNCH_CHECK();
+    }
+    if (noise && noise_cursor) {
+        k_advance_cursor<<<(Q + 127) / 128, 128, 0, st>>>(noise_cursor, n_steps, active, Q);
         CRLK_LAUNCH_CHECK();
     }
     return CRLK_OK;

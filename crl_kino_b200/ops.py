@@ -286,7 +286,23 @@ def estimator_forward(est, obs32):
     return e, p
 
 
-def extend_rl(env, pol, xp, from_states, targets, noise=None, eps=0.0, active=None, want_actions=False):
+def estimator_choose_parent(env, est, states, n_nodes, targets, max_nodes=None):
+    """states: float64 CUDA [Q, stride, 5]; n_nodes int32 [Q]; targets [Q, 5] -> (idx i32[Q], cost f64[Q])."""
+    Q, stride, _ = states.shape
+    targets = as_dev(targets).reshape(Q, 5)
+    n_nodes = n_nodes.to(device=states.device, dtype=torch.int32).contiguous()
+    max_nodes = int(max_nodes or stride)
+    idx = torch.empty(Q, dtype=torch.int32, device=states.device)
+    cost = torch.empty(Q, dtype=torch.float64, device=states.device)
+    nbytes = lib().crlk_estimator_cp_workspace_bytes(Q, max_nodes)
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=states.device)
+    check(lib().crlk_estimator_choose_parent(env.h, est.h, _ptr(states), stride, _ptr(n_nodes), max_nodes,
+                                             _ptr(targets), Q, _ptr(idx), _ptr(cost), _ptr(ws), _stream()))
+    return idx, cost
+
+
+def extend_rl(env, pol, xp, from_states, targets, noise=None, eps=0.0, active=None, want_actions=False,
+              noise_cursor=None):
     from_states = as_dev(from_states).reshape(-1, 5)
     Q = from_states.shape[0]
     targets = as_dev(targets).reshape(Q, 5)
@@ -300,13 +316,16 @@ def extend_rl(env, pol, xp, from_states, targets, noise=None, eps=0.0, active=No
                flags=torch.empty(Q, dtype=torch.uint8, device=d),
                actions=torch.zeros(Q, xp.n_max_extend, 2, dtype=torch.float32, device=d)
                if want_actions else None)
+    noise_rows = 0
     if noise is not None:
-        noise = as_dev(noise, torch.float32).reshape(Q, xp.n_max_extend, 2)
+        noise = as_dev(noise, torch.float32).reshape(Q, -1, 2)
+        noise_rows = noise.shape[1]
     nbytes = lib().crlk_extend_rl_workspace_bytes(pol.h, Q)
     ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=d)
     off = (-ws.data_ptr()) % 256
     check(lib().crlk_extend_rl(env.h, pol.h, C.byref(xp), _ptr(from_states), _ptr(targets), Q,
-                               _ptr(noise), float(eps), _ptr(out["path"]), _ptr(out["n_steps"]),
+                               _ptr(noise), noise_rows, _ptr(noise_cursor), float(eps), _ptr(out["path"]),
+                               _ptr(out["n_steps"]),
                                _ptr(out["status"]), _ptr(out["node_step"]), _ptr(out["n_nodes"]),
                                _ptr(out["actions"]), _ptr(out["flags"]), _ptr(active),
                                C.c_void_p(ws.data_ptr() + off), _stream()))

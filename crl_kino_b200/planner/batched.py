@@ -192,7 +192,8 @@ class BatchedRRT:
         self._fv = fv
         self._C = C
         self._ExtendView = ExtendView
-        self.noise = None
+        self.noise = None             # float32 [Q, rows, 2] standard-normal stream per query (eps != 0)
+        self.noise_cursor = torch.zeros(Q, dtype=torch.int32, device=d)
 
     # ---- one extension pass ------------------------------------------------
     def _extend(self, slot, from_states, targets, active):
@@ -201,7 +202,8 @@ class BatchedRRT:
                                             active=active, out=self.out[slot], stats=self.stats)
         else:
             self.out[slot] = ops.extend_rl(self.env.handle, self.policy.actor.handle, self.xp, from_states,
-                                           targets, self.noise, self.eps, active=active)
+                                           targets, self.noise, self.eps, active=active,
+                                           noise_cursor=self.noise_cursor if self.noise is not None else None)
         return self.out[slot]
 
     def _append(self, out, parent_idx, active, primary):
@@ -234,10 +236,13 @@ class BatchedRRT:
         self._append(out2, self.retry_parent, self.retry_active, False)               # rrt.py:81-83
         self.rounds += 1
 
-    def plan(self, streams, check_every=8, max_rounds=None):
+    def plan(self, streams, check_every=8, max_rounds=None, noise=None):
         """streams: float64 [Q, S, 5] pre-drawn samples per query (host or device).
+        noise: float32 [Q, rows, 2] exploration draws per query (RL steering with eps != 0).
         Runs rounds until every query is done or its stream is exhausted."""
         streams = ops.as_dev(streams)
+        if noise is not None:
+            self.noise = ops.as_dev(noise, torch.float32).contiguous()
         S = streams.shape[1]
         max_rounds = min(S, max_rounds or S)
         step = torch.zeros(self.Q, dtype=torch.int32, device=streams.device)

@@ -15,28 +15,10 @@ class RRT_RL_Estimator(RRT_RL):
         self.classifier = classifier
 
     def choose_parent(self, node_list, rnd_node):
-        """rrt_rl_estimator.py:26-79."""
-        states = np.array([n.state for n in node_list], dtype=np.float64)
-        tgt = np.asarray(rnd_node.state, dtype=np.float64)
-        sd = ops.as_dev(states)
-        # per-node Euclidean distance on the device (one-node trees share the nearest kernel)
-        n = sd.shape[0]
-        x = sd[:, 0:1].contiguous()
-        y = sd[:, 1:2].contiguous()
-        ones = torch.ones(n, dtype=torch.int32, device=sd.device)
-        _, dist, _ = ops.nearest(x, y, ones, np.tile(tgt[None, :2], (n, 1)))
-        valid = (dist >= 1.0) & (dist < 20.0)
-        vidx = torch.nonzero(valid).reshape(-1)
-        if vidx.numel() == 0:
-            return 0, 100
-        goals = ops.as_dev(np.tile(tgt[None], (int(vidx.numel()), 1)))
-        _, obs32, _ = ops.local_obs(self.robot_env.handle, sd[vidx].contiguous(), goals,
-                                    want64=False, want32=True)
-        est = self.estimator.forward_obs(obs32).double()
-        prob = self.classifier.forward_obs(obs32).double()
-        fail = 1 - torch.round(prob)
-        cost = dist.clone()
-        cost[vidx] = (est + 1) * 15 + 100 * fail
-        c = cost.cpu().numpy()
-        i = int(np.argmin(c))
-        return i, c[i]
+        """rrt_rl_estimator.py:26-79: distance filter, observations, both CNNs, cost and
+        argmin in one device call (crlk_estimator_choose_parent)."""
+        states = ops.as_dev(np.array([n.state for n in node_list], dtype=np.float64))[None].contiguous()
+        n = torch.tensor([len(node_list)], dtype=torch.int32, device=states.device)
+        idx, cost = ops.estimator_choose_parent(self.robot_env.handle, self.estimator.pair.handle, states, n,
+                                                np.asarray(rnd_node.state, dtype=np.float64)[None])
+        return int(idx[0].item()), float(cost[0].item())

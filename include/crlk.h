@@ -200,13 +200,18 @@ int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_t ld_obs, c
 int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
 
 /* RRT_RL.steer (planner/rrt_rl.py:22-63): like crlk_extend_dwa with the policy
- * as controller.  noise dev f32[Q x n_max_extend x 2] (nullable), consumed one
- * row per executed step.  workspace: crlk_extend_rl_workspace_bytes. */
+ * as controller.  noise dev f32[Q x noise_rows x 2] (nullable): standard-normal draws,
+ * one row per executed step (the reference draws torch.randn inside the actor,
+ * net.py:147-150).  noise_cursor dev i32[Q] (nullable): first row to use per query;
+ * advanced by the number of executed steps, so consecutive extensions of a query
+ * walk its stream (the caller keeps noise_rows large enough).  Without a cursor
+ * row k-1 is used at step k (noise_rows >= n_max_extend).
+ * workspace: crlk_extend_rl_workspace_bytes. */
 int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
                    const double *from_states, const double *targets, int32_t Q, const float *noise,
-                   float eps, double *path, int32_t *n_steps, int32_t *status, int32_t *node_step,
-                   int32_t *n_nodes, float *actions, uint8_t *flags, const uint8_t *active,
-                   void *workspace, void *stream);
+                   int32_t noise_rows, int32_t *noise_cursor, float eps, double *path, int32_t *n_steps,
+                   int32_t *status, int32_t *node_step, int32_t *n_nodes, float *actions, uint8_t *flags,
+                   const uint8_t *active, void *workspace, void *stream);
 int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q);
 
 /* ---- learned parent selection (estimator/network.py, rrt_rl_estimator.py:57-74) ---- */
@@ -219,6 +224,18 @@ int crlk_estimator_destroy(CrlkEstimator *e);
 /* obs dev f32[B x ld_obs] (the 733-vector of crlk_local_obs); est, prob dev f32[B]. */
 int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, int32_t ld_obs, int32_t B,
                            float *est, float *prob, void *stream);
+
+/* RRT_RL_Estimator.choose_parent (planner/rrt_rl_estimator.py:26-79) for Q queries at once:
+ * per node the Euclidean distance to the query's target; nodes with 1 <= d < 20 get their local
+ * observation built and scored by both CNNs: cost = (est + 1) * 15 + 100 * (1 - round(prob));
+ * other nodes keep the distance as cost; first minimum.  (0, 100) when no node passes the filter.
+ *   states dev f64[Q x stride x 5] node tables, n_nodes dev i32[Q], targets dev f64[Q x 5]
+ *   idx dev i32[Q], cost dev f64[Q]; workspace: crlk_estimator_cp_workspace_bytes(Q, max_nodes). */
+int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstimator *e, const double *states,
+                                 int64_t stride, const int32_t *n_nodes, int32_t max_nodes,
+                                 const double *targets, int32_t Q, int32_t *idx, double *cost,
+                                 void *workspace, void *stream);
+int64_t crlk_estimator_cp_workspace_bytes(int32_t Q, int32_t max_nodes);
 
 /* ---- planner bookkeeping on the device: RRT.planning (planner/rrt.py:51-89) ---- */
 

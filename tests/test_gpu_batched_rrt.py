@@ -65,3 +65,54 @@ def test_batched_rrt_vs_oracle_dense_map():
         np.testing.assert_allclose(np.array(p.final_course(q)), np.array(port.path), rtol=1e-7, atol=1e-9)
         n_ok += 1
     assert n_ok >= Q - 1, f"only {n_ok}/{Q} queries identical to the planner port"
+
+
+def _policy(seed=0):
+    from crl_kino_b200.env import DifferentialDriveGym
+    from crl_kino_b200.policy.rl_policy import load_policy
+    return load_policy(DifferentialDriveGym(), [1024, 512, 512, 512], None, seed=seed)
+
+
+def _check_rl_tree(states, parents, path, g, kind):
+    assert np.array_equal(parents, g[kind + "_parents"])
+    np.testing.assert_allclose(states, g[kind + "_node_states"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(np.array(path), g[kind + "_path"], rtol=1e-4, atol=1e-4)
+
+
+def test_batched_rrt_rl_reproduces_reference_run():
+    """RRT_RL.planning (policy steering, eps = 0.05) with the recorded sample and noise streams."""
+    from crl_kino_b200.planner.batched import BatchedRRT
+    g = golden("plan_rl")
+    env, _ = make_envs(fixture_map("test_env1"))
+    start, goal = np.array([[-5, -15, 0, 0, 0.0]]), np.array([[10, 10, 0, 0, 0.0]])
+    p = BatchedRRT(env, start, goal, max_iter=int(g["rl_max_iter"]), policy=_policy(int(g["seed"])), eps=0.05)
+    noise = np.concatenate([g["rl_noise"], np.zeros((128, 2), dtype=np.float32)])[None]
+    reached = p.plan(g["rl_samples"][None], check_every=4, noise=noise)
+    states, parents = p.tree(0)
+    _check_rl_tree(states, parents, p.final_course(0), g, "rl")
+    assert int(p.noise_cursor[0].item()) == len(g["rl_noise"])          # one draw per executed step
+    assert bool(reached[0]) == bool(g["rl_reach"])
+
+
+def test_rrt_rl_estimator_class_reproduces_reference_run():
+    """RRT_RL_Estimator (learned parent selection + policy steering), single-query drop-in class."""
+    from crl_kino_b200.estimator import load_estimator
+    from crl_kino_b200.planner.rrt_rl_estimator import RRT_RL_Estimator
+    g = golden("plan_rl")
+    w = golden("estimator_weights")
+    est, cls = load_estimator({k[4:]: w[k] for k in w.files if k.startswith("est.")},
+                              {k[4:]: w[k] for k in w.files if k.startswith("cls.")})
+    env, _ = make_envs(fixture_map("test_env1"))
+    p = RRT_RL_Estimator(env, _policy(int(g["seed"])), est, cls, max_iter=int(g["rl_est_max_iter"]))
+    p.verbose = False
+    p.set_start_and_goal(np.array([-5, -15, 0, 0, 0.0]), np.array([10, 10, 0, 0, 0.0]))
+    it = iter(g["rl_est_samples"])
+    p.sample = lambda goal: p.Node(next(it))
+    p.set_noise_stream(np.concatenate([g["rl_est_noise"], np.zeros((64, 2), dtype=np.float32)]))
+    path = p.planning()
+    index = {id(n): i for i, n in enumerate(p.node_list)}
+    parents = np.array([-1 if n.parent is None else index[id(n.parent)] for n in p.node_list])
+    states = np.array([n.state for n in p.node_list])
+    _check_rl_tree(states, parents, path, g, "rl_est")
+    assert p.n_control_steps == len(g["rl_est_noise"])
+    assert next(it, None) is None                                      # every recorded sample was consumed
