@@ -17,6 +17,7 @@
 // quadrant each).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "crlk_internal.h"
 
@@ -136,6 +137,44 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16 &a, __nv_bfloat16 
     c = __float2bfloat16_rn(r2);
 }
 
+// bias + ReLU on 32 accumulator columns of one row; writes float32 and/or the
+// three bf16 planes of the next layer's operand.
+__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int m, int n, const float *__restrict__ bias,
+                                               int Mpad, __nv_bfloat16 *__restrict__ planes_out, int ld_out,
+                                               float *__restrict__ c32, int ldc)
+{
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = fmaxf(__uint_as_float(r[j]) + __ldg(&bias[n + j]), 0.f);
+    if (c32) {
+        float4 *dst = reinterpret_cast<float4 *>(c32 + (size_t)m * ldc + n);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (planes_out) {
+        uint32_t p0[16], p1[16], p2[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            __nv_bfloat16 a0, b0, c0, a1, b1, c1;
+            split3(v[2 * j], a0, b0, c0);
+            split3(v[2 * j + 1], a1, b1, c1);
+            p0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
+            p1[j] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+            p2[j] = (uint32_t)__bfloat16_as_ushort(c0) | ((uint32_t)__bfloat16_as_ushort(c1) << 16);
+        }
+        const size_t plane = (size_t)Mpad * ld_out;
+        uint4 *d0 = reinterpret_cast<uint4 *>(planes_out + (size_t)m * ld_out + n);
+        uint4 *d1 = reinterpret_cast<uint4 *>(planes_out + plane + (size_t)m * ld_out + n);
+        uint4 *d2 = reinterpret_cast<uint4 *>(planes_out + 2 * plane + (size_t)m * ld_out + n);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            d0[j] = make_uint4(p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+            d1[j] = make_uint4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+            d2[j] = make_uint4(p2[4 * j], p2[4 * j + 1], p2[4 * j + 2], p2[4 * j + 3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the GEMM
 
 // planes_out: [3][Mpad][ld_out] bf16 (nullable), c32: [B][ldc] float (nullable).
@@ -206,39 +245,7 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int c = 0; c < TC_BN / 32; c++) {
             uint32_t r[32];
             tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
-            if (m < B) {
-                const int n = n0 + 32 * c;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = fmaxf(__uint_as_float(r[j]) + __ldg(&bias[n + j]), 0.f);
-                if (c32) {
-                    float4 *dst = reinterpret_cast<float4 *>(c32 + (size_t)m * ldc + n);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-                if (planes_out) {
-                    uint32_t p0[16], p1[16], p2[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        __nv_bfloat16 a0, b0, c0, a1, b1, c1;
-                        split3(v[2 * j], a0, b0, c0);
-                        split3(v[2 * j + 1], a1, b1, c1);
-                        p0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
-                        p1[j] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-                        p2[j] = (uint32_t)__bfloat16_as_ushort(c0) | ((uint32_t)__bfloat16_as_ushort(c1) << 16);
-                    }
-                    const size_t plane = (size_t)Mpad * ld_out;
-                    uint4 *d0 = reinterpret_cast<uint4 *>(planes_out + (size_t)m * ld_out + n);
-                    uint4 *d1 = reinterpret_cast<uint4 *>(planes_out + plane + (size_t)m * ld_out + n);
-                    uint4 *d2 = reinterpret_cast<uint4 *>(planes_out + 2 * plane + (size_t)m * ld_out + n);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        d0[j] = make_uint4(p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
-                        d1[j] = make_uint4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
-                        d2[j] = make_uint4(p2[4 * j], p2[4 * j + 1], p2[4 * j + 2], p2[4 * j + 3]);
-                    }
-                }
-            }
+            if (m < B) epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -246,6 +253,207 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_BN));
+    }
+}
+
+// Variant with plane-complete stages: one stage holds the three A planes and the
+// three W planes of a k block (6 tiles, 96 KB), and all six plane products are
+// issued from it.  Each operand tile is then fetched from L2 once per k block
+// instead of up to three times (the 128x128x64 tile at 64 FLOP per staged byte
+// is L2-bandwidth bound otherwise).  2 stages, 1 CTA per SM.
+#define TCF_STAGES 2
+#define TCF_STAGE_BYTES (6 * TC_STAGE_BYTES)
+#define TCF_SMEM_BYTES (TCF_STAGES * TCF_STAGE_BYTES + 1024 + 256)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16x3_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
+                    __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + TCF_STAGES * TCF_STAGE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * TCF_STAGES, tfull = bars + 16 * TCF_STAGES;
+    const uint32_t tslot = tfull + 8;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + TCF_STAGES * TCF_STAGE_BYTES + 16 * TCF_STAGES + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TCF_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(TC_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        for (int kb = 0; kb < kblocks; kb++) {
+            int s = kb % TCF_STAGES, ph = (kb / TCF_STAGES) & 1;
+            uint32_t st = base + s * TCF_STAGE_BYTES;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            mbar_expect_tx(full0 + 8 * s, TCF_STAGE_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++) {
+                tma_load_2d(st + pl * TC_STAGE_BYTES, &tmA, kb * TC_BK, pl * Mpad + m0, full0 + 8 * s);
+                tma_load_2d(st + (3 + pl) * TC_STAGE_BYTES, &tmW, kb * TC_BK, pl * N + n0, full0 + 8 * s);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+        for (int kb = 0; kb < kblocks; kb++) {
+            int s = kb % TCF_STAGES, ph = (kb / TCF_STAGES) & 1;
+            uint32_t st = base + s * TCF_STAGE_BYTES;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int pair = 0; pair < TC_NPAIR; pair++) {
+                uint64_t da = umma_desc_sw128(st + c_pair_a[pair] * TC_STAGE_BYTES);
+                uint64_t db = umma_desc_sw128(st + (3 + c_pair_w[pair]) * TC_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; k++)
+                    umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | pair | k) != 0);
+            }
+            umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int m = m0 + 32 * q + lane;
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; c++) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+            if (m < B) epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_BN));
+    }
+}
+
+// Persistent variant of the plane-complete kernel: one CTA per SM loops over
+// output tiles; the accumulator is double buffered in TMEM (2 x 128 columns) so
+// the epilogue of tile i (TMEM -> registers -> bias/ReLU/split -> global) runs
+// under the MMAs of tile i + 1.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                      int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
+                      __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + TCF_STAGES * TCF_STAGE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * TCF_STAGES;
+    const uint32_t tfull0 = bars + 16 * TCF_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tslot = tempty0 + 16;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + TCF_STAGES * TCF_STAGE_BYTES + 16 * TCF_STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = N / TC_BN, tiles = tiles_n * (Mpad / TC_BM);
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TCF_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(2 * TC_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        int git = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * TC_BN;
+            for (int kb = 0; kb < kblocks; kb++, git++) {
+                int s = git % TCF_STAGES, ph = (git / TCF_STAGES) & 1;
+                uint32_t st = base + s * TCF_STAGE_BYTES;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, TCF_STAGE_BYTES);
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    tma_load_2d(st + pl * TC_STAGE_BYTES, &tmA, kb * TC_BK, pl * Mpad + m0, full0 + 8 * s);
+                    tma_load_2d(st + (3 + pl) * TC_STAGE_BYTES, &tmW, kb * TC_BK, pl * N + n0, full0 + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+        int git = 0, ti = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ti++) {
+            const int as = ti & 1, aph = (ti >> 1) & 1;
+            mbar_wait(tempty0 + 8 * as, aph ^ 1);            // epilogue drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + (uint32_t)(as * TC_BN);
+            for (int kb = 0; kb < kblocks; kb++, git++) {
+                int s = git % TCF_STAGES, ph = (git / TCF_STAGES) & 1;
+                uint32_t st = base + s * TCF_STAGE_BYTES;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int pair = 0; pair < TC_NPAIR; pair++) {
+                    uint64_t da = umma_desc_sw128(st + c_pair_a[pair] * TC_STAGE_BYTES);
+                    uint64_t db = umma_desc_sw128(st + (3 + c_pair_w[pair]) * TC_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        umma_bf16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | pair | k) != 0);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(tfull0 + 8 * as);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        int ti = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ti++) {
+            const int as = ti & 1, aph = (ti >> 1) & 1;
+            const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * TC_BN;
+            const int m = m0 + 32 * q + lane;
+            mbar_wait(tfull0 + 8 * as, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * TC_BN + 32 * c), r);
+                if (c == TC_BN / 32 - 1) {
+                    // all of this warp's TMEM reads are done: hand the accumulator back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+                }
+                if (m < B) epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TC_BN));
     }
 }
 
@@ -368,6 +576,8 @@ int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_ho
         if (rc) return rc;
     }
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
     *out = t;
     return CRLK_OK;
 }
@@ -412,9 +622,24 @@ int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, 
         if (rc) return rc;
         bool is_last = (i == t->n_hidden - 1);
         dim3 grid(L.N / TC_BN, Mpad / TC_BM);
-        k_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
-            mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
-            is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
+        static const bool unfused = getenv("CRLK_MLP_UNFUSED") != nullptr;    // A/B switches
+        static const bool persist = getenv("CRLK_MLP_NOPERSIST") == nullptr;
+        static int n_sms = 0;
+        if (!n_sms) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dv); }
+        if (unfused)
+            k_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
+                mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
+                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
+        else if (persist) {
+            int tiles = (L.N / TC_BN) * (Mpad / TC_BM);
+            int ctas = tiles < n_sms ? tiles : n_sms;
+            k_gemm_bf16x3_persist<<<ctas, TC_THREADS, TCF_SMEM_BYTES, st>>>(
+                mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
+                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
+        } else
+            k_gemm_bf16x3_fused<<<grid, TC_THREADS, TCF_SMEM_BYTES, st>>>(
+                mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
+                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
         CRLK_LAUNCH_CHECK();
     }
     *out = last;
