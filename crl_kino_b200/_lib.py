@@ -37,6 +37,11 @@ class ExtendView(C.Structure):
                 ("node_step", C.c_void_p), ("n_nodes", C.c_void_p)]
 
 
+class PlanParams(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("d_min", C.c_double), ("d_max", C.c_double),
+                ("goal_radius", C.c_double), ("retry_radius", C.c_double)]
+
+
 class ExtendParams(C.Structure):
     _fields_ = [("n_max_extend", C.c_int32), ("n_tree", C.c_int32), ("step_dt", C.c_double),
                 ("reach_radius", C.c_double)]
@@ -74,6 +79,7 @@ PROTOTYPES = {
     "crlk_estimator_cp_workspace_bytes": (I64, [I32, I32]),
     "crlk_rrt_select": (C.c_int, [P, P, I32, I32, F64, F64, P, P, P, P]),
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
+    "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),
     "crlk_policy_destroy": (C.c_int, [P]),
     "crlk_policy_forward": (C.c_int, [P, P, I32, P, F32, I32, P, P, P]),

@@ -1099,6 +1099,71 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, double x, double
     return (any_coll ? 1 : 0) | ((any_mar && !any_def) ? 2 : 0);
 }
 
+struct ExtResult {
+    int nn, status, steps, flags;
+    unsigned long long rolls;
+};
+
+// RRT.steer (rrt.py:99-135) by one CTA: up to n_max_extend closed-loop control
+// steps from s_state (block-uniform, shared memory; overwritten with the last
+// executed state) toward (gx, gy).  path (nullable) receives one row of 5 per
+// executed step; ctrl_idx (nullable) the chosen rollout per step.  on_node(k_node,
+// step) is called by EVERY thread (uniformly) when a node is emitted at `step`
+// with the node's state in s_state; it returns false to stop the extension
+// (capacity exhausted).  Every thread returns the same result.
+template <class OnNode>
+__device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &x, const ObsSet &os,
+                                      const DwaSmem &sm, double *s_state, double *s_next, double gx,
+                                      double gy, double *path, int *ctrl_idx, OnNode on_node)
+{
+    const int tid = threadIdx.x;
+    ExtResult res;
+    res.nn = 0; res.status = CRLK_EXT_TIMEOUT; res.steps = 0; res.flags = 0; res.rolls = 0;
+    for (int k = 1; k <= x.n_max_extend; k++) {
+        // rrt.py:116-118: control, then thread 0 advances the state inside the
+        // control block's closing section (no extra barrier round trip)
+        DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm,
+            [&](double cv, double cw, int ix, const double *row1) {
+                double s[5];
+                if (x.n_sub_step == d.n_sub) {
+                    // executing the control for step_dt == dwa.dt IS the winner's trajectory row 1
+                    for (int c = 0; c < 5; c++) s[c] = row1[c];
+                } else {
+                    for (int c = 0; c < 5; c++) s[c] = s_state[c];
+                    motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
+                }
+                for (int c = 0; c < 5; c++) s_next[c] = s[c];
+                if (path)
+                    for (int c = 0; c < 5; c++) path[(size_t)(k - 1) * 5 + c] = s[c];
+                if (ctrl_idx) ctrl_idx[k - 1] = ix;
+            });
+        res.flags |= r.near_tie ? 2 : 0;
+        res.rolls += (unsigned long long)r.R;
+        if (tid < 5) s_state[tid] = s_next[tid];
+        __syncthreads();
+        res.steps = k;
+        // rrt.py:121: valid_state_check on the new state
+        PHASE_START();
+        int col = collision_block(e, os, s_state[0], s_state[1], s_state[2], sm.queue, nullptr);
+        PHASE_MARK(8);
+        if (col & 2) res.flags |= 1;
+        col &= 1;
+        if (col == 1) { res.status = CRLK_EXT_COLLISION; break; }
+        double ddx = s_state[0] - gx, ddy = s_state[1] - gy;
+        double dist = sqrt(fma(ddy, ddy, ddx * ddx));                            // rrt.py:124
+        if (dist <= x.reach_radius) {
+            on_node(res.nn, k);
+            res.nn++; res.status = CRLK_EXT_REACHED; break;
+        }
+        if (k % x.n_tree == 0) {                                                 // rrt.py:128
+            bool go = on_node(res.nn, k);
+            res.nn++;
+            if (!go) break;
+        }
+    }
+    return res;
+}
+
 __global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
 k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
              const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
@@ -1110,7 +1175,6 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5], s_next[5];
-    __shared__ int s_ctl[8];
     __shared__ int s_q;
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
@@ -1132,57 +1196,20 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
         if (tid < 5) s_state[tid] = from_states[5 * (size_t)q + tid];
         __syncthreads();
         const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
-        int nn = 0, st_code = CRLK_EXT_TIMEOUT, steps = 0, fl = 0;
-        unsigned long long rolls = 0;
-        for (int k = 1; k <= x.n_max_extend; k++) {
-            // rrt.py:116-118: control, then thread 0 advances the state inside the
-            // control block's closing section (no extra barrier round trip)
-            DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm,
-                [&](double cv, double cw, int ix, const double *row1) {
-                    double s[5];
-                    if (x.n_sub_step == d.n_sub) {
-                        // executing the control for step_dt == dwa.dt IS the winner's trajectory row 1
-                        for (int c = 0; c < 5; c++) s[c] = row1[c];
-                    } else {
-                        for (int c = 0; c < 5; c++) s[c] = s_state[c];
-                        motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
-                    }
-                    for (int c = 0; c < 5; c++) {
-                        s_next[c] = s[c];
-                        path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
-                    }
-                    if (ctrl_idx) ctrl_idx[(size_t)q * x.n_max_extend + (k - 1)] = ix;
-                });
-            fl |= r.near_tie ? 2 : 0;
-            rolls += (unsigned long long)r.R;
-            if (tid < 5) s_state[tid] = s_next[tid];
-            __syncthreads();
-            steps = k;
-            // rrt.py:121: valid_state_check on the new state
-            PHASE_START();
-            int col = collision_block(e, os, s_state[0], s_state[1], s_state[2], sm.queue, s_ctl);
-            PHASE_MARK(8);
-            if (col & 2) fl |= 1;
-            col &= 1;
-            if (col == 1) { st_code = CRLK_EXT_COLLISION; break; }
-            double ddx = s_state[0] - gx, ddy = s_state[1] - gy;
-            double dist = sqrt(fma(ddy, ddy, ddx * ddx));                            // rrt.py:124
-            if (dist <= x.reach_radius) {
-                if (tid == 0) node_step[(size_t)q * per + nn] = k;
-                nn++; st_code = CRLK_EXT_REACHED; break;
-            }
-            if (k % x.n_tree == 0) {                                                 // rrt.py:128
-                if (tid == 0) node_step[(size_t)q * per + nn] = k;
-                nn++;
-            }
-        }
+        ExtResult r = extend_dwa_block(e, d, x, os, sm, s_state, s_next, gx, gy,
+                                       path + (size_t)q * x.n_max_extend * 5,
+                                       ctrl_idx ? ctrl_idx + (size_t)q * x.n_max_extend : nullptr,
+                                       [&](int kn, int step) {
+                                           if (tid == 0) node_step[(size_t)q * per + kn] = step;
+                                           return true;
+                                       });
         if (tid == 0) {
-            n_steps[q] = steps; status[q] = st_code; n_nodes[q] = nn;
-            if (flags) flags[q] = (uint8_t)fl;
+            n_steps[q] = r.steps; status[q] = r.status; n_nodes[q] = r.nn;
+            if (flags) flags[q] = (uint8_t)r.flags;
             if (stats) {
-                atomicAdd(&stats[0], 1ull);                          // extensions
-                atomicAdd(&stats[1], (unsigned long long)steps);     // control steps
-                atomicAdd(&stats[2], rolls);                         // rollouts scored
+                atomicAdd(&stats[0], 1ull);                            // extensions
+                atomicAdd(&stats[1], (unsigned long long)r.steps);     // control steps
+                atomicAdd(&stats[2], r.rolls);                         // rollouts scored
             }
         }
     }
@@ -1243,6 +1270,197 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
     k_extend_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
         env->p, d, x, env->os, from_states, targets, Q, path, n_steps, status, node_step,
         n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// --------------------------- whole-query planning on the device, DWA steering (R12)
+
+struct PlanP {
+    int max_iter, S;
+    double d_min, d_max, goal_radius, retry_radius;
+};
+
+// RRT.choose_parent (rrt.py:156-161) over one tree by the whole CTA: exact
+// float64 distances, first minimum.  Every thread returns the same (idx, dist).
+__device__ __forceinline__ void nearest_block(const double *xs, const double *ys, int lo, int n, double tx,
+                                              double ty, double *red_v, int *red_i, int &idx, double &dist)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double bd = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int j = lo + tid; j < n; j += DWA_THREADS) {
+        double dx = xs[j] - tx, dy = ys[j] - ty;
+        double dd = sqrt(fma(dy, dy, dx * dx));          // np.linalg.norm of a 2-vector
+        if (dd < bd) { bd = dd; bi = j; }
+    }
+    warp_argmin(bd, bi);
+    __syncthreads();                                     // earlier readers of red_v / red_i are done
+    if (lane == 0) { red_v[warp] = bd; red_i[warp] = bi; }
+    __syncthreads();
+    bd = red_v[0]; bi = red_i[0];
+#pragma unroll
+    for (int w = 1; w < DWA_THREADS / 32; w++) {
+        double ob = red_v[w];
+        int oi = red_i[w];
+        if (ob < bd || (ob == bd && oi < bi)) { bd = ob; bi = oi; }
+    }
+    idx = bi; dist = bd;
+}
+
+// RRT.planning (rrt.py:51-89) with DWA steering, one CTA per query from the
+// first sample to the last node: sample validity (rrt.py:66), nearest node
+// (:68), acceptance band (:69), extension (:72), node append with path segments
+// (:125-134), goal test (:75) and the steer-to-goal retry (:78-83).  Persistent
+// CTAs pull queries from an atomic counter (queries differ widely in length).
+// The tree is the same SoA forest crlk_rrt_append maintains; sampling stays a
+// pre-drawn per-query stream (the reference's RNG order is host state).
+__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
+k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
+           const double *__restrict__ goals, const double *__restrict__ streams, int Q, int *iters_out,
+           int *cursor_out, uint8_t *reached_out, uint8_t *flags_out, int *overflow, int *work_counter,
+           unsigned long long *stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DwaSmem sm;
+    dwa_carve(d, smem_raw, &sm);
+    __shared__ double s_state[5], s_next[5];
+    __shared__ int s_q;
+    const int tid = threadIdx.x;
+    if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int q = s_q;
+        if (q >= Q) break;
+        const size_t tb = (size_t)f.stride * q;
+        double *tx64 = f.x64 + tb, *ty64 = f.y64 + tb;
+        int n = f.n_nodes[q];
+        int pool_used = f.pool ? f.pool_used[q] : 0;
+        const double gx = goals[5 * (size_t)q], gy = goals[5 * (size_t)q + 1];
+        int iters = 0, cur = 0, fl = 0;
+        bool reached = false, over = false;
+        unsigned long long n_ext = 0, n_ctl = 0, rolls = 0;
+
+        // one extension from node `from` toward (tx, ty); emitted nodes go straight into the tree
+        auto steer = [&](int from, double tx, double ty) {
+            if (f.pool && (long long)pool_used + x.n_max_extend > f.pool_cap) { over = true; return; }
+            __syncthreads();
+            if (tid < 5) s_state[tid] = f.states[(tb + from) * 5 + tid];
+            __syncthreads();
+            double *prow = f.pool ? f.pool + ((size_t)f.pool_cap * q + pool_used) * 5 : nullptr;
+            int prev_step = 0;
+            ExtResult r = extend_dwa_block(e, d, x, os, sm, s_state, s_next, tx, ty, prow, nullptr,
+                [&](int kn, int step) {
+                    if (n >= f.stride) { over = true; return false; }
+                    if (tid < 5) f.states[(tb + n) * 5 + tid] = s_state[tid];
+                    if (tid == 0) {
+                        tx64[n] = s_state[0]; ty64[n] = s_state[1];
+                        if (f.x32) { f.x32[tb + n] = (float)s_state[0]; f.y32[tb + n] = (float)s_state[1]; }
+                        f.parent[tb + n] = (kn == 0) ? from : n - 1;
+                        if (f.pool) {
+                            f.seg_off[tb + n] = pool_used + prev_step;
+                            f.seg_len[tb + n] = step - prev_step;
+                            // Node.path of a steer's first node lacks the parent state (rrt.py:102-104 vs :133)
+                            f.seg_flag[tb + n] = (kn == 0) ? 0 : 1;
+                        }
+                    }
+                    n++; prev_step = step;
+                    return true;
+                });
+            pool_used += prev_step;       // rows past the last emitted node are dropped (rrt.py:121-123)
+            fl |= r.flags;
+            n_ext++; n_ctl += (unsigned long long)r.steps; rolls += r.rolls;
+        };
+        // np.linalg.norm(node_list[-1].state[:2] - goal.state[:2]) <= goal_radius
+        auto last_at_goal = [&]() {
+            __syncthreads();              // the node rows written by threads 0-4 are visible
+            double dx = tx64[n - 1] - gx, dy = ty64[n - 1] - gy;
+            return sqrt(fma(dy, dy, dx * dx)) <= pp.goal_radius;
+        };
+
+        while (iters < pp.max_iter && cur < pp.S && !over) {
+            const double *sp = streams + ((size_t)q * pp.S + cur) * 5;
+            cur++;
+            const double sx = sp[0], sy = sp[1], sth = sp[2];
+            int col = collision_block(e, os, sx, sy, sth, sm.queue, nullptr);         // rrt.py:66
+            if (col & 2) fl |= 1;
+            if (col & 1) continue;
+            int idx;
+            double dist;
+            nearest_block(tx64, ty64, 0, n, sx, sy, sm.red_v, sm.red_i, idx, dist);   // rrt.py:68
+            if (!(dist >= pp.d_min && dist < pp.d_max)) continue;                     // rrt.py:69
+            iters++;
+            const int n0 = n;
+            steer(idx, sx, sy);                                                       // rrt.py:72
+            if (n > n0) {
+                if (last_at_goal()) { reached = true; break; }                        // rrt.py:75
+                int best;
+                double bd;
+                nearest_block(tx64, ty64, n0, n, gx, gy, sm.red_v, sm.red_i, best, bd);   // rrt.py:78
+                if (bd < pp.retry_radius && !over) {
+                    steer(best, gx, gy);                                              // rrt.py:80
+                    if (last_at_goal()) { reached = true; break; }                    // rrt.py:81
+                }
+            }
+        }
+        if (tid == 0) {
+            f.n_nodes[q] = n;
+            if (f.pool) f.pool_used[q] = pool_used;
+            iters_out[q] = iters; cursor_out[q] = cur;
+            reached_out[q] = reached ? 1 : 0;
+            if (flags_out) flags_out[q] = (uint8_t)(fl | (over ? 4 : 0));
+            if (over) atomicAdd(overflow, 1);
+            if (stats) {
+                atomicAdd(&stats[0], n_ext);
+                atomicAdd(&stats[1], n_ctl);
+                atomicAdd(&stats[2], rolls);
+            }
+        }
+    }
+}
+
+extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
+                             const CrlkPlanParams *plan, const CrlkForestView *forest, const double *goals,
+                             const double *streams, int32_t S, int32_t Q, int32_t *iters, int32_t *cursor,
+                             uint8_t *reached, uint8_t *flags, int32_t *overflow, uint64_t *stats,
+                             void *stream)
+{
+    CRLK_REQUIRE(env != nullptr && plan != nullptr && forest != nullptr, "env/plan/forest is NULL");
+    DwaP d;
+    ExtP x;
+    int rc = crlk_make_dwa(env, dwa, &d);
+    if (rc) return rc;
+    rc = crlk_make_ext(env, ext, &x);
+    if (rc) return rc;
+    CRLK_REQUIRE(Q >= 0 && S >= 0 && plan->max_iter >= 0, "shape");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(goals && (S == 0 || streams) && iters && cursor && reached && overflow, "NULL array");
+    CRLK_REQUIRE(forest->x64 && forest->y64 && forest->states && forest->parent && forest->n_nodes &&
+                 forest->stride >= 1, "forest");
+    CRLK_REQUIRE(!forest->pool || (forest->seg_off && forest->seg_len && forest->seg_flag && forest->pool_used),
+                 "forest path pool");
+    CRLK_REQUIRE((forest->x32 == nullptr) == (forest->y32 == nullptr), "x32/y32 must both be given or both NULL");
+    PlanP pp;
+    pp.max_iter = plan->max_iter; pp.S = S;
+    pp.d_min = plan->d_min; pp.d_max = plan->d_max;
+    pp.goal_radius = plan->goal_radius; pp.retry_radius = plan->retry_radius;
+    size_t smem = crlk_dwa_smem_bytes(d);
+    rc = set_smem_attr((const void *)k_plan_dwa, smem);
+    if (rc) return rc;
+    int dev = env->device, sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan_dwa, DWA_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sms * per_sm;
+    if (grid > Q) grid = Q;
+    int *counter = nullptr;
+    rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
+    if (rc) return rc;
+    k_plan_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
+        env->p, d, x, env->os, *forest, pp, goals, streams, Q, iters, cursor, reached, flags, overflow,
+        counter, (unsigned long long *)stats);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

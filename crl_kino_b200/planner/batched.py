@@ -195,6 +195,18 @@ class BatchedRRT:
         self.noise = None             # float32 [Q, rows, 2] standard-normal stream per query (eps != 0)
         self.noise_cursor = torch.zeros(Q, dtype=torch.int32, device=d)
 
+    def reset(self):
+        """Back to the single-node trees (start states), all counters cleared."""
+        f = self.forest
+        f.fill(self.starts.reshape(self.Q, 1, 5))
+        f.parent.fill_(-1)
+        for t in (self.iters, self.done, self.reached, self.active, self.retry_active, self.overflow,
+                  self.cursor, self.stats, self.noise_cursor):
+            t.zero_()
+        if self.keep_paths:
+            self.pool_used.zero_()
+        self.rounds = 0
+
     # ---- one extension pass ------------------------------------------------
     def _extend(self, slot, from_states, targets, active):
         if self.policy is None:
@@ -282,3 +294,43 @@ class BatchedRRT:
             path = full[1:] + path
             node = parents[node]
         return [states[node]] + path
+
+
+class FusedRRT(BatchedRRT):
+    """Q independent RRT.planning() runs (rrt.py:51-89, DWA steering) in ONE kernel
+    launch (crlk_plan_dwa): a thread block owns a query from its first sample to
+    its last node, persistent blocks pull queries from a work counter, so no query
+    waits for another (BatchedRRT advances all queries in lock step, one sample
+    per round, with five launches per round).  Same forest, same pre-drawn sample
+    streams, same trees and paths as BatchedRRT / the sequential planner."""
+
+    def __init__(self, env, starts, goals, max_iter=500, dwa=None, keep_paths=True, node_capacity=None,
+                 with_f32=False):
+        super().__init__(env, starts, goals, max_iter=max_iter, dwa=dwa, policy=None, keep_paths=keep_paths,
+                         node_capacity=node_capacity, with_f32=with_f32)
+        d = self.starts.device
+        self.flags = torch.zeros(self.Q, dtype=torch.uint8, device=d)
+
+    def plan_async(self, streams):
+        """Launch the planning kernel on the current stream; streams: CUDA float64 [Q, S, 5]."""
+        from .._lib import PlanParams, check, lib
+        C = self._C
+        assert streams.is_cuda and streams.dtype == torch.float64 and streams.is_contiguous()
+        assert streams.shape[0] == self.Q and streams.shape[2] == 5
+        p = lambda t: C.c_void_p(t.data_ptr())
+        pp = PlanParams(self.max_iter, 1.0, 20.0, 1.0, 5.0)            # rrt.py:69, :75, :79
+        self._streams = streams
+        check(lib().crlk_plan_dwa(self.env.handle.h, C.byref(self.dwa.params()), C.byref(self.xp), C.byref(pp),
+                                  C.byref(self._fv), p(self.goals), p(streams), streams.shape[1], self.Q,
+                                  p(self.iters), p(self.cursor), p(self.reached), p(self.flags),
+                                  p(self.overflow), p(self.stats), ops._stream()))
+
+    def plan(self, streams, **_):
+        streams = ops.as_dev(streams).contiguous()
+        self.plan_async(streams)
+        torch.cuda.synchronize()
+        if int(self.overflow.item()):
+            raise RuntimeError(f"{int(self.overflow.item())} trees ran out of node/path capacity")
+        self.done = ((self.reached != 0) | (self.iters >= self.max_iter)).to(torch.uint8)
+        self.samples_used = int(self.cursor.max().item())
+        return self.reached.cpu().numpy().astype(bool)

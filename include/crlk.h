@@ -282,6 +282,39 @@ int crlk_rrt_append(const CrlkForestView *forest, const CrlkExtendView *ext, con
                     uint8_t *reached, uint8_t *retry_active, double *retry_from, int32_t *retry_parent,
                     int32_t *overflow, void *stream);
 
+/* ---- whole-query planning on the device: RRT.planning (planner/rrt.py:51-89), DWA steering ---- */
+
+typedef struct {
+    int32_t max_iter;            /* RRT(max_iter), rrt.py:36: accepted samples per query */
+    double d_min, d_max;         /* sample acceptance band 1.0 <= d < 20 (rrt.py:69) */
+    double goal_radius;          /* 1.0 (rrt.py:75, :81) */
+    double retry_radius;         /* 5.0 (rrt.py:79) */
+} CrlkPlanParams;
+
+/* Q complete RRT.planning runs in ONE launch, one thread block per query from its
+ * first sample to its last node: per consumed sample the validity check
+ * (rrt.py:66), nearest node (:68), acceptance (:69), the extension (:72,
+ * RRT.steer :99-135 with DWA.control as controller), node append with path
+ * segments, goal test (:75) and the steer-to-goal retry (:78-83).  Replaces the
+ * crlk_valid_state / crlk_nearest / crlk_rrt_select / crlk_extend_dwa /
+ * crlk_rrt_append rounds for DWA steering; results are identical.
+ *   forest   trees holding the start node (n_nodes[q] = 1) on entry, the final
+ *            trees on return; with a path pool, pool_cap >= 2 * max_iter * n_max_extend
+ *   goals    dev f64[Q x 5]
+ *   streams  dev f64[Q x S x 5] pre-drawn samples per query (RRT.sample, rrt.py:146-154,
+ *            draws from host RNG state; the stream is that sequence), consumed in order
+ *   iters    dev i32[Q] accepted samples (loop index of rrt.py:60 at exit)
+ *   cursor   dev i32[Q] samples consumed (== S with iters < max_iter: stream exhausted)
+ *   reached  dev u8[Q]  reach_exactly (rrt.py:76, :82)
+ *   flags    dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin
+ *            somewhere in the run, bit2 out of node / pool capacity
+ *   overflow dev i32[1] += number of queries that ran out of capacity
+ *   stats    dev u64[3] (nullable) += extensions, control steps, rollouts */
+int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
+                  const CrlkPlanParams *plan, const CrlkForestView *forest, const double *goals,
+                  const double *streams, int32_t S, int32_t Q, int32_t *iters, int32_t *cursor,
+                  uint8_t *reached, uint8_t *flags, int32_t *overflow, uint64_t *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,9 +10,15 @@ from oracle import oracle as orc
 pytestmark = pytest.mark.gpu
 
 
+def _planner_cls(kind):
+    from crl_kino_b200.planner import batched
+    return {"lockstep": batched.BatchedRRT, "fused": batched.FusedRRT}[kind]
+
+
+@pytest.mark.parametrize("kind", ("lockstep", "fused"))
 @pytest.mark.parametrize("runs", ((0, 1), (2,)))
-def test_batched_rrt_reproduces_reference_runs(runs):
-    from crl_kino_b200.planner.batched import BatchedRRT
+def test_batched_rrt_reproduces_reference_runs(runs, kind):
+    BatchedRRT = _planner_cls(kind)
     g = golden("plan_dwa")
     env, _ = make_envs(fixture_map(str(g[f"run{runs[0]}_map"])))
     starts = np.array([g[f"run{r}_start"] for r in runs])
@@ -34,8 +40,9 @@ def test_batched_rrt_reproduces_reference_runs(runs):
         np.testing.assert_allclose(path, g[f"run{r}_path"], rtol=1e-9, atol=1e-11)
 
 
-def test_batched_rrt_vs_oracle_dense_map():
-    from crl_kino_b200.planner.batched import BatchedRRT
+@pytest.mark.parametrize("kind", ("lockstep", "fused"))
+def test_batched_rrt_vs_oracle_dense_map(kind):
+    BatchedRRT = _planner_cls(kind)
     from crl_kino_b200.policy.dwa import DWA
     from crl_kino_b200.workloads import dense_map, query_pairs, sample_stream
     rects = dense_map(n_cells=3000, seed=2)
@@ -65,6 +72,42 @@ def test_batched_rrt_vs_oracle_dense_map():
         np.testing.assert_allclose(np.array(p.final_course(q)), np.array(port.path), rtol=1e-7, atol=1e-9)
         n_ok += 1
     assert n_ok >= Q - 1, f"only {n_ok}/{Q} queries identical to the planner port"
+
+
+def test_fused_rrt_equals_lockstep_cfg4_sizes():
+    """One-launch planner vs the lock-step planner on the cfg4 map (10,004 obstacles, 64 x 64 DWA
+    grid): identical trees, parents, path pools, iteration and sample counts for every query."""
+    from crl_kino_b200.planner.batched import BatchedRRT, FusedRRT
+    from crl_kino_b200.policy.dwa import DWA
+    from crl_kino_b200.workloads import DENSE_DWA, dense_map, query_pairs, sample_stream
+    rects = dense_map()
+    env, o = make_envs(rects)
+    Q, iters, S = 48, 8, 96
+    s, gl = query_pairs(lambda c: o.valid_state_batch(c)[1], Q, seed=11)
+    sb = env.get_bounds()["state_bounds"]
+    streams = np.stack([sample_stream(sb, gl[q], S, seed=700 + q) for q in range(Q)])
+    planners = []
+    for cls in (BatchedRRT, FusedRRT):
+        d = DWA(env)
+        d.set_dwa(**DENSE_DWA)
+        p = cls(env, s, gl, max_iter=iters, dwa=d)
+        reached = p.plan(streams, check_every=4)
+        planners.append((p, reached))
+    (a, ra), (b, rb) = planners
+    assert np.array_equal(ra, rb)
+    assert np.array_equal(np_(a.forest.n_nodes), np_(b.forest.n_nodes))
+    assert np.array_equal(np_(a.iters), np_(b.iters))
+    assert int(np_(b.forest.n_nodes).sum()) > 2 * Q          # the runs did grow trees
+    for q in range(Q):
+        sa, pa = a.tree(q)
+        sb_, pb = b.tree(q)
+        assert np.array_equal(pa, pb)
+        assert np.array_equal(sa, sb_)                       # same kernels, same operations: bit-identical
+        assert np.array_equal(np.array(a.final_course(q)), np.array(b.final_course(q)))
+    # a query that is not done when its stream ends reports cursor == S
+    cur, it = np_(b.cursor), np_(b.iters)
+    assert np.all((cur <= S) & (it <= iters))
+    assert np.all(rb | (it == iters) | (cur == S))
 
 
 def _policy(seed=0):
