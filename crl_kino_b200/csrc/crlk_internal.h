@@ -100,8 +100,22 @@ int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x);
     } while (0)
 
 int crlk_require_device(void);
-int crlk_local_obs_masked(const CrlkEnv *env, const double *states, const double *goals, int32_t goal_stride,
-                          int32_t B, float *obs32, int32_t ld32, const int *skip, void *stream);
+int crlk_local_obs_compact(const CrlkEnv *env, const double *states, const double *goals,
+                           int32_t goal_stride, int32_t Bmax, const int *list, const int *count,
+                           float *obs32, int32_t ld32, void *planes, int32_t Mpad, int32_t Kp, void *stream);
+
+#ifdef __CUDACC__
+#include <cuda_bf16.h>
+// x = a + b + c exactly (three bf16 planes cover the 24-bit float32 significand)
+__device__ __forceinline__ void crlk_split3(float x, __nv_bfloat16 &a, __nv_bfloat16 &b, __nv_bfloat16 &c)
+{
+    a = __float2bfloat16_rn(x);
+    float r1 = x - __bfloat162float(a);
+    b = __float2bfloat16_rn(r1);
+    float r2 = r1 - __bfloat162float(b);
+    c = __float2bfloat16_rn(r2);
+}
+#endif
 
 // tensor-core MLP (crlk_mlp_tc.cu)
 struct CrlkPolicyTc;
@@ -109,5 +123,8 @@ int crlk_tc_supported(const int *dims, int n_layers);
 int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_host, CrlkPolicyTc **out);
 void crlk_tc_destroy(CrlkPolicyTc *t);
 size_t crlk_tc_workspace_bytes(const CrlkPolicyTc *t, int B);
+void crlk_tc_input_planes(const CrlkPolicyTc *t, void *workspace, int B, void **planes, int *Mpad, int *Kp);
+int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const float *const *d_bias,
+                           const int *n_rows_dev, int a_lo_kb, const float **out, int *ld_out, cudaStream_t st);
 int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, int B, void *workspace,
                            const float *const *d_bias, const float **out, int *ld_out, cudaStream_t st);

@@ -404,22 +404,31 @@ extern "C" int crlk_dynamic_window(const CrlkEnv *env, const double *states, dou
 // the point are tested (closed intervals, rigid.py:158-166).  A point inside an
 // obstacle always falls in a cell of that obstacle's range because the cell
 // function is monotone, so the result equals the scan over all obstacles.
+// Outputs (each nullable): float64 rows (the reference dtype), zero-padded
+// float32 rows, and/or the three bf16 operand planes of the actor's first layer
+// ([3][Mpad][Kp]; the map entries are exactly 0/1 in bf16, so planes 2 and 3 are
+// non-zero only in the first four columns and only their first 64 are written).
+// With `list` the CTA index is a row of a compacted batch: row b reads state and
+// goal of query list[b] and writes output row b; rows >= *count do nothing.
 __global__ void __launch_bounds__(256)
 k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
             const double *__restrict__ goals, int goal_stride, int B, double *obs64, float *obs32,
-            int ld32, uint8_t *near_boundary, const int *__restrict__ skip)
+            int ld32, uint8_t *near_boundary, const int *__restrict__ list, const int *__restrict__ count,
+            __nv_bfloat16 *planes, int Mpad, int Kp)
 {
     __shared__ int s_near;
-    int b = blockIdx.x;
+    const int b = blockIdx.x;
     if (b >= B) return;
-    if (skip && skip[b]) return;
-    const double *st = states + 5 * (size_t)b;
+    if (count && b >= *count) return;
+    const int q = list ? list[b] : b;
+    const double *st = states + 5 * (size_t)q;
     double x = st[0], y = st[1], th = st[2];
     double sn, cs;
     sincos(th, &sn, &cs);
     if (threadIdx.x == 0) s_near = 0;
     __syncthreads();
     bool nearp = false;
+    __nv_bfloat16 *p0 = planes ? planes + (size_t)b * Kp : nullptr;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         int p = threadIdx.x + k * 256;
@@ -433,10 +442,19 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
         double v = occ ? 0.0 : 1.0;
         if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
         if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
+        if (p0) p0[4 + p] = __float2bfloat16_rn((float)v);
     }
     if (nearp) s_near = 1;
+    if (planes) {
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+        for (int c = 4 + OBS_NPTS + threadIdx.x; c < Kp; c += 256) p0[c] = z;
+        if (threadIdx.x >= 4 && threadIdx.x < 64) {
+            planes[((size_t)Mpad + b) * Kp + threadIdx.x] = z;
+            planes[((size_t)2 * Mpad + b) * Kp + threadIdx.x] = z;
+        }
+    }
     if (threadIdx.x == 0) {
-        const double *g = goals + (size_t)goal_stride * b;
+        const double *g = goals + (size_t)goal_stride * q;
         double qx = g[0] - x, qy = g[1] - y;     // differential_gym.py:186-187 as R^T (g - t)
         double gbx = cs * qx + sn * qy;
         double gby = (-sn) * qx + cs * qy;
@@ -448,6 +466,16 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
             float *o = obs32 + (size_t)b * ld32;
             o[0] = (float)gbx; o[1] = (float)gby; o[2] = (float)st[3]; o[3] = (float)st[4];
             for (int k = 4 + OBS_NPTS; k < ld32; k++) o[k] = 0.f;
+        }
+        if (planes) {
+            const float h[4] = {(float)gbx, (float)gby, (float)st[3], (float)st[4]};
+            for (int k = 0; k < 4; k++) {
+                __nv_bfloat16 a0, a1, a2;
+                crlk_split3(h[k], a0, a1, a2);
+                p0[k] = a0;
+                planes[((size_t)Mpad + b) * Kp + k] = a1;
+                planes[((size_t)2 * Mpad + b) * Kp + k] = a2;
+            }
         }
     }
     __syncthreads();
@@ -465,19 +493,21 @@ extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const do
     if (B == 0) return CRLK_OK;
     k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
                                                     goal_stride, B, obs64, obs32, ld32, near_boundary,
-                                                    nullptr);
+                                                    nullptr, nullptr, nullptr, 0, 0);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
 
-// Same, skipping rows whose skip[b] != 0 (finished extensions of the RL steer loop).
-int crlk_local_obs_masked(const CrlkEnv *env, const double *states, const double *goals,
-                          int32_t goal_stride, int32_t B, float *obs32, int32_t ld32, const int *skip,
-                          void *stream)
+// Compacted batch of the RL steer loop: row b < *count observes query list[b];
+// output as float32 rows and/or bf16 operand planes (see k_local_obs).
+int crlk_local_obs_compact(const CrlkEnv *env, const double *states, const double *goals,
+                           int32_t goal_stride, int32_t Bmax, const int *list, const int *count,
+                           float *obs32, int32_t ld32, void *planes, int32_t Mpad, int32_t Kp, void *stream)
 {
-    if (B == 0) return CRLK_OK;
-    k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
-                                                    goal_stride, B, nullptr, obs32, ld32, nullptr, skip);
+    if (Bmax == 0) return CRLK_OK;
+    k_local_obs<<<Bmax, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                       goal_stride, Bmax, nullptr, obs32, ld32, nullptr,
+                                                       list, count, (__nv_bfloat16 *)planes, Mpad, Kp);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

@@ -357,8 +357,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                       int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
-                      __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc)
+                      __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc,
+                      const int *__restrict__ n_rows_dev, int a_lo_kb)
 {
+    // n_rows_dev (nullable): the live row count is read on the device (compacted batches of the
+    // RL steer loop), row tiles past it are skipped.  a_lo_kb: A planes 2 and 3 are zero beyond
+    // the first a_lo_kb k blocks (the local map of the observation is exactly 0/1 in bf16), so
+    // those blocks load 4 tiles and issue the 3 products of A plane 1 only.
+    if (n_rows_dev) B = min(B, *n_rows_dev);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + TCF_STAGES * TCF_STAGE_BYTES;
@@ -369,7 +375,7 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + TCF_STAGES * TCF_STAGE_BYTES + 16 * TCF_STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_n = N / TC_BN, tiles = tiles_n * (Mpad / TC_BM);
+    const int tiles_n = N / TC_BN, tiles = tiles_n * ((B + TC_BM - 1) / TC_BM);     // Mpad is the plane pitch
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TCF_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -393,10 +399,12 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 int s = git % TCF_STAGES, ph = (git / TCF_STAGES) & 1;
                 uint32_t st = base + s * TCF_STAGE_BYTES;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
-                mbar_expect_tx(full0 + 8 * s, TCF_STAGE_BYTES);
+                const bool lo = kb < a_lo_kb;
+                mbar_expect_tx(full0 + 8 * s, lo ? TCF_STAGE_BYTES : 4 * TC_STAGE_BYTES);
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++) {
-                    tma_load_2d(st + pl * TC_STAGE_BYTES, &tmA, kb * TC_BK, pl * Mpad + m0, full0 + 8 * s);
+                    if (pl == 0 || lo)
+                        tma_load_2d(st + pl * TC_STAGE_BYTES, &tmA, kb * TC_BK, pl * Mpad + m0, full0 + 8 * s);
                     tma_load_2d(st + (3 + pl) * TC_STAGE_BYTES, &tmW, kb * TC_BK, pl * N + n0, full0 + 8 * s);
                 }
             }
@@ -414,8 +422,10 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 uint32_t st = base + s * TCF_STAGE_BYTES;
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool lo = kb < a_lo_kb;
 #pragma unroll
                 for (int pair = 0; pair < TC_NPAIR; pair++) {
+                    if (!lo && c_pair_a[pair] != 0) continue;
                     uint64_t da = umma_desc_sw128(st + c_pair_a[pair] * TC_STAGE_BYTES);
                     uint64_t db = umma_desc_sw128(st + (3 + c_pair_w[pair]) * TC_STAGE_BYTES);
 #pragma unroll
@@ -598,23 +608,31 @@ size_t crlk_tc_workspace_bytes(const CrlkPolicyTc *t, int B)
     return 2 * planes + last + 1024;
 }
 
-// Hidden layers: obs (float32) -> float32 activations of the last hidden layer.
-// Returns the pointer / leading dimension of that activation through out/ld_out.
-int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, int B, void *workspace,
-                           const float *const *d_bias, const float **out, int *ld_out, cudaStream_t st)
+// The layer-0 operand planes inside a workspace: [3][Mpad][Kp0] bf16.
+void crlk_tc_input_planes(const CrlkPolicyTc *t, void *workspace, int B, void **planes, int *Mpad, int *Kp)
+{
+    uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    *planes = ws;
+    *Mpad = rup(B, TC_BM);
+    *Kp = t->layer[0].Kp;
+}
+
+// Hidden layers over operand planes that are already in the workspace
+// (crlk_tc_input_planes).  n_rows_dev (nullable): live row count on the device.
+// a_lo_kb: leading k blocks of layer 0 whose A planes 2/3 are non-zero (<= 0: all).
+int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const float *const *d_bias,
+                           const int *n_rows_dev, int a_lo_kb, const float **out, int *ld_out, cudaStream_t st)
 {
     const int Mpad = rup(B, TC_BM);
     uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     size_t planes_bytes = 3 * (size_t)Mpad * t->max_width * sizeof(uint16_t);
     __nv_bfloat16 *pl[2] = {(__nv_bfloat16 *)ws, (__nv_bfloat16 *)(ws + planes_bytes)};
     float *last = (float *)(ws + 2 * planes_bytes);
-    // layer-0 operand planes from the float32 observation
-    {
-        const TcLayer &L = t->layer[0];
-        size_t total = (size_t)Mpad * L.Kp;
-        k_split_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, ld_obs, L.K, B, Mpad, pl[0], L.Kp);
-        CRLK_LAUNCH_CHECK();
-    }
+    static const bool unfused = getenv("CRLK_MLP_UNFUSED") != nullptr;    // A/B switches
+    static const bool persist = getenv("CRLK_MLP_NOPERSIST") == nullptr;
+    static int n_sms = 0;
+    if (!n_sms) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dv); }
+    const bool need_persist = n_rows_dev != nullptr || a_lo_kb > 0;
     for (int i = 0; i < t->n_hidden; i++) {
         const TcLayer &L = t->layer[i];
         CUtensorMap mapA;
@@ -622,27 +640,41 @@ int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, 
         if (rc) return rc;
         bool is_last = (i == t->n_hidden - 1);
         dim3 grid(L.N / TC_BN, Mpad / TC_BM);
-        static const bool unfused = getenv("CRLK_MLP_UNFUSED") != nullptr;    // A/B switches
-        static const bool persist = getenv("CRLK_MLP_NOPERSIST") == nullptr;
-        static int n_sms = 0;
-        if (!n_sms) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dv); }
-        if (unfused)
+        const int kblocks = L.Kp / TC_BK;
+        if (unfused && !need_persist)
             k_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
-                mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
+                mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
                 is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
-        else if (persist) {
+        else if (persist || need_persist) {
             int tiles = (L.N / TC_BN) * (Mpad / TC_BM);
             int ctas = tiles < n_sms ? tiles : n_sms;
             k_gemm_bf16x3_persist<<<ctas, TC_THREADS, TCF_SMEM_BYTES, st>>>(
-                mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
-                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
+                mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
+                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N, n_rows_dev,
+                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks);
         } else
             k_gemm_bf16x3_fused<<<grid, TC_THREADS, TCF_SMEM_BYTES, st>>>(
-                mapA, L.map_w, Mpad, L.N, L.Kp / TC_BK, d_bias[i], B,
+                mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
                 is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);
         CRLK_LAUNCH_CHECK();
     }
     *out = last;
     *ld_out = t->layer[t->n_hidden - 1].N;
     return CRLK_OK;
+}
+
+// Hidden layers: obs (float32) -> float32 activations of the last hidden layer.
+// Returns the pointer / leading dimension of that activation through out/ld_out.
+int crlk_tc_hidden_forward(const CrlkPolicyTc *t, const float *obs, int ld_obs, int B, void *workspace,
+                           const float *const *d_bias, const float **out, int *ld_out, cudaStream_t st)
+{
+    const int Mpad = rup(B, TC_BM);
+    uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    // layer-0 operand planes from the float32 observation
+    const TcLayer &L = t->layer[0];
+    size_t total = (size_t)Mpad * L.Kp;
+    k_split_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, ld_obs, L.K, B, Mpad, (__nv_bfloat16 *)ws,
+                                                                   L.Kp);
+    CRLK_LAUNCH_CHECK();
+    return crlk_tc_layers_forward(t, B, workspace, d_bias, nullptr, 0, out, ld_out, st);
 }

@@ -83,12 +83,14 @@ extern "C" int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B)
 __global__ void __launch_bounds__(256)
 k_linear_relu(const float *__restrict__ A, int lda, const float *__restrict__ W, int K,
               const float *__restrict__ bias, float *__restrict__ Cout, int ldc, int B, int N,
-              const int *__restrict__ row_active)
+              const int *__restrict__ n_rows_dev)
 {
     __shared__ float As[GM_BK][GM_BM + 4];
     __shared__ float Ws[GM_BK][GM_BN + 4];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    if (n_rows_dev) B = min(B, *n_rows_dev);       // compacted batch: live rows counted on the device
+    if (m0 >= B) return;
     const int tr = tid / 16, tc = tid % 16;        // 16 x 16 threads, each 4 x 4 outputs
     const int lr = tid / 4, lk = (tid % 4) * 4;    // loader: row lr, k offset lk
     float acc[4][4] = {};
@@ -125,16 +127,24 @@ k_linear_relu(const float *__restrict__ A, int lda, const float *__restrict__ W,
 
 struct HeadP { float low[2], high[2], scale[2], bias[2]; };
 
+static bool policy_uses_tc(const CrlkPolicy *p)
+{
+    static const bool force_simt = getenv("CRLK_MLP_SIMT") != nullptr;   // A/B switch for the tests
+    return p->tc && !force_simt;
+}
+
 // Last layer (K -> 2) + tanh + exploration noise + scale/bias + clamp
 // (net.py:145-153, ddpg.py:126-130).  One warp per row.
 __global__ void __launch_bounds__(256)
 k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W, int K,
               const float *__restrict__ bias, const float *__restrict__ noise, long long noise_stride,
               const int *__restrict__ noise_cursor, int noise_off, float eps, HeadP hp, int B,
-              float *__restrict__ act)
+              float *__restrict__ act, const int *__restrict__ n_rows_dev, const int *__restrict__ list)
 {
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= B) return;
+    if (n_rows_dev && row >= *n_rows_dev) return;
+    const int q = list ? list[row] : row;          // the query this (compacted) row belongs to
     const float *a = A + (size_t)row * lda;
     float s0 = 0.f, s1 = 0.f;
     for (int k = lane; k < K; k += 32) {
@@ -151,8 +161,8 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
         float z = (lane == 0 ? s0 : s1) + __ldg(&bias[lane]);
         z = tanhf(z);
         if (noise) {
-            long long off = (long long)noise_off + (noise_cursor ? noise_cursor[row] : 0);
-            z = z + noise[(size_t)row * noise_stride + off * 2 + lane] * eps;
+            long long off = (long long)noise_off + (noise_cursor ? noise_cursor[q] : 0);
+            z = z + noise[(size_t)q * noise_stride + off * 2 + lane] * eps;
         }
         z = z * hp.scale[lane] + hp.bias[lane];
         z = fminf(fmaxf(z, hp.low[lane]), hp.high[lane]);
@@ -160,19 +170,25 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
     }
 }
 
+// Hidden layers + head.  Operand source: float32 `obs` rows, or (obs == NULL) bf16
+// operand planes already placed in the workspace (crlk_tc_input_planes; a_lo_kb as
+// in crlk_tc_layers_forward).  n_rows_dev / list (nullable): compacted batch of the
+// RL steer loop -- live row count on the device and the query of each row.
 static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs, const float *noise,
                                long long noise_stride, const int *noise_cursor, int noise_off, float eps, int B,
-                               float *act, void *workspace, cudaStream_t st)
+                               float *act, void *workspace, cudaStream_t st, const int *n_rows_dev = nullptr,
+                               const int *list = nullptr, int a_lo_kb = 0)
 {
     const int L = p->n_layers;
     const float *in = obs;
     int ld_in = ld_obs;
-    static const bool force_simt = getenv("CRLK_MLP_SIMT") != nullptr;   // A/B switch for the tests
-    if (p->tc && !force_simt) {
+    if (policy_uses_tc(p)) {
         // hidden layers on the tensor cores (tcgen05, bf16 x 3 split, float32 accumulate)
-        int rc = crlk_tc_hidden_forward(p->tc, obs, ld_obs, B, workspace, p->d_b, &in, &ld_in, st);
+        int rc = obs ? crlk_tc_hidden_forward(p->tc, obs, ld_obs, B, workspace, p->d_b, &in, &ld_in, st)
+                     : crlk_tc_layers_forward(p->tc, B, workspace, p->d_b, n_rows_dev, a_lo_kb, &in, &ld_in, st);
         if (rc) return rc;
     } else {
+        CRLK_REQUIRE(obs != nullptr, "float32 observations required on the SIMT path");
         float *buf[2];
         size_t half = (size_t)round_up(B, 64) * p->max_dim;
         buf[0] = (float *)workspace;
@@ -183,7 +199,7 @@ static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs
             float *outb = buf[i & 1];
             dim3 grid((N + GM_BN - 1) / GM_BN, (B + GM_BM - 1) / GM_BM);
             k_linear_relu<<<grid, 256, 0, st>>>(in, ld_in, p->d_w[i], p->kpad[i], p->d_b[i], outb, ldc, B, N,
-                                               nullptr);
+                                               n_rows_dev);
             CRLK_LAUNCH_CHECK();
             in = outb;
             ld_in = ldc;
@@ -194,7 +210,8 @@ static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs
         hp.low[k] = p->low[k]; hp.high[k] = p->high[k]; hp.scale[k] = p->scale[k]; hp.bias[k] = p->bias[k];
     }
     k_policy_head<<<(B + 7) / 8, 256, 0, st>>>(in, ld_in, p->d_w[L - 1], p->kpad[L - 1], p->d_b[L - 1],
-                                              noise, noise_stride, noise_cursor, noise_off, eps, hp, B, act);
+                                              noise, noise_stride, noise_cursor, noise_off, eps, hp, B, act,
+                                              n_rows_dev, list);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -553,10 +570,11 @@ extern "C" int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstima
 
 struct RlWs {
     double *state;     // [Q][5]
-    int *done;         // [Q]
     int *nn;           // [Q]
-    float *obs;        // [Q][736]
-    float *act;        // [Q][2]
+    int *list[2];      // [Q] queries still extending (ping-pong between steps)
+    int *count;        // [n_max_extend + 2] live rows per step
+    float *obs;        // [Q][736] (SIMT path only)
+    float *act;        // [Q][2], compacted rows
     void *mlp;         // policy workspace
 };
 
@@ -565,14 +583,18 @@ static size_t rl_carve(const CrlkPolicy *p, int Q, unsigned char *base, RlWs *w)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_state = take(sizeof(double) * 5 * Q);
-    size_t o_done = take(sizeof(int) * Q);
     size_t o_nn = take(sizeof(int) * Q);
-    size_t o_obs = take(sizeof(float) * 736 * (size_t)Q);
+    size_t o_l0 = take(sizeof(int) * Q);
+    size_t o_l1 = take(sizeof(int) * Q);
+    size_t o_cnt = take(sizeof(int) * 4096);
+    size_t o_obs = take(policy_uses_tc(p) ? 0 : sizeof(float) * 736 * (size_t)Q);
     size_t o_act = take(sizeof(float) * 2 * Q);
     size_t o_mlp = take((size_t)crlk_policy_workspace_bytes(p, Q));
     if (w) {
-        w->state = (double *)(base + o_state); w->done = (int *)(base + o_done);
-        w->nn = (int *)(base + o_nn); w->obs = (float *)(base + o_obs);
+        w->state = (double *)(base + o_state); w->nn = (int *)(base + o_nn);
+        w->list[0] = (int *)(base + o_l0); w->list[1] = (int *)(base + o_l1);
+        w->count = (int *)(base + o_cnt);
+        w->obs = (float *)(base + o_obs);
         w->act = (float *)(base + o_act); w->mlp = base + o_mlp;
     }
     return off;
@@ -584,36 +606,53 @@ extern "C" int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q
     return (int64_t)rl_carve(p, Q, nullptr, nullptr);
 }
 
+// count[] is zeroed before this launch; the active queries become step 1's row list.
 __global__ void k_rl_init(const double *__restrict__ from_states, const uint8_t *__restrict__ active,
-                          int Q, double *state, int *done, int *nn, int *n_steps, int *status,
+                          int Q, double *state, int *nn, int *list0, int *count, int *n_steps, int *status,
                           int *n_nodes, uint8_t *flags)
 {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     for (int c = 0; c < 5; c++) state[5 * (size_t)q + c] = from_states[5 * (size_t)q + c];
-    done[q] = (active && !active[q]) ? 1 : 0;
     nn[q] = 0;
     n_steps[q] = 0; status[q] = CRLK_EXT_TIMEOUT; n_nodes[q] = 0;
     if (flags) flags[q] = 0;
+    if (!active) {
+        list0[q] = q;
+        if (q == 0) count[0] = Q;
+    } else {
+        // warp-aggregated append (order inside the list does not affect any result: rows are independent)
+        bool a = active[q] != 0;
+        unsigned m = __ballot_sync(__activemask(), a);
+        if (a) {
+            int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+            if (lane == leader) base = atomicAdd(&count[0], __popc(m));
+            base = __shfl_sync(m, base, leader);
+            list0[base + __popc(m & ((1u << lane) - 1u))] = q;
+        }
+    }
 }
 
-// One warp per query: apply the action (differential_gym.py:139), then the
-// planner's checks (rrt_rl.py:48-57).
+// One warp per live row: apply the action (differential_gym.py:139), then the
+// planner's checks (rrt_rl.py:48-57); queries that keep extending are appended
+// to the next step's row list.
 __global__ void __launch_bounds__(256)
 k_rl_step(EnvP e, ExtP x, ObsSet os, const double *__restrict__ targets,
-          const float *__restrict__ act, int k, int Q, double *state, int *done, int *nn, double *path,
-          int *n_steps, int *status, int *node_step, int *n_nodes, float *actions, uint8_t *flags)
+          const float *__restrict__ act, int k, int Q, const int *__restrict__ list_in,
+          const int *__restrict__ count_in, int *list_out, int *count_out, double *state, int *nn,
+          double *path, int *n_steps, int *status, int *node_step, int *n_nodes, float *actions,
+          uint8_t *flags)
 {
     __shared__ int s_queue[8][WQ_CAP_RL];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int q = blockIdx.x * 8 + warp;
-    if (q >= Q) return;
-    if (done[q]) return;
+    int row = blockIdx.x * 8 + warp;
+    if (row >= Q || row >= *count_in) return;
+    const int q = list_in[row];
     const int per = x.n_max_extend / x.n_tree + 1;
     double s[5];
     for (int c = 0; c < 5; c++) s[c] = state[5 * (size_t)q + c];
     // the float32 action promoted to float64 (differential_env.py:67-70)
-    double cv = (double)act[2 * (size_t)q], cw = (double)act[2 * (size_t)q + 1];
+    double cv = (double)act[2 * (size_t)row], cw = (double)act[2 * (size_t)row + 1];
     motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
     // collision test (flag only)
     RobotPose g;
@@ -661,24 +700,26 @@ k_rl_step(EnvP e, ExtP x, ObsSet os, const double *__restrict__ targets,
         path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
     }
     if (actions) {
-        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2] = act[2 * (size_t)q];
-        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2 + 1] = act[2 * (size_t)q + 1];
+        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2] = act[2 * (size_t)row];
+        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2 + 1] = act[2 * (size_t)row + 1];
     }
     n_steps[q] = k;
     if (flags && marginal && !definite) flags[q] |= 1;
     const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
     double ddx = s[0] - gx, ddy = s[1] - gy;
     double dist = sqrt(fma(ddy, ddy, ddx * ddx));
+    bool go_on = true;
     if (coll) {
-        status[q] = CRLK_EXT_COLLISION; done[q] = 1;
+        status[q] = CRLK_EXT_COLLISION; go_on = false;
     } else if (dist <= x.reach_radius) {
         node_step[(size_t)q * per + nn[q]] = k;
         nn[q] += 1; n_nodes[q] = nn[q];
-        status[q] = CRLK_EXT_REACHED; done[q] = 1;
+        status[q] = CRLK_EXT_REACHED; go_on = false;
     } else if (k % x.n_tree == 0) {
         node_step[(size_t)q * per + nn[q]] = k;
         nn[q] += 1; n_nodes[q] = nn[q];
     }
+    if (go_on && k < x.n_max_extend) list_out[atomicAdd(count_out, 1)] = q;
 }
 
 // every executed step consumed one noise draw (net.py:147-150)
@@ -707,23 +748,36 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
                  "NULL array");
     CRLK_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     CRLK_REQUIRE(!noise || noise_rows >= (noise_cursor ? 1 : x.n_max_extend), "noise_rows too small");
+    CRLK_REQUIRE(x.n_max_extend + 2 <= 4096, "n_max_extend too large");
     cudaStream_t st = (cudaStream_t)stream;
     RlWs w;
     rl_carve(p, Q, (unsigned char *)workspace, &w);
-    k_rl_init<<<(Q + 127) / 128, 128, 0, st>>>(from_states, active, Q, w.state, w.done, w.nn, n_steps,
-                                              status, n_nodes, flags);
+    // Every step runs on the COMPACTED batch of queries that are still extending:
+    // k_rl_step appends the survivors to the next step's row list and counts them on the
+    // device; the observation, GEMM and head kernels read that count (no host sync) and
+    // skip the rows / row tiles past it.
+    CRLK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * (x.n_max_extend + 2), st));
+    k_rl_init<<<(Q + 127) / 128, 128, 0, st>>>(from_states, active, Q, w.state, w.nn, w.list[0], w.count,
+                                              n_steps, status, n_nodes, flags);
     CRLK_LAUNCH_CHECK();
+    const bool tc = policy_uses_tc(p);
+    void *planes = nullptr;
+    int Mpad = 0, Kp = 0;
+    if (tc) crlk_tc_input_planes(p->tc, w.mlp, Q, &planes, &Mpad, &Kp);
     for (int k = 1; k <= x.n_max_extend; k++) {
-        // observation of the current state (rrt_rl.py:34 / differential_gym.py:141)
-        rc = crlk_local_obs_masked(env, w.state, targets, 5, Q, w.obs, 736, w.done, stream);
+        const int *list = w.list[(k - 1) & 1], *cnt = w.count + (k - 1);
+        // observation of the current state (rrt_rl.py:34 / differential_gym.py:141): straight
+        // into the bf16 operand planes of the first layer on the tensor-core path
+        rc = crlk_local_obs_compact(env, w.state, targets, 5, Q, list, cnt, tc ? nullptr : w.obs, 736,
+                                    planes, Mpad, Kp, stream);
         if (rc) return rc;
-        // action = policy(obs) (rrt_rl.py:41)
-        rc = policy_forward_impl(p, w.obs, 736, noise, (long long)noise_rows * 2, noise_cursor, k - 1, eps, Q,
-                                 w.act, w.mlp, st);
+        // action = policy(obs) (rrt_rl.py:41); only the four goal / velocity inputs have low planes
+        rc = policy_forward_impl(p, tc ? nullptr : w.obs, 736, noise, (long long)noise_rows * 2, noise_cursor,
+                                 k - 1, eps, Q, w.act, w.mlp, st, cnt, list, 1);
         if (rc) return rc;
-        k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->os, targets, w.act, k, Q,
-                                              w.state, w.done, w.nn, path, n_steps, status, node_step,
-                                              n_nodes, actions, flags);
+        k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->os, targets, w.act, k, Q, list, cnt,
+                                              w.list[k & 1], w.count + k, w.state, w.nn, path, n_steps,
+                                              status, node_step, n_nodes, actions, flags);
         CRLK_LAUNCH_CHECK();
     }
     if (noise && noise_cursor) {

@@ -74,6 +74,47 @@ def test_batched_rrt_vs_oracle_dense_map(kind):
     assert n_ok >= Q - 1, f"only {n_ok}/{Q} queries identical to the planner port"
 
 
+@pytest.mark.parametrize("mname", ("env1", "env2"))
+def test_fused_rrt_benchmark_positions_vs_oracle(mname):
+    """BASELINE config 3 (examples/benchmark.py:48-75): all 12 ordered (start, goal) pairs of the
+    reference's benchmark_position_test_env{1,2}.pkl on test_env{1,2}.pkl, DWA steering with the
+    RRT defaults, planned together in one launch; trees, parents, reach flags and final paths
+    against the planner port (itself pinned to three full runs of the unmodified reference)."""
+    from crl_kino_b200.planner.batched import FusedRRT
+    from crl_kino_b200.workloads import sample_stream
+    fx = golden("fixtures")
+    env, o = make_envs(fx["map_test_" + mname])
+    pos = fx["positions_" + mname]
+    pairs = [(i, j) for i in range(4) for j in range(4) if i != j]       # benchmark.py:56-59
+    starts = np.array([pos[i] for i, _ in pairs])
+    goals = np.array([pos[j] for _, j in pairs])
+    iters, S = 30, 400
+    sb = env.get_bounds()["state_bounds"]
+    streams = np.stack([sample_stream(sb, goals[q], S, seed=900 + q) for q in range(len(pairs))])
+    p = FusedRRT(env, starts, goals, max_iter=iters)
+    reached = p.plan(streams)
+    flags = np_(p.flags)
+    n_same = 0
+    for q in range(len(pairs)):
+        port = orc.PlannerPort(o, max_iter=iters)
+        port.set_start_and_goal(starts[q], goals[q])
+        port.planning(iter(streams[q]))
+        ref_states = np.array([n.state for n in port.node_list])
+        states, parents = p.tree(q)
+        same = len(states) == len(ref_states) and np.allclose(states, ref_states, rtol=1e-7, atol=1e-9)
+        if not same:
+            assert flags[q] & 3, f"query {q} differs from the planner port without a near-tie/near-boundary report"
+            continue
+        index = {id(n): i for i, n in enumerate(port.node_list)}
+        ref_par = np.array([-1 if n.parent is None else index[id(n.parent)] for n in port.node_list])
+        assert np.array_equal(parents, ref_par)
+        assert reached[q] == port.reach_exactly
+        assert int(np_(p.cursor)[q]) == port.n_samples            # same number of draws consumed
+        np.testing.assert_allclose(np.array(p.final_course(q)), np.array(port.path), rtol=1e-7, atol=1e-9)
+        n_same += 1
+    assert n_same >= len(pairs) - 1, f"only {n_same}/{len(pairs)} queries identical to the planner port"
+
+
 def test_fused_rrt_equals_lockstep_cfg4_sizes():
     """One-launch planner vs the lock-step planner on the cfg4 map (10,004 obstacles, 64 x 64 DWA
     grid): identical trees, parents, path pools, iteration and sample counts for every query."""
