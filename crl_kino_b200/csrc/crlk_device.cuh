@@ -286,6 +286,7 @@ __device__ __forceinline__ void body_to_world(double cs, double sn, double x, do
 // intervals, rigid.py:158-166).  A point inside an obstacle always falls in a
 // cell of that obstacle's range (the cell function is monotone), so this equals
 // the scan over all obstacles.  `near` is OR-ed with "within 1e-9 of a face".
+template <bool WANT_NEAR = true>
 __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, double py, bool &near)
 {
     const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
@@ -302,6 +303,7 @@ __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, 
                 float4 r = __ldg(&os.rects[__ldg(&os.cell_items[i])]);
                 double l = r.x, bo = r.y, rr = r.z, t = r.w;
                 occ |= (px >= l && px <= rr && py >= bo && py <= t);
+                if (!WANT_NEAR) continue;
                 bool in_big = (px >= l - OBS_NEAR_EPS && px <= rr + OBS_NEAR_EPS &&
                                py >= bo - OBS_NEAR_EPS && py <= t + OBS_NEAR_EPS);
                 bool in_small = (px >= l + OBS_NEAR_EPS && px <= rr - OBS_NEAR_EPS &&

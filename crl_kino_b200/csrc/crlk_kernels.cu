@@ -410,6 +410,7 @@ extern "C" int crlk_dynamic_window(const CrlkEnv *env, const double *states, dou
 // non-zero only in the first four columns and only their first 64 are written).
 // With `list` the CTA index is a row of a compacted batch: row b reads state and
 // goal of query list[b] and writes output row b; rows >= *count do nothing.
+template <bool WANT_NEAR>
 __global__ void __launch_bounds__(256)
 k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
             const double *__restrict__ goals, int goal_stride, int B, double *obs64, float *obs32,
@@ -417,16 +418,21 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
             __nv_bfloat16 *planes, int Mpad, int Kp)
 {
     __shared__ int s_near;
+    __shared__ double s_cs[2];
     const int b = blockIdx.x;
     if (b >= B) return;
     if (count && b >= *count) return;
     const int q = list ? list[b] : b;
     const double *st = states + 5 * (size_t)q;
     double x = st[0], y = st[1], th = st[2];
-    double sn, cs;
-    sincos(th, &sn, &cs);
-    if (threadIdx.x == 0) s_near = 0;
+    if (threadIdx.x == 0) {           // one float64 sincos per observation, not per thread
+        double sn0, cs0;
+        sincos(th, &sn0, &cs0);
+        s_cs[0] = cs0; s_cs[1] = sn0;
+        s_near = 0;
+    }
     __syncthreads();
+    const double cs = s_cs[0], sn = s_cs[1];
     bool nearp = false;
     __nv_bfloat16 *p0 = planes ? planes + (size_t)b * Kp : nullptr;
 #pragma unroll
@@ -438,13 +444,13 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
         double by = arange_at(og.lr0, og.lr1, og.lrd, il);
         double px, py;
         body_to_world(cs, sn, x, y, bx, by, px, py);     // differential_gym.py:83 (wTb @ [bx, by, 1])
-        bool occ = local_map_occupied(os, px, py, nearp);
+        bool occ = local_map_occupied<WANT_NEAR>(os, px, py, nearp);
         double v = occ ? 0.0 : 1.0;
         if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
         if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
         if (p0) p0[4 + p] = __float2bfloat16_rn((float)v);
     }
-    if (nearp) s_near = 1;
+    if (WANT_NEAR && nearp) s_near = 1;
     if (planes) {
         const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
         for (int c = 4 + OBS_NPTS + threadIdx.x; c < Kp; c += 256) p0[c] = z;
@@ -491,9 +497,14 @@ extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const do
     CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
     CRLK_REQUIRE(obs32 == nullptr || ld32 >= 4 + OBS_NPTS, "ld32 < 733");
     if (B == 0) return CRLK_OK;
-    k_local_obs<<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
-                                                    goal_stride, B, obs64, obs32, ld32, near_boundary,
-                                                    nullptr, nullptr, nullptr, 0, 0);
+    if (near_boundary)
+        k_local_obs<true><<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                              goal_stride, B, obs64, obs32, ld32,
+                                                              near_boundary, nullptr, nullptr, nullptr, 0, 0);
+    else
+        k_local_obs<false><<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                               goal_stride, B, obs64, obs32, ld32, nullptr,
+                                                               nullptr, nullptr, nullptr, 0, 0);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -505,10 +516,85 @@ int crlk_local_obs_compact(const CrlkEnv *env, const double *states, const doubl
                            float *obs32, int32_t ld32, void *planes, int32_t Mpad, int32_t Kp, void *stream)
 {
     if (Bmax == 0) return CRLK_OK;
-    k_local_obs<<<Bmax, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
-                                                       goal_stride, Bmax, nullptr, obs32, ld32, nullptr,
-                                                       list, count, (__nv_bfloat16 *)planes, Mpad, Kp);
+    k_local_obs<false><<<Bmax, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                              goal_stride, Bmax, nullptr, obs32, ld32, nullptr,
+                                                              list, count, (__nv_bfloat16 *)planes, Mpad, Kp);
     CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+// ------------------------------------------ gym step (differential_gym.py:136-178)
+
+struct GymP { double rp[8]; double goal_radius, clearance_cap; };
+
+// DifferentialDriveGym.step for one environment per thread: the state update
+// (:139), _info (:147-166) and _reward = info_arr @ reward_param (:177-178).
+// info columns follow the dict order of :148-157: goal, goal_dis, heading,
+// collision, clearance, v, |w|, step.
+__global__ void __launch_bounds__(128)
+k_gym_step(EnvP e, ObsSet os, GymP gp, double *states, const double *__restrict__ goals, int goal_stride,
+           const double *__restrict__ actions, int n_sub, int B, double *info, double *reward,
+           uint8_t *near_boundary)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double s[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) s[k] = states[5 * (size_t)i + k];
+    if (actions) motion_velocity_dev(e, s, actions[2 * (size_t)i], actions[2 * (size_t)i + 1], n_sub);
+    const double gx = goals[(size_t)goal_stride * i], gy = goals[(size_t)goal_stride * i + 1];
+    double dx = s[0] - gx, dy = s[1] - gy;
+    double gd = sqrt(fma(dy, dy, dx * dx));                                   // np.linalg.norm (:158)
+    double head = fabs(normalize_angle(atan2(gy - s[1], gx - s[0]) - s[2]));    // :161-162
+    bool d, m;
+    double clr = clearance_grid_thread(e, os, s[0], s[1], s[2], &d, &m);        // get_clearance: -1 on collision
+    double v[8];
+    v[0] = (gd <= gp.goal_radius) ? 1.0 : 0.0;
+    v[1] = gd;
+    v[2] = head;
+    v[3] = (clr < 0.0) ? 1.0 : 0.0;                                             // not valid_state_check (:164)
+    v[4] = pymin(clr, gp.clearance_cap);                                        // min(get_clearance, 1.0) (:163)
+    v[5] = s[3];
+    v[6] = fabs(s[4]);
+    v[7] = 1.0;
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (info) info[8 * (size_t)i + k] = v[k];
+        r += v[k] * gp.rp[k];
+    }
+    if (reward) reward[i] = r;
+    if (near_boundary) near_boundary[i] = (m && !d) ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) states[5 * (size_t)i + k] = s[k];
+}
+
+extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *goals, int32_t goal_stride,
+                             const double *actions, double step_dt, const double *reward_param_host,
+                             int32_t B, double *info, double *reward, double *obs64, float *obs32,
+                             int32_t ld32, uint8_t *near_boundary, void *stream)
+{
+    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_REQUIRE(B >= 0 && (B == 0 || (states && goals)), "NULL array");
+    CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
+    CRLK_REQUIRE(!reward || reward_param_host, "reward_param required with reward");
+    CRLK_REQUIRE(obs32 == nullptr || ld32 >= 4 + OBS_NPTS, "ld32 < 733");
+    CRLK_REQUIRE(!actions || step_dt > 0, "step_dt must be positive");
+    if (B == 0) return CRLK_OK;
+    GymP gp;
+    for (int k = 0; k < 8; k++) gp.rp[k] = reward_param_host ? reward_param_host[k] : 0.0;
+    gp.goal_radius = 1.0;        // differential_gym.py:159
+    gp.clearance_cap = 1.0;      // :163
+    int n_sub = actions ? crlk_count_loop_lt(step_dt, env->p.base_dt) : 0;
+    k_gym_step<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, env->os, gp, states, goals, goal_stride,
+                                                                 actions, n_sub, B, info, reward, near_boundary);
+    CRLK_LAUNCH_CHECK();
+    if (obs64 || obs32) {
+        k_local_obs<false><<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals, goal_stride,
+                                                               B, obs64, obs32, ld32, nullptr, nullptr, nullptr,
+                                                               nullptr, 0, 0);
+        CRLK_LAUNCH_CHECK();
+    }
     return CRLK_OK;
 }
 

@@ -455,7 +455,7 @@ k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const
         double px, py;
         body_to_world(cs, sn, x, y, arange_at(og.ba0, og.ba1, og.bad, ib), arange_at(og.lr0, og.lr1, og.lrd, il),
                       px, py);
-        s_in[p] = local_map_occupied(os, px, py, nearp) ? 0.f : 1.f;
+        s_in[p] = local_map_occupied<false>(os, px, py, nearp) ? 0.f : 1.f;
     }
     if (threadIdx.x == 0) {
         double qx = __dadd_rn(targets[5 * (size_t)q], -x), qy = __dadd_rn(targets[5 * (size_t)q + 1], -y);

@@ -121,6 +121,28 @@ def local_obs(env, states, goals, want64=True, want32=False, want_near=False, ld
     return o64, o32, near
 
 
+def gym_step(env, states, goals, actions, reward_param, step_dt=0.2, want64=True, want32=False,
+             want_near=False, ld32=OBS_LD):
+    """DifferentialDriveGym.step for B environments (differential_gym.py:136-178).  `states`
+    (float64 CUDA [B, 5]) is advanced IN PLACE; actions None = info / reward / obs of the current
+    states.  Returns (info [B, 8], reward [B], obs64, obs32, near)."""
+    assert states.is_cuda and states.dtype == torch.float64 and states.is_contiguous()
+    B = states.shape[0]
+    goals = as_dev(goals).reshape(B, -1)
+    actions = None if actions is None else as_dev(actions).reshape(B, 2)
+    d = states.device
+    info = torch.empty(B, 8, dtype=torch.float64, device=d)
+    reward = torch.empty(B, dtype=torch.float64, device=d)
+    o64 = torch.empty(B, OBS_DIM, dtype=torch.float64, device=d) if want64 else None
+    o32 = torch.empty(B, ld32, dtype=torch.float32, device=d) if want32 else None
+    near = torch.empty(B, dtype=torch.uint8, device=d) if want_near else None
+    rp = (C.c_double * 8)(*[float(x) for x in np.asarray(reward_param, dtype=np.float64).reshape(8)])
+    check(lib().crlk_gym_step(env.h, _ptr(states), _ptr(goals), goals.shape[1], _ptr(actions), float(step_dt),
+                              rp, B, _ptr(info), _ptr(reward), _ptr(o64), _ptr(o32), ld32, _ptr(near),
+                              _stream()))
+    return info, reward, o64, o32, near
+
+
 def dwa_traj_rows(env, dp):
     r = lib().crlk_dwa_traj_rows(env.h, C.byref(dp))
     if r < 0:

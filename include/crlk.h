@@ -282,6 +282,21 @@ int crlk_rrt_append(const CrlkForestView *forest, const CrlkExtendView *ext, con
                     uint8_t *reached, uint8_t *retry_active, double *retry_from, int32_t *retry_parent,
                     int32_t *overflow, void *stream);
 
+/* ---- gym side of the env: DifferentialDriveGym.step (env/differential_gym.py:136-178) ---- */
+
+/* B environments over one obstacle set, one call per step:
+ *   state <- motion_velocity(state, action, step_dt)   (:139; actions NULL: no motion, info/obs only)
+ *   info  = _info()  (:147-166), columns in the dict order goal, goal_dis, heading, collision,
+ *           clearance (= min(get_clearance, 1.0), -1 when colliding), v, |w|, step (= 1.0)
+ *   reward = info @ reward_param  (:177-178; reward_param_host: 8 doubles, host memory)
+ *   obs    = _obs()  (:180-190), float64 [B x 733] and/or float32 [B x ld32] as crlk_local_obs
+ *   states dev f64[B x 5] IN/OUT; goals dev f64[B x goal_stride]; actions dev f64[B x 2] (v, w)
+ *   info dev f64[B x 8], reward dev f64[B], near_boundary dev u8[B] (all nullable). */
+int crlk_gym_step(const CrlkEnv *env, double *states, const double *goals, int32_t goal_stride,
+                  const double *actions, double step_dt, const double *reward_param_host, int32_t B,
+                  double *info, double *reward, double *obs64, float *obs32, int32_t ld32,
+                  uint8_t *near_boundary, void *stream);
+
 /* ---- whole-query planning on the device: RRT.planning (planner/rrt.py:51-89), DWA steering ---- */
 
 typedef struct {

@@ -495,3 +495,36 @@ class PlannerPort:
             path = node.path[1:] + path
             node = node.parent
         return [node.state] + path
+
+
+# ------------------------------------------------------------------ gym side
+# DifferentialDriveGym.step / _info / _reward (env/differential_gym.py:136-178)
+
+GYM_INFO_KEYS = ("goal", "goal_dis", "heading", "collision", "clearance", "v", "w", "step")
+GYM_REWARD_PARAM = np.array([50.0, -1.5, -0.5, -300.0, 1.0, 1.0, -.5, -2.5])   # differential_gym.py:28-29
+
+
+def _normalize_angle(a):
+    """differential_env.py:20-24."""
+    m = a % (2 * math.pi)
+    if m > math.pi:
+        m -= 2 * math.pi
+    return m
+
+
+def gym_info(env, state, goal):
+    """differential_gym.py:147-166 as the 8-vector in dict order."""
+    state = np.asarray(state, dtype=np.float64)
+    goal = np.asarray(goal, dtype=np.float64)
+    gd = float(np.linalg.norm(state[:2] - goal[:2]))
+    head = abs(_normalize_angle(np.arctan2(goal[1] - state[1], goal[0] - state[0]) - state[2]))
+    clr = min(env.get_clearance(state), 1.0)
+    col = not env.valid_state_check(state)
+    return np.array([float(gd <= 1.0), gd, head, float(col), clr, state[3], abs(state[4]), 1.0])
+
+
+def gym_step(env, state, goal, action, reward_param=GYM_REWARD_PARAM, dt=1.0 / 5.0):
+    """differential_gym.py:136-145 -> (state', obs, reward, info vector)."""
+    s = env.motion_velocity(state, action, dt)
+    info = gym_info(env, s, goal)
+    return s, env.local_obs(s, goal), float(info @ np.asarray(reward_param, dtype=np.float64)), info

@@ -696,10 +696,62 @@ def g_plan_rl():
     save("plan_rl", seed=np.array(0), **out)
 
 
+def g_gym():
+    """DifferentialDriveGym.reset / step / _info / _reward (env/differential_gym.py:136-253):
+    seeded episodes of the unmodified reference with recorded velocity commands."""
+    maps = load_maps()
+    names = [f"obs_list_{i}" for i in range(8)]
+    sets = [maps[n] for n in names]
+    out = {}
+    for ep, (seed, ori) in enumerate(((0, False), (1, False), (2, True), (3, False), (4, False))):
+        np.random.seed(seed)
+        gym_env = DifferentialDriveGym(make_env(sets[0]), obs_list_list=sets)
+        gym_env.set_curriculum(ori=ori)
+        obs0 = gym_env.reset()
+        picked = [i for i, m in enumerate(sets) if gym_env.robot_env.obs_list is m or gym_env.robot_env.obs_list == m][0]
+        rng = np.random.default_rng(100 + seed)
+        T = 30 if ep < 4 else 120
+        # head toward the goal most of the time so that episodes see goal / collision / free steps
+        acts, states, obss, rews, dones, infos = [], [], [], [], [], []
+        for t in range(T):
+            s, g = gym_env.state, gym_env.goal
+            ang = np.arctan2(g[1] - s[1], g[0] - s[0]) - s[2]
+            ang = (ang + np.pi) % (2 * np.pi) - np.pi
+            a = np.array([rng.uniform(0.3, 1.0), np.clip(2.0 * ang, -np.pi, np.pi) + rng.normal(0, 0.3)])
+            if ep == 3:
+                a = rng.uniform(gym_env.action_space.low, gym_env.action_space.high)      # random walk
+            if ep == 4:
+                a = np.array([1.0, 0.0])                                                  # straight into a wall
+            obs, rew, done, info = gym_env.step(a)
+            acts.append(a); states.append(gym_env.state.copy()); obss.append(obs)
+            rews.append(rew); dones.append(done)
+            infos.append([float(info[k]) for k in info])
+            if done:
+                break
+        out.update({f"ep{ep}_seed": seed, f"ep{ep}_ori": ori, f"ep{ep}_map": names[picked],
+                    f"ep{ep}_start": states[0] * 0 + 0, f"ep{ep}_goal": gym_env.goal.copy(),
+                    f"ep{ep}_obs0": obs0, f"ep{ep}_actions": np.array(acts), f"ep{ep}_states": np.array(states),
+                    f"ep{ep}_obs": np.array(obss), f"ep{ep}_reward": np.array(rews),
+                    f"ep{ep}_done": np.array(dones), f"ep{ep}_info": np.array(infos)})
+        # the start state is the state before the first step: recover it by replaying reset
+        np.random.seed(seed)
+        g2 = DifferentialDriveGym(make_env(sets[0]), obs_list_list=sets)
+        g2.set_curriculum(ori=ori)
+        g2.reset()
+        out[f"ep{ep}_start"] = g2.state.copy()
+        assert np.array_equal(g2.goal, gym_env.goal)
+        # a2v / v2a round trip values
+        out[f"ep{ep}_a2v"] = g2.a2v(np.array(acts[0]))
+        out[f"ep{ep}_v2a"] = g2.v2a(np.array(acts[0]))
+    out["n_episodes"] = 5
+    out["map_names"] = np.array(names)
+    save("gym", **out)
+
+
 ALL = dict(fixtures=g_fixtures, numerics=g_numerics, motion=g_motion, dwa=g_dwa,
            dwa_clearance=g_dwa_clearance, geometry=g_geometry, obs=g_obs, nearest=g_nearest,
            steer_dwa=g_steer_dwa, plan_dwa=g_plan_dwa, policy=g_policy, estimator=g_estimator,
-           steer_rl=g_steer_rl, plan_rl=g_plan_rl)
+           steer_rl=g_steer_rl, plan_rl=g_plan_rl, gym=g_gym)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
