@@ -14,7 +14,7 @@ class CrlkError(RuntimeError):
 class EnvParams(C.Structure):
     _fields_ = [("max_v", C.c_double), ("min_v", C.c_double), ("max_w", C.c_double),
                 ("max_acc_v", C.c_double), ("max_acc_w", C.c_double), ("base_dt", C.c_double),
-                ("env_bounds", C.c_double * 4), ("robot_rect", C.c_float * 4)]
+                ("env_bounds", C.c_double * 4), ("robot_rect", C.c_float * 4), ("robot_radius", C.c_double)]
 
 
 class DwaParams(C.Structure):

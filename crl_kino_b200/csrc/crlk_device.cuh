@@ -141,6 +141,15 @@ __device__ __forceinline__ double dis2obs_exact(const EnvP &e, const RobotPose &
                                                 bool &definite, bool &marginal)
 {
     double l = o.x, b = o.y, r = o.z, t = o.w;
+    if (e.radius > 0.0) {
+        // CircleRobot.dis2obs (rigid.py:336-347): centre inside the closed rectangle collides,
+        // else boundary distance minus the radius against the same 0.05 threshold
+        if (g.x >= l && g.x <= r && g.y >= b && g.y <= t) { definite = true; marginal = false; return -1.0; }
+        double dc = sqrt(point_rect_boundary_d2(g.x, g.y, l, b, r, t)) - e.radius;
+        marginal = fabs(dc - CRLK_COLLISION_DIS) < CRLK_NEAR_EPS;
+        definite = dc <= CRLK_COLLISION_DIS - CRLK_NEAR_EPS;
+        return (dc > CRLK_COLLISION_DIS) ? dc : -1.0;
+    }
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {

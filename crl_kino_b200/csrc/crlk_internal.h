@@ -11,7 +11,8 @@
 struct EnvP {
     double max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt;
     float rl, rb, rr, rt;   // robot rectangle (float32 values)
-    float rc;               // circumradius of the robot rectangle about the body origin
+    float rc;               // circumradius of the footprint about the body origin
+    double radius;          // > 0: circular footprint (CircleRobot, rigid.py:331-347)
 };
 
 // Obstacle set on the device: rectangles plus a uniform grid of index lists

@@ -72,6 +72,8 @@ static void fill_envp(const CrlkEnvParams *in, EnvP *p)
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 2; j++) m = fmaxf(m, sqrtf(xs[i] * xs[i] + ys[j] * ys[j]));
     p->rc = m * 1.0001f;
+    p->radius = in->robot_radius > 0 ? in->robot_radius : 0.0;
+    if (p->radius > 0) p->rc = (float)p->radius * 1.0001f;
 }
 
 // Uniform grid over the obstacles' bounding box: cell (cx, cy) lists every

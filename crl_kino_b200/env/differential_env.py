@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..utils.rigid import Obstacle, RectRobot, rects_of
+from ..utils.rigid import CircleRobot, Obstacle, RectRobot, rects_of
 from .robot_env import RobotEnv
 
 
@@ -36,6 +36,7 @@ class DifferentialDriveEnv(RobotEnv):
         self.min_acc_v = -self.max_acc_v
         self.max_acc_w = max_acc_w
         self.min_acc_w = -self.max_acc_w
+        self._handle = None
         self.rigid_robot = RectRobot(np.array([[-0.7, -0.5], [0.7, 0.5]]), color="k")
         self.env_bounds = np.zeros((2, 2))
         self.env_bounds[0, 0] = env_bounds[0]
@@ -48,14 +49,29 @@ class DifferentialDriveEnv(RobotEnv):
         self._rects = np.zeros((0, 4), dtype=np.float32)
         self._dirty = True
 
+    # ---- footprint (differential_env.py:41; RectRobot or CircleRobot, rigid.py:256-347) ----
+    @property
+    def rigid_robot(self):
+        return self._rigid_robot
+
+    @rigid_robot.setter
+    def rigid_robot(self, robot):
+        if not isinstance(robot, (RectRobot, CircleRobot)):
+            raise NotImplementedError("Unsupported robot footprint")
+        self._rigid_robot = robot
+        self._handle = None          # the footprint is baked into the device handle
+
     # ---- device handle -------------------------------------------------
     @property
     def handle(self):
         """The CrlkEnv handle (created lazily on the current CUDA device)."""
         if self._handle is None:
+            rb = self._rigid_robot
+            circle = isinstance(rb, CircleRobot)
+            rect = np.array([-0.7, -0.5, 0.7, 0.5], dtype=np.float32) if circle else rb.rect.reshape(4)
             self._handle = ops.EnvHandle(self.max_v, self.min_v, self.max_w, self.max_acc_v,
                                          self.max_acc_w, self.base_dt, self.env_bounds.reshape(4),
-                                         self._rects, self.rigid_robot.rect.reshape(4))
+                                         self._rects, rect, float(rb.radius) if circle else 0.0)
             self._dirty = False
         elif self._dirty:
             self._handle.set_obs(self._rects)

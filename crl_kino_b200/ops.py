@@ -37,11 +37,11 @@ class EnvHandle:
     """Owns a CrlkEnv* (obstacle set + vehicle limits on the device)."""
 
     def __init__(self, max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt, env_bounds, rects,
-                 robot_rect=ROBOT_RECT):
+                 robot_rect=ROBOT_RECT, robot_radius=0.0):
         require_cuda()
         self.params = EnvParams(max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt,
                                 (C.c_double * 4)(*[float(x) for x in env_bounds]),
-                                (C.c_float * 4)(*[float(x) for x in robot_rect]))
+                                (C.c_float * 4)(*[float(x) for x in robot_rect]), float(robot_radius))
         rects = np.ascontiguousarray(np.asarray(rects, dtype=np.float32).reshape(-1, 4))
         self.M = len(rects)
         h = C.c_void_p()

@@ -45,6 +45,14 @@ class RectRobot(Rigid):
         self.rect = np.array(rect, dtype=np.float32)
 
 
+class CircleRobot(Rigid):
+    """rigid.py:331-347: circular footprint about the body origin."""
+
+    def __init__(self, radius, pose=np.zeros(3), color="black"):
+        super().__init__(pose, color)
+        self.radius = radius
+
+
 def rects_of(obs_list):
     """list[RectObs] (or an (M, 4) / (M, 2, 2) array) -> float32 [M, 4] left, bottom, right, top."""
     if isinstance(obs_list, np.ndarray):
@@ -59,7 +67,7 @@ class _RefUnpickler(pickle.Unpickler):
 
     def find_class(self, module, name):
         if module.startswith("crl_kino.utils.rigid"):
-            return {"RectObs": RectObs, "RectRobot": RectRobot}[name]
+            return {"RectObs": RectObs, "RectRobot": RectRobot, "CircleRobot": CircleRobot}[name]
         return super().find_class(module, name)
 
 

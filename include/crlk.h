@@ -36,7 +36,7 @@ extern "C" {
 #define CRLK_E_NODEVICE (-3)  /* no CUDA device: there is NO CPU fallback */
 #define CRLK_E_CAPACITY (-4)  /* a caller-provided capacity is too small */
 
-#define CRLK_ABI_VERSION 1
+#define CRLK_ABI_VERSION 2
 
 /* status codes written by the extend kernels (rrt.py:121-128) */
 #define CRLK_EXT_TIMEOUT 0    /* n_max_extend steps executed */
@@ -52,6 +52,7 @@ typedef struct {
     double max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt;
     double env_bounds[4];   /* xmin xmax ymin ymax */
     float robot_rect[4];    /* RectRobot rect, float32 values (differential_env.py:41) */
+    double robot_radius;    /* > 0: CircleRobot(radius) footprint (utils/rigid.py:331-347) replaces the rectangle */
 } CrlkEnvParams;
 
 /* DWA.__init__ / set_dwa (policy/dwa.py:13-33).  use_clearance = 0 is the

@@ -27,6 +27,7 @@ typedef struct {
     double max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt;
     double env_bounds[4]; /* xmin xmax ymin ymax */
     float robot_rect[4];  /* left bottom right top, float32 VALUES (rigid.py:263) */
+    double robot_radius;  /* > 0: CircleRobot(radius) footprint (rigid.py:331-347) instead of the rectangle */
 } OrcEnv;
 
 typedef struct {
@@ -267,11 +268,27 @@ double orc_dis2obs(const float *robot_rect, const double *pose, const float *obs
     return (dis > 0.05) ? dis : -1.0;
 }
 
+/* CircleRobot.dis2obs (rigid.py:336-347): the centre is wTb @ [0, 0, 1] = the pose's xy. */
+double orc_dis2obs_circle(double radius, const double *pose, const float *obs)
+{
+    double cx = pose[0], cy = pose[1];
+    if ((double)obs[0] <= cx && cx <= (double)obs[2] && (double)obs[1] <= cy && cy <= (double)obs[3])
+        return -1.0;                                   /* point_in_obstacle, closed (rigid.py:148-156) */
+    double dis = rect_dis2point(obs, cx, cy) - radius;
+    return (dis > 0.05) ? dis : -1.0;
+}
+
+static double env_dis2obs(const OrcEnv *e, const double *state, const float *obs)
+{
+    return (e->robot_radius > 0.0) ? orc_dis2obs_circle(e->robot_radius, state, obs)
+                                   : orc_dis2obs(e->robot_rect, state, obs);
+}
+
 /* differential_env.py:146-151 (sequential early exit). obs = M x 4 float32. */
 int orc_valid_state(const OrcEnv *e, const float *obs, int M, const double *state)
 {
     for (int k = 0; k < M; k++)
-        if (orc_dis2obs(e->robot_rect, state, obs + 4 * k) == -1.0) return 0;
+        if (env_dis2obs(e, state, obs + 4 * k) == -1.0) return 0;
     return 1;
 }
 
@@ -279,7 +296,7 @@ int orc_valid_state(const OrcEnv *e, const float *obs, int M, const double *stat
 double orc_get_clearance(const OrcEnv *e, const float *obs, int M, const double *state)
 {
     double dis = 100.0;
-    for (int k = 0; k < M; k++) dis = pymin(dis, orc_dis2obs(e->robot_rect, state, obs + 4 * k));
+    for (int k = 0; k < M; k++) dis = pymin(dis, env_dis2obs(e, state, obs + 4 * k));
     return dis;
 }
 

@@ -31,7 +31,7 @@ def build(force=False):
 class OrcEnv(C.Structure):
     _fields_ = [("max_v", C.c_double), ("min_v", C.c_double), ("max_w", C.c_double),
                 ("max_acc_v", C.c_double), ("max_acc_w", C.c_double), ("base_dt", C.c_double),
-                ("env_bounds", C.c_double * 4), ("robot_rect", C.c_float * 4)]
+                ("env_bounds", C.c_double * 4), ("robot_rect", C.c_float * 4), ("robot_radius", C.c_double)]
 
 
 class OrcDwa(C.Structure):
@@ -54,6 +54,8 @@ def lib():
         _lib.orc_pairwise_sum.restype = C.c_double
         _lib.orc_pairwise_sum.argtypes = [C.c_void_p, C.c_long, C.c_long]
         _lib.orc_dis2obs.restype = C.c_double
+        _lib.orc_dis2obs_circle.restype = C.c_double
+        _lib.orc_dis2obs_circle.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
         _lib.orc_get_clearance.restype = C.c_double
         _lib.orc_arange.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int]
         _lib.orc_motion_velocity.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -90,10 +92,11 @@ class Env:
     """Oracle counterpart of DifferentialDriveEnv (differential_env.py:27-169)."""
 
     def __init__(self, max_v=1.0, min_v=-0.1, max_w=math.pi, max_acc_v=1.0, max_acc_w=math.pi,
-                 env_bounds=(-20, 20, -20, 20), base_dt=0.1, robot_rect=ROBOT_RECT):
+                 env_bounds=(-20, 20, -20, 20), base_dt=0.1, robot_rect=ROBOT_RECT, robot_radius=0.0):
+        """robot_radius > 0: CircleRobot(radius) footprint (rigid.py:331-347) instead of the rectangle."""
         self.p = OrcEnv(max_v, min_v, max_w, max_acc_v, max_acc_w, base_dt,
                         (C.c_double * 4)(*[float(x) for x in env_bounds]),
-                        (C.c_float * 4)(*[float(x) for x in robot_rect]))
+                        (C.c_float * 4)(*[float(x) for x in robot_rect]), float(robot_radius))
         self.rects = np.zeros((0, 4), dtype=np.float32)
         self.max_v, self.min_v, self.max_w = max_v, min_v, max_w
         self.max_acc_v, self.max_acc_w, self.base_dt = max_acc_v, max_acc_w, base_dt
@@ -144,6 +147,10 @@ class Env:
         rect = np.ascontiguousarray(rect, dtype=np.float32).reshape(4)
         rr = np.ctypeslib.as_array(self.p.robot_rect).astype(np.float32)
         return lib().orc_dis2obs(_p(rr), _p(_f64(pose)), _p(rect))
+
+    def dis2obs_circle(self, radius, pose, rect):
+        rect = np.ascontiguousarray(rect, dtype=np.float32).reshape(4)
+        return lib().orc_dis2obs_circle(float(radius), _p(_f64(pose)), _p(rect))
 
     def valid_state_check(self, state):
         return bool(lib().orc_valid_state(self.ref, _p(self.rects), self.M, _p(_f64(state))))

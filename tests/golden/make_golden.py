@@ -748,10 +748,88 @@ def g_gym():
     save("gym", **out)
 
 
+def g_circle():
+    """CircleRobot footprint (utils/rigid.py:331-347): pairwise dis2obs and whole-map
+    validity / clearance with env.rigid_robot = CircleRobot(radius)."""
+    from crl_kino.utils.rigid import CircleRobot
+    rng = np.random.default_rng(14)
+    maps = load_maps()
+    out = {}
+    radius = 0.6
+    robot = CircleRobot(radius)
+    poses, rects, dis = [], [], []
+    for mname in ("test_env1", "test_env2"):
+        for o in maps[mname]:
+            l, b, r, t = o.rect.reshape(4)
+            for _ in range(30):
+                p = np.array([rng.uniform(l - 1.5, r + 1.5), rng.uniform(b - 1.5, t + 1.5), rng.uniform(-np.pi, np.pi)])
+                robot.pose = p
+                poses.append(p); rects.append(o.rect.reshape(4)); dis.append(robot.dis2obs(o))
+    out["radius"] = np.array(radius)
+    out["pair_pose"] = np.array(poses)
+    out["pair_rect"] = np.array(rects, dtype=np.float32)
+    out["pair_dis"] = np.array(dis, dtype=np.float64)
+    print("circle pairs:", len(dis), "colliding:", int(np.sum(np.array(dis) == -1)))
+    for mname in ("test_env1", "test_env2"):
+        env = make_env(maps[mname])
+        env.rigid_robot = CircleRobot(radius)
+        s = random_states(rng, 200)
+        out[f"{mname}_states"] = s
+        out[f"{mname}_valid"] = np.array([env.valid_state_check(x) for x in s])
+        out[f"{mname}_clear"] = np.array([env.get_clearance(x) for x in s], dtype=np.float64)
+    save("circle", **out)
+
+
+def g_formats():
+    """The reference's on-disk formats: bytes pickled BY THE REFERENCE's classes
+    (obstacle list, list of obstacle lists, node_list, path, benchmark positions, results dict)
+    plus the arrays they hold; and the converse check, done here once: files written by
+    crl_kino_b200.utils.io load under the unmodified reference."""
+    maps = load_maps()
+    out = {}
+    as_u8 = lambda b: np.frombuffer(b, dtype=np.uint8)
+    out["obs_pickle"] = as_u8(pickle.dumps(maps["test_env2"]))
+    out["obs_rects"] = rects_of(maps["test_env2"])
+    lol = [maps["obs_list_0"], maps["obs_list_1"]]
+    out["obs_lol_pickle"] = as_u8(pickle.dumps(lol))
+    out["obs_lol_rects0"] = rects_of(lol[0])
+    out["obs_lol_rects1"] = rects_of(lol[1])
+    pos = pickle.load(open(os.path.join(REF, "examples", "benchmark_position_test_env2.pkl"), "rb"))
+    out["positions_pickle"] = as_u8(pickle.dumps(pos))
+    out["positions"] = np.array(pos, dtype=np.float64)
+    env = make_env(maps["test_env1"])
+    planner = RRT(env, max_iter=4)
+    planner.set_start_and_goal(np.array([-5, -15, 0, 0, 0.0]), np.array([10, 10, 0, 0, 0.0]))
+    random.seed(5); np.random.seed(5)
+    with quiet():
+        path = planner.planning()
+    states, parents, plen = pack_tree(planner)
+    out["tree_pickle"] = as_u8(pickle.dumps(planner.node_list))
+    out["tree_states"] = states
+    out["tree_parents"] = parents
+    out["tree_plen"] = plen
+    out["path_pickle"] = as_u8(pickle.dumps(path))
+    out["path"] = np.array(path)
+    data = {"runtime": np.array([1.25, -1, 3.5]), "path_len": np.array([12.4, 30.0])}     # benchmark.py:86-88
+    out["results_pickle"] = as_u8(pickle.dumps(data))
+    # converse direction: our writers, the reference's loaders
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from crl_kino_b200.utils import io as cio
+    back = pickle.loads(cio.save_obstacles(out["obs_rects"]))
+    assert type(back[0]) is RectObs and np.array_equal(rects_of(back), out["obs_rects"])
+    assert back[3].point_in_obstacle(back[3].rect.mean(0))
+    nodes = pickle.loads(cio.save_tree(planner.node_list))
+    assert type(nodes[0]) is RRT.Node
+    s2, p2, l2 = pack_tree(type("P", (), {"node_list": nodes})())
+    assert np.array_equal(s2, states) and np.array_equal(p2, parents) and np.array_equal(l2, plen)
+    print("formats: reference loaded the files written by crl_kino_b200.utils.io")
+    save("formats", **out)
+
+
 ALL = dict(fixtures=g_fixtures, numerics=g_numerics, motion=g_motion, dwa=g_dwa,
            dwa_clearance=g_dwa_clearance, geometry=g_geometry, obs=g_obs, nearest=g_nearest,
            steer_dwa=g_steer_dwa, plan_dwa=g_plan_dwa, policy=g_policy, estimator=g_estimator,
-           steer_rl=g_steer_rl, plan_rl=g_plan_rl, gym=g_gym)
+           steer_rl=g_steer_rl, plan_rl=g_plan_rl, gym=g_gym, circle=g_circle, formats=g_formats)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -26,12 +26,13 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(raw, n), f"{n} declared in crlk.h but not exported by libcrlk.so"
         assert n in PROTOTYPES, f"{n} has no ctypes prototype"
     assert sorted(PROTOTYPES) == names
-    assert lib().crlk_abi_version() == 1
+    assert lib().crlk_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
-    from crl_kino_b200._lib import DwaParams, EnvParams, ExtendParams
-    assert ctypes.sizeof(EnvParams) == 6 * 8 + 4 * 8 + 4 * 4
+    from crl_kino_b200._lib import DwaParams, EnvParams, ExtendParams, PlanParams
+    assert ctypes.sizeof(EnvParams) == 6 * 8 + 4 * 8 + 4 * 4 + 8
+    assert ctypes.sizeof(PlanParams) == 8 + 4 * 8
     assert ctypes.sizeof(DwaParams) == 7 * 8 + 2 * 4
     assert ctypes.sizeof(ExtendParams) == 4 + 4 + 8 + 8
 
@@ -44,7 +45,7 @@ def test_no_cpu_fallback():
     l = lib()
     assert l.crlk_device_count() == 0
     p = EnvParams(1.0, -0.1, np.pi, 1.0, np.pi, 0.1, (ctypes.c_double * 4)(-20, 20, -20, 20),
-                  (ctypes.c_float * 4)(-0.7, -0.5, 0.7, 0.5))
+                  (ctypes.c_float * 4)(-0.7, -0.5, 0.7, 0.5), 0.0)
     h = ctypes.c_void_p()
     rc = l.crlk_env_create(ctypes.byref(p), None, 0, ctypes.byref(h))
     assert rc == -3 and b"no CPU fallback" in l.crlk_last_error()

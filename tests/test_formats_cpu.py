@@ -1,0 +1,67 @@
+"""The reference's on-disk formats through crl_kino_b200.utils.io: files
+pickled by the unmodified reference (bytes kept in tests/golden/formats.npz) are read without
+the reference installed, and files written here carry the reference's class paths (the
+generating script checked that the reference's own pickle.load accepts them).  CPU only."""
+import pickle
+import sys
+import types
+
+import numpy as np
+
+from conftest import golden
+from crl_kino_b200.utils import io as cio
+
+
+def test_read_reference_pickles():
+    g = golden("formats")
+    assert "crl_kino" not in sys.modules                      # read without the reference importable
+    obs = cio.load_obstacles(g["obs_pickle"].tobytes())
+    assert type(obs[0]).__name__ == "RectObs" and obs[0].rect.dtype == np.float32
+    assert np.array_equal(cio.load_obstacles_flat(g["obs_pickle"].tobytes()), g["obs_rects"])
+    lol = cio.load_obstacles_flat(g["obs_lol_pickle"].tobytes())
+    assert np.array_equal(lol[0], g["obs_lol_rects0"]) and np.array_equal(lol[1], g["obs_lol_rects1"])
+    assert np.array_equal(cio.load_positions(g["positions_pickle"].tobytes()), g["positions"])
+    nodes = cio.load_tree(g["tree_pickle"].tobytes())
+    states, parents = cio.tree_arrays(nodes)
+    assert np.array_equal(states, g["tree_states"]) and np.array_equal(parents, g["tree_parents"])
+    assert np.array_equal([len(n.path) for n in nodes], g["tree_plen"])
+    assert np.array_equal(cio.load_path(g["path_pickle"].tobytes()), g["path"])
+    res = cio.load_results(g["results_pickle"].tobytes())
+    assert set(res) == {"runtime", "path_len"} and res["runtime"][1] == -1
+
+
+def test_written_files_carry_reference_class_paths(tmp_path):
+    g = golden("formats")
+    blob = cio.save_obstacles(g["obs_rects"], str(tmp_path / "map.pkl"))
+    assert b"crl_kino.utils.rigid" in blob and b"RectObs" in blob and b"crl_kino_b200" not in blob
+    assert "crl_kino" not in sys.modules                      # the stand-in modules are gone again
+    assert np.array_equal(cio.load_obstacles_flat(str(tmp_path / "map.pkl")), g["obs_rects"])
+    nodes = cio.load_tree(g["tree_pickle"].tobytes())
+    tblob = cio.save_tree(nodes)
+    assert b"crl_kino.planner.rrt" in tblob and b"RRT.Node" in tblob and b"crl_kino_b200" not in tblob
+    # a stand-in for the reference's modules (plain classes, as pickle needs) loads both files
+    mods = {n: types.ModuleType(n) for n in ("crl_kino", "crl_kino.utils", "crl_kino.utils.rigid",
+                                             "crl_kino.planner", "crl_kino.planner.rrt")}
+    mods["crl_kino.utils.rigid"].RectObs = type("RectObs", (), {"__module__": "crl_kino.utils.rigid"})
+    node = type("Node", (), {"__module__": "crl_kino.planner.rrt", "__qualname__": "RRT.Node"})
+    mods["crl_kino.planner.rrt"].RRT = type("RRT", (), {"Node": node})
+    sys.modules.update(mods)
+    try:
+        back = pickle.loads(blob)
+        assert np.array_equal(np.array([o.rect.reshape(4) for o in back]), g["obs_rects"]) and back[0].color == "black"
+        tb = pickle.loads(tblob)
+        assert tb[1].parent is tb[int(g["tree_parents"][1])] and np.array_equal(tb[-1].state, g["tree_states"][-1])
+    finally:
+        for n in mods:
+            sys.modules.pop(n, None)
+
+
+def test_planning_results_dict(tmp_path):
+    """examples/benchmark.py:38-43, :69-75, :86-88."""
+    data = cio.planning_results([True, False, True], [1.5, 9.0, 2.5], [63, 10, 151])
+    assert np.array_equal(data["runtime"], [1.5, -1, 2.5])
+    np.testing.assert_allclose(data["path_len"], [0.2 * 62, 0.2 * 150])
+    cio.save_results(data, str(tmp_path / "planning_results_env1"))
+    back = pickle.load(open(tmp_path / "planning_results_env1.pkl", "rb"))
+    assert np.array_equal(back["runtime"], data["runtime"]) and np.array_equal(back["path_len"], data["path_len"])
+    assert cio.benchmark_pairs(np.zeros((4, 5)))[:4] == [(0, 1), (0, 2), (0, 3), (1, 0)]

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 def test_library_loaded():
     from crl_kino_b200._lib import lib
     assert lib().crlk_device_count() >= 1
-    assert lib().crlk_abi_version() == 1
+    assert lib().crlk_abi_version() == 2
 
 
 def test_motion_golden():
@@ -141,3 +141,31 @@ def test_edge_cases():
     assert not env2.valid_state_check(np.zeros(5))
     with pytest.raises(AssertionError):
         env2.add_obs("not an obstacle")
+
+
+@pytest.mark.parametrize("mname", ("test_env1", "test_env2"))
+def test_circle_robot_golden(mname):
+    """env.rigid_robot = CircleRobot(radius) (rigid.py:331-347): validity and clearance against
+    the unmodified reference; near-threshold states are reported, not compared."""
+    from crl_kino_b200.utils.rigid import CircleRobot
+    g = golden("circle")
+    env, _ = make_envs(fixture_map(mname))
+    env.rigid_robot = CircleRobot(float(g["radius"]))
+    valid, clr, near = env.valid_state_batch(g[f"{mname}_states"], want_clearance=True, want_near=True)
+    assert_flags(np_(valid), g[f"{mname}_valid"], np_(near), "circle valid")
+    ok = np_(near) == 0
+    np.testing.assert_allclose(np_(clr)[ok], g[f"{mname}_clear"][ok], rtol=1e-9, atol=1e-12)
+    assert env.valid_state_check(g[f"{mname}_states"][0]) == bool(g[f"{mname}_valid"][0])
+    # one robot-obstacle pair at a time: a single-obstacle env per golden pair
+    env1, _ = make_envs(g["pair_rect"][:1])
+    env1.rigid_robot = CircleRobot(float(g["radius"]))
+    for k in range(0, len(g["pair_dis"]), 17):
+        env1.set_obs(g["pair_rect"][k:k + 1])
+        s = np.zeros(5)
+        s[:3] = g["pair_pose"][k]
+        c = env1.get_clearance(s)
+        ref = g["pair_dis"][k]
+        if abs(abs(ref) - 0.05) > 1e-6:
+            assert (c == -1.0) == (ref == -1.0)
+            if ref != -1.0:
+                assert abs(c - min(ref, 100.0)) <= 1e-9 * max(1.0, abs(ref))

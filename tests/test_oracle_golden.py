@@ -154,3 +154,21 @@ def test_estimator_choose_parent(fixtures):
             gi, gc = p.choose_parent(nodes, orc.Node(t))
             assert gi == i
             assert gc == pytest.approx(c, rel=1e-5)
+
+
+def test_circle_robot_golden(fixtures):
+    """CircleRobot footprint (rigid.py:331-347)."""
+    g = golden("circle")
+    radius = float(g["radius"])
+    e = orc.Env()
+    for pose, rect, ref in zip(g["pair_pose"], g["pair_rect"], g["pair_dis"]):
+        got = e.dis2obs_circle(radius, pose, rect)
+        assert (got == -1.0) == (ref == -1.0)
+        if ref != -1.0:
+            assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref))
+    for mname in ("test_env1", "test_env2"):
+        env = orc.Env(robot_radius=radius)
+        env.set_obs(fixtures["map_" + mname])
+        valid, clr = env.valid_state_batch(g[f"{mname}_states"])
+        assert np.array_equal(valid, g[f"{mname}_valid"])
+        np.testing.assert_allclose(clr, g[f"{mname}_clear"], rtol=1e-9, atol=1e-12)
