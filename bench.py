@@ -177,10 +177,14 @@ def planning_leg(args, env, dwa, rank):
     for rep in range(3):                       # first pass = warm-up, best of the next two
         fp.reset()
         torch.cuda.synchronize()
+        if rep == 2:
+            torch.cuda.profiler.start()        # second ncu range (the first is the extend step loop)
         e0.record()
         fp.plan_async(dstreams)
         e1.record()
         torch.cuda.synchronize()
+        if rep == 2:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         if rep > 0:
             best = ms if best is None else min(best, ms)

@@ -92,6 +92,20 @@ struct RobotPose {
     double wx[4], wy[4];   // robot corners in the world frame: (l,b) (l,t) (r,t) (r,b)
 };
 
+// Footprint corners from a pose whose heading is given as (cos, sin).
+__device__ __forceinline__ void robot_pose_from_cs(const EnvP &e, double x, double y, double cs, double sn,
+                                                   RobotPose &g)
+{
+    g.x = x; g.y = y; g.c = cs; g.s = sn;
+    const double bx[4] = {(double)e.rl, (double)e.rl, (double)e.rr, (double)e.rr};
+    const double by[4] = {(double)e.rb, (double)e.rt, (double)e.rt, (double)e.rb};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        g.wx[i] = (cs * bx[i] + (-sn) * by[i]) + x;   // rigid.py:223-227
+        g.wy[i] = (sn * bx[i] + cs * by[i]) + y;
+    }
+}
+
 __device__ __forceinline__ void robot_pose_setup(const EnvP &e, double x, double y, double th,
                                                  RobotPose &g)
 {

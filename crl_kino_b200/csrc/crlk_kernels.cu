@@ -602,10 +602,17 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
 
 // ------------------------------------------------------------------- DWA (K1)
 
+// Two launch shapes of the DWA kernels (template parameter T = threads per CTA):
+//   throughput: 256 threads, 3 CTAs per SM (85 registers; measured best of 2, 3, 4) -- many more
+//               extensions than CTAs, the phases of co-resident CTAs interleave;
+//   latency:    768 threads, 1 CTA per SM (same 85-register budget) -- few extensions per SM, the
+//               launch time is the longest chain of dependent control steps, so each step gets
+//               three times the threads.
 #define DWA_THREADS 256
 #ifndef DWA_MIN_BLOCKS
-#define DWA_MIN_BLOCKS 3     // 85 registers per thread: 3 CTAs (24 warps) per SM (measured best of 2,3,4)
+#define DWA_MIN_BLOCKS 3
 #endif
+#define DWA_WIDE_THREADS 768
 #define PW_BLOCK 128
 
 struct DwaSmem {
@@ -617,8 +624,12 @@ struct DwaSmem {
     int *leaf_ids;                    // [nmax] ids of the leaf nodes
     double *nd_val;                   // [3][nmax] per-column node sums
     int *lvl_start;                   // [PW_MAX_LEVELS + 1]
-    double *red_v, *red_s;            // [32]
+    double *red_v, *red_s;            // [32] screened minimum / runner-up per warp
     int *red_i;                       // [32]
+    double *red2_v;                   // [32] exact minimum per warp
+    double *hdr;                      // [8]  v_hi v_lo w_hi w_lo of the current window
+    int *ihdr;                        // [4]  nv nw
+    RobotPose *pose;                  // footprint of the state the next validity test looks at
     double *scal;                     // [16]
     int *iscal;                       // [8]: 0 n_leaves, 1 opt idx, 2 near tie, 3 cached R, 4 n_levels, 5 n_nodes
     int *queue;                       // [1024] scratch for the collision survivor list
@@ -657,6 +668,10 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_rv = take(sizeof(double) * 32);
     size_t o_rs = take(sizeof(double) * 32);
     size_t o_ri = take(sizeof(int) * 32);
+    size_t o_r2 = take(sizeof(double) * 32);
+    size_t o_hd = take(sizeof(double) * 8);
+    size_t o_ih = take(sizeof(int) * 4);
+    size_t o_po = take(sizeof(RobotPose));
     size_t o_sc = take(sizeof(double) * 16);
     size_t o_is = take(sizeof(int) * 8);
     size_t o_q = take(sizeof(int) * 1024);
@@ -672,6 +687,8 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->nd_val = (double *)(base + o_nval); s->lvl_start = (int *)(base + o_lvl);
         s->red_v = (double *)(base + o_rv); s->red_s = (double *)(base + o_rs);
         s->red_i = (int *)(base + o_ri);
+        s->red2_v = (double *)(base + o_r2); s->hdr = (double *)(base + o_hd);
+        s->ihdr = (int *)(base + o_ih); s->pose = (RobotPose *)(base + o_po);
         s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
         s->queue = (int *)(base + o_q);
         s->spos = spos; s->rmax = rmax; s->nmax = nmax;
@@ -812,29 +829,35 @@ __device__ __forceinline__ double clearance_thread(const EnvP &e, const ObsSet &
 
 // DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
 // doubles) and the goal must be block-uniform.  Every thread returns the result.
-template <class Epi>
+template <int T, class Epi>
 __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSet &os,
                                        const double *st, double gx, double gy,
                                        const DwaSmem &sm, Epi epilogue)
 {
-    const int tid = threadIdx.x, T = DWA_THREADS;
+    const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const double dt = e.base_dt;
-    // dynamic window over d.dt (dwa.py:46, differential_env.py:107-114)
-    double v_hi = pymin(st[3] + e.max_acc_v * d.dt, e.max_v);
-    double v_lo = pymax(st[3] - e.max_acc_v * d.dt, e.min_v);
-    double w_hi = pymin(st[4] + e.max_acc_w * d.dt, e.max_w);
-    double w_lo = pymax(st[4] - e.max_acc_w * d.dt, -e.max_w);
-    int nv = min(arange_len(v_lo, v_hi + d.v_res, d.v_res), d.nv_max);
-    int nw = min(arange_len(w_lo, w_hi + d.w_res, d.w_res), d.nw_max);
-    double v1 = v_lo + d.v_res, vd = v1 - v_lo;
-    double w1 = w_lo + d.w_res, wd = w1 - w_lo;
-    const int R = nv * nw;
+    // dynamic window over d.dt (dwa.py:46, differential_env.py:107-114) and the grid sizes: one
+    // thread (the two float64 divisions of arange_len are not worth 256+ copies)
+    if (tid == 0) {
+        double vh = pymin(st[3] + e.max_acc_v * d.dt, e.max_v);
+        double vl = pymax(st[3] - e.max_acc_v * d.dt, e.min_v);
+        double wh = pymin(st[4] + e.max_acc_w * d.dt, e.max_w);
+        double wl = pymax(st[4] - e.max_acc_w * d.dt, -e.max_w);
+        sm.hdr[0] = vh; sm.hdr[1] = vl; sm.hdr[2] = wh; sm.hdr[3] = wl;
+        sm.ihdr[0] = min(arange_len(vl, vh + d.v_res, d.v_res), d.nv_max);
+        sm.ihdr[1] = min(arange_len(wl, wh + d.w_res, d.w_res), d.nw_max);
+    }
     const int S = d.n_sub * d.n_outer, spos = sm.spos;
 
     PHASE_START();
-    __syncthreads();   // previous users of the shared tables are done
+    __syncthreads();   // previous users of the shared tables are done; the header is visible
     PHASE_MARK(0);
+    const double v_hi = sm.hdr[0], v_lo = sm.hdr[1], w_lo = sm.hdr[3];
+    const int nv = sm.ihdr[0], nw = sm.ihdr[1];
+    const double v1 = v_lo + d.v_res, vd = v1 - v_lo;
+    const double w1 = w_lo + d.w_res, wd = w1 - w_lo;
+    const int R = nv * nw;
     // velocity chains (one per v command) and heading chains (one per w command)
     for (int i = tid; i < nv; i += T) {
         double cv = arange_at(v_lo, v1, vd, i);
@@ -850,19 +873,22 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         }
         sm.vlast[i] = cur;
     }
-    for (int j = T - 1 - tid; j < nw; j += T) {
+    // heading chains: one task per (w command, sub-step) -- the omega / theta recurrences up to the
+    // sub-step are cheap, the float64 sincos at its end is not, so the sub-steps run side by side
+    for (int task = T - 1 - tid; task < nw * spos; task += T) {
+        const int j = task / spos, ks = task - j * spos;
         double cw = arange_at(w_lo, w1, wd, j);
         double cur = st[4], th = st[2];
-        for (int k = 0; k < spos; k++) {
+        for (int k = 0; k <= ks; k++) {
             cur = vel_substep(cur, cw, e.max_acc_w, -e.max_w, e.max_w, dt);
             th = normalize_angle(th + cur * dt);
-            double sn, cs;
-            sincos(th, &sn, &cs);
-            sm.wcos[j * spos + k] = cs;
-            sm.wsin[j * spos + k] = sn;
-            if ((k + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (k + 1) / d.n_sub - 1] = th;
-            if (k + 1 == d.n_sub) sm.wom[j] = cur;      // omega after the first dt step
         }
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        sm.wcos[task] = cs;
+        sm.wsin[task] = sn;
+        if ((ks + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (ks + 1) / d.n_sub - 1] = th;
+        if (ks + 1 == d.n_sub) sm.wom[j] = cur;      // omega after the first dt step
     }
     if (warp == 3 && sm.iscal[3] != R) pw_build_tree_warp(R, sm);   // warps 3-4 have no chain work
     // clearance of the shared first row (dwa.py:65-67, i = 0)
@@ -1030,11 +1056,14 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     }
     __syncthreads();
     PHASE_MARK(5);
-    double m_a = sm.red_v[0], s_a = sm.red_s[0];
+    // block minimum and runner-up from the per-warp pairs: every warp reduces them with shuffles
+    double m_a = (lane < T / 32) ? sm.red_v[lane] : CUDART_INF;
+    double s_a = (lane < T / 32) ? sm.red_s[lane] : CUDART_INF;
 #pragma unroll
-    for (int w = 1; w < T / 32; w++) {
-        double ob = sm.red_v[w], os = sm.red_s[w];
-        s_a = fmin(fmin(s_a, os), fmax(m_a, ob));
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, m_a, o);
+        double os2 = __shfl_xor_sync(0xffffffffu, s_a, o);
+        s_a = fmin(fmin(s_a, os2), fmax(m_a, ob));
         m_a = fmin(m_a, ob);
     }
     const double lim = m_a + fabs(m_a) * 1e-12;
@@ -1057,19 +1086,19 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             bi = abi;
         }
     }
-    __syncthreads();          // red_v / red_s are reused below
     warp_argmin(best, bi);
-    if (lane == 0) { sm.red_v[warp] = best; sm.red_i[warp] = bi; }
+    if (lane == 0) { sm.red2_v[warp] = best; sm.red_i[warp] = bi; }
     __syncthreads();
     PHASE_MARK(6);
+    if (warp == 0) {
+        double b = (lane < T / 32) ? sm.red2_v[lane] : CUDART_INF;
+        int ix = (lane < T / 32) ? sm.red_i[lane] : 0x7fffffff;
+        warp_argmin(b, ix);
+        best = b; bi = ix;
+    }
     if (tid == 0) {
-        double b = sm.red_v[0];
-        int ix = sm.red_i[0];
-        for (int w = 1; w < T / 32; w++) {
-            double ob = sm.red_v[w];
-            int oi = sm.red_i[w];
-            if (ob < b || (ob == b && oi < ix)) { b = ob; ix = oi; }
-        }
+        double b = best;
+        int ix = bi;
         int i = ix / nw, j = ix - i * nw;
         sm.scal[4] = arange_at(v_lo, v1, vd, i);
         sm.scal[5] = arange_at(w_lo, w1, wd, j);
@@ -1090,7 +1119,8 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             row1[0] = x; row1[1] = y; row1[2] = sm.wth[j * d.n_outer];
             row1[3] = vt[d.n_sub - 1]; row1[4] = sm.wom[j];
         }
-        epilogue(sm.scal[4], sm.scal[5], ix, row1);    // thread 0 only, before the closing barrier
+        // thread 0 only, before the closing barrier; also gets cos / sin of row 1's heading
+        epilogue(sm.scal[4], sm.scal[5], ix, row1, sm.wcos[j * spos + d.n_sub - 1], sm.wsin[j * spos + d.n_sub - 1]);
     }
     __syncthreads();
     PHASE_MARK(7);
@@ -1100,7 +1130,8 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     return res;
 }
 
-__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 k_dwa_control(EnvP e, DwaP d, ObsSet os,
               const double *__restrict__ states, const double *__restrict__ goals, int goal_stride,
               int B, double *opt_v, int *opt_idx, double *opt_cost, double *opt_traj,
@@ -1116,7 +1147,8 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
         __syncthreads();
         double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
-        DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm, [](double, double, int, const double *) {});
+        DwaResult r = dwa_control_block<T>(e, d, os, s_state, gx, gy, sm,
+                                           [](double, double, int, const double *, double, double) {});
         if (threadIdx.x == 0) {
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
@@ -1136,6 +1168,15 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
             }
         }
     }
+}
+
+// Launch-shape choice: with fewer work items than ~2 throughput-shaped waves (148 SMs x 3 CTAs)
+// the launch is bound by its longest dependent chain, not by total work.  CRLK_DWA_WIDE=0/1 forces.
+static bool dwa_use_wide(int n_items)
+{
+    static const char *env = getenv("CRLK_DWA_WIDE");
+    if (env) return atoi(env) != 0;
+    return n_items <= 2 * 148 * DWA_MIN_BLOCKS * 2;
 }
 
 static int set_smem_attr(const void *fn, size_t bytes)
@@ -1173,28 +1214,36 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
     CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
     if (B == 0) return CRLK_OK;
     size_t smem = crlk_dwa_smem_bytes(d);
-    rc = set_smem_attr((const void *)k_dwa_control, smem);
-    if (rc) return rc;
-    k_dwa_control<<<B, DWA_THREADS, smem, (cudaStream_t)stream>>>(
-        env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
-        opt_traj, n_rollouts, near_tie);
+    if (dwa_use_wide(B)) {
+        rc = set_smem_attr((const void *)k_dwa_control<DWA_WIDE_THREADS, 1>, smem);
+        if (rc) return rc;
+        k_dwa_control<DWA_WIDE_THREADS, 1><<<B, DWA_WIDE_THREADS, smem, (cudaStream_t)stream>>>(
+            env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
+            opt_traj, n_rollouts, near_tie);
+    } else {
+        rc = set_smem_attr((const void *)k_dwa_control<DWA_THREADS, DWA_MIN_BLOCKS>, smem);
+        if (rc) return rc;
+        k_dwa_control<DWA_THREADS, DWA_MIN_BLOCKS><<<B, DWA_THREADS, smem, (cudaStream_t)stream>>>(
+            env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
+            opt_traj, n_rollouts, near_tie);
+    }
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
 
 // ------------------------------------------------- fused extend, DWA steering (R1)
 
-// valid_state_check for a block-uniform pose by the whole CTA: FP32 screen of
-// all M obstacles, survivors queued in shared memory, exact FP64 tests spread
-// over the threads.  Returns bit0 = collision, bit1 = the decision is within
-// 1e-6 of the 0.05 threshold (reported, not claimed).
-__device__ int collision_block(const EnvP &e, const ObsSet &os, double x, double y, double th,
-                               int *s_queue /*unused*/, int *s_ctl /*unused*/)
+// valid_state_check for a block-uniform pose by the whole CTA.  The footprint (*gp, shared
+// memory, written by one thread before the preceding barrier) is read by every thread; each
+// thread screens its share of the grid cells around the pose in FP32 and tests its survivors
+// exactly in FP64.  Returns bit0 = collision, bit1 = the decision is within 1e-6 of the 0.05
+// threshold (reported, not claimed).  Ends with block-wide barriers.
+__device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose *gp)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     const float4 *__restrict__ rects = os.rects;
-    RobotPose g;
-    robot_pose_setup(e, x, y, th, g);
+    const RobotPose g = *gp;
+    const double x = g.x, y = g.y;
     float px = (float)x, py = (float)y;
     float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
     float thr2 = thr * thr;
@@ -1229,40 +1278,41 @@ struct ExtResult {
 // step) is called by EVERY thread (uniformly) when a node is emitted at `step`
 // with the node's state in s_state; it returns false to stop the extension
 // (capacity exhausted).  Every thread returns the same result.
-template <class OnNode>
+template <int T, class OnNode>
 __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &x, const ObsSet &os,
-                                      const DwaSmem &sm, double *s_state, double *s_next, double gx,
+                                      const DwaSmem &sm, double *s_state, double gx,
                                       double gy, double *path, int *ctrl_idx, OnNode on_node)
 {
-    const int tid = threadIdx.x;
     ExtResult res;
     res.nn = 0; res.status = CRLK_EXT_TIMEOUT; res.steps = 0; res.flags = 0; res.rolls = 0;
     for (int k = 1; k <= x.n_max_extend; k++) {
-        // rrt.py:116-118: control, then thread 0 advances the state inside the
-        // control block's closing section (no extra barrier round trip)
-        DwaResult r = dwa_control_block(e, d, os, s_state, gx, gy, sm,
-            [&](double cv, double cw, int ix, const double *row1) {
+        // rrt.py:116-118: control, then thread 0 advances the state inside the control block's
+        // closing section: s_state (nobody reads it any more) and the footprint of the new state
+        // for the validity test, both visible after the block's closing barrier
+        DwaResult r = dwa_control_block<T>(e, d, os, s_state, gx, gy, sm,
+            [&](double cv, double cw, int ix, const double *row1, double cs1, double sn1) {
                 double s[5];
                 if (x.n_sub_step == d.n_sub) {
-                    // executing the control for step_dt == dwa.dt IS the winner's trajectory row 1
+                    // executing the control for step_dt == dwa.dt IS the winner's trajectory row 1,
+                    // and cos / sin of its heading are already in the chain tables
                     for (int c = 0; c < 5; c++) s[c] = row1[c];
+                    robot_pose_from_cs(e, s[0], s[1], cs1, sn1, *sm.pose);
                 } else {
                     for (int c = 0; c < 5; c++) s[c] = s_state[c];
                     motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
+                    robot_pose_setup(e, s[0], s[1], s[2], *sm.pose);
                 }
-                for (int c = 0; c < 5; c++) s_next[c] = s[c];
+                for (int c = 0; c < 5; c++) s_state[c] = s[c];
                 if (path)
                     for (int c = 0; c < 5; c++) path[(size_t)(k - 1) * 5 + c] = s[c];
                 if (ctrl_idx) ctrl_idx[k - 1] = ix;
             });
         res.flags |= r.near_tie ? 2 : 0;
         res.rolls += (unsigned long long)r.R;
-        if (tid < 5) s_state[tid] = s_next[tid];
-        __syncthreads();
         res.steps = k;
         // rrt.py:121: valid_state_check on the new state
         PHASE_START();
-        int col = collision_block(e, os, s_state[0], s_state[1], s_state[2], sm.queue, nullptr);
+        int col = collision_block(e, os, sm.pose);
         PHASE_MARK(8);
         if (col & 2) res.flags |= 1;
         col &= 1;
@@ -1282,7 +1332,8 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
     return res;
 }
 
-__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
              const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
              double *path, int *n_steps, int *status, int *node_step, int *n_nodes, int *ctrl_idx,
@@ -1292,7 +1343,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
-    __shared__ double s_state[5], s_next[5];
+    __shared__ double s_state[5];
     __shared__ int s_q;
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
@@ -1314,7 +1365,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
         if (tid < 5) s_state[tid] = from_states[5 * (size_t)q + tid];
         __syncthreads();
         const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
-        ExtResult r = extend_dwa_block(e, d, x, os, sm, s_state, s_next, gx, gy,
+        ExtResult r = extend_dwa_block<T>(e, d, x, os, sm, s_state, gx, gy,
                                        path + (size_t)q * x.n_max_extend * 5,
                                        ctrl_idx ? ctrl_idx + (size_t)q * x.n_max_extend : nullptr,
                                        [&](int kn, int step) {
@@ -1374,18 +1425,21 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
     CRLK_REQUIRE(from_states && targets && path && n_steps && status && node_step && n_nodes,
                  "NULL array");
     size_t smem = crlk_dwa_smem_bytes(d);
-    rc = set_smem_attr((const void *)k_extend_dwa, smem);
+    const bool wide = dwa_use_wide(Q);
+    auto kern = wide ? k_extend_dwa<DWA_WIDE_THREADS, 1> : k_extend_dwa<DWA_THREADS, DWA_MIN_BLOCKS>;
+    const int threads = wide ? DWA_WIDE_THREADS : DWA_THREADS;
+    rc = set_smem_attr((const void *)kern, smem);
     if (rc) return rc;
     int dev = env->device, sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_dwa, DWA_THREADS, smem));
+    CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sms * per_sm;
     if (grid > Q) grid = Q;
     int *counter = nullptr;
     rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
     if (rc) return rc;
-    k_extend_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(
         env->p, d, x, env->os, from_states, targets, Q, path, n_steps, status, node_step,
         n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats);
     CRLK_LAUNCH_CHECK();
@@ -1401,13 +1455,14 @@ struct PlanP {
 
 // RRT.choose_parent (rrt.py:156-161) over one tree by the whole CTA: exact
 // float64 distances, first minimum.  Every thread returns the same (idx, dist).
+template <int T>
 __device__ __forceinline__ void nearest_block(const double *xs, const double *ys, int lo, int n, double tx,
                                               double ty, double *red_v, int *red_i, int &idx, double &dist)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double bd = CUDART_INF;
     int bi = 0x7fffffff;
-    for (int j = lo + tid; j < n; j += DWA_THREADS) {
+    for (int j = lo + tid; j < n; j += T) {
         double dx = xs[j] - tx, dy = ys[j] - ty;
         double dd = sqrt(fma(dy, dy, dx * dx));          // np.linalg.norm of a 2-vector
         if (dd < bd) { bd = dd; bi = j; }
@@ -1418,7 +1473,7 @@ __device__ __forceinline__ void nearest_block(const double *xs, const double *ys
     __syncthreads();
     bd = red_v[0]; bi = red_i[0];
 #pragma unroll
-    for (int w = 1; w < DWA_THREADS / 32; w++) {
+    for (int w = 1; w < T / 32; w++) {
         double ob = red_v[w];
         int oi = red_i[w];
         if (ob < bd || (ob == bd && oi < bi)) { bd = ob; bi = oi; }
@@ -1433,7 +1488,8 @@ __device__ __forceinline__ void nearest_block(const double *xs, const double *ys
 // CTAs pull queries from an atomic counter (queries differ widely in length).
 // The tree is the same SoA forest crlk_rrt_append maintains; sampling stays a
 // pre-drawn per-query stream (the reference's RNG order is host state).
-__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS)
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
            const double *__restrict__ goals, const double *__restrict__ streams, int Q, int *iters_out,
            int *cursor_out, uint8_t *reached_out, uint8_t *flags_out, int *overflow, int *work_counter,
@@ -1442,7 +1498,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
-    __shared__ double s_state[5], s_next[5];
+    __shared__ double s_state[5];
     __shared__ int s_q;
     const int tid = threadIdx.x;
     if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
@@ -1469,7 +1525,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
             __syncthreads();
             double *prow = f.pool ? f.pool + ((size_t)f.pool_cap * q + pool_used) * 5 : nullptr;
             int prev_step = 0;
-            ExtResult r = extend_dwa_block(e, d, x, os, sm, s_state, s_next, tx, ty, prow, nullptr,
+            ExtResult r = extend_dwa_block<T>(e, d, x, os, sm, s_state, tx, ty, prow, nullptr,
                 [&](int kn, int step) {
                     if (n >= f.stride) { over = true; return false; }
                     if (tid < 5) f.states[(tb + n) * 5 + tid] = s_state[tid];
@@ -1502,12 +1558,14 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
             const double *sp = streams + ((size_t)q * pp.S + cur) * 5;
             cur++;
             const double sx = sp[0], sy = sp[1], sth = sp[2];
-            int col = collision_block(e, os, sx, sy, sth, sm.queue, nullptr);         // rrt.py:66
+            if (tid == 0) robot_pose_setup(e, sx, sy, sth, *sm.pose);
+            __syncthreads();
+            int col = collision_block(e, os, sm.pose);                                // rrt.py:66
             if (col & 2) fl |= 1;
             if (col & 1) continue;
             int idx;
             double dist;
-            nearest_block(tx64, ty64, 0, n, sx, sy, sm.red_v, sm.red_i, idx, dist);   // rrt.py:68
+            nearest_block<T>(tx64, ty64, 0, n, sx, sy, sm.red_v, sm.red_i, idx, dist);   // rrt.py:68
             if (!(dist >= pp.d_min && dist < pp.d_max)) continue;                     // rrt.py:69
             iters++;
             const int n0 = n;
@@ -1516,7 +1574,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
                 if (last_at_goal()) { reached = true; break; }                        // rrt.py:75
                 int best;
                 double bd;
-                nearest_block(tx64, ty64, n0, n, gx, gy, sm.red_v, sm.red_i, best, bd);   // rrt.py:78
+                nearest_block<T>(tx64, ty64, n0, n, gx, gy, sm.red_v, sm.red_i, best, bd);   // rrt.py:78
                 if (bd < pp.retry_radius && !over) {
                     steer(best, gx, gy);                                              // rrt.py:80
                     if (last_at_goal()) { reached = true; break; }                    // rrt.py:81
@@ -1565,18 +1623,21 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
     pp.d_min = plan->d_min; pp.d_max = plan->d_max;
     pp.goal_radius = plan->goal_radius; pp.retry_radius = plan->retry_radius;
     size_t smem = crlk_dwa_smem_bytes(d);
-    rc = set_smem_attr((const void *)k_plan_dwa, smem);
+    const bool wide = dwa_use_wide(Q);
+    auto kern = wide ? k_plan_dwa<DWA_WIDE_THREADS, 1> : k_plan_dwa<DWA_THREADS, DWA_MIN_BLOCKS>;
+    const int threads = wide ? DWA_WIDE_THREADS : DWA_THREADS;
+    rc = set_smem_attr((const void *)kern, smem);
     if (rc) return rc;
     int dev = env->device, sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan_dwa, DWA_THREADS, smem));
+    CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sms * per_sm;
     if (grid > Q) grid = Q;
     int *counter = nullptr;
     rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
     if (rc) return rc;
-    k_plan_dwa<<<grid, DWA_THREADS, smem, (cudaStream_t)stream>>>(
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(
         env->p, d, x, env->os, *forest, pp, goals, streams, Q, iters, cursor, reached, flags, overflow,
         counter, (unsigned long long *)stats);
     CRLK_LAUNCH_CHECK();
