@@ -79,6 +79,7 @@ PROTOTYPES = {
     "crlk_estimator_cp_workspace_bytes": (I64, [I32, I32]),
     "crlk_rrt_select": (C.c_int, [P, P, I32, I32, F64, F64, P, P, P, P]),
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
+    "crlk_debug_atan2": (C.c_int, [P, P, I32, P, P]),
     "crlk_gym_step": (C.c_int, [P, P, P, I32, P, F64, P, I32, P, P, P, P, I32, P, P]),
     "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),

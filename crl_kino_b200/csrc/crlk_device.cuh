@@ -85,6 +85,46 @@ __device__ __forceinline__ void motion_velocity_dev(const EnvP &e, double *s, do
     }
 }
 
+// ---------------------------------------------------------------------- atan2
+#include "crlk_atan_table.h"
+
+// 1 / a for a normal, positive a: hardware seed (about 20 bits) + two Newton steps.
+__device__ __forceinline__ double crlk_rcp_pos(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = fma(fma(-a, r, 1.0), r, r);
+    r = fma(fma(-a, r, 1.0), r, r);
+    return r;
+}
+
+// atan2 for the rollout scoring loop (dwa.py:58), about 30 float64 instructions instead of
+// the library's ~65: q = min/max of |y|, |x| by a Newton division with residual correction,
+// then the degree-10 Taylor polynomial of atan about the nearest multiple of 1/16 (`tab`:
+// CRLK_ATAN_NK x (CRLK_ATAN_DEG + 1) coefficients, shared memory), then the octant fix-ups.
+// Worst error 1.5 ulp against a 200-bit reference (tools/gen_atan_table.py; measured on the
+// device by tests/test_gpu_dwa.py) -- the library's bound is 2 ulp, numpy's own SIMD arctan2
+// differs from libm in the last bit for 8 % of inputs.  Zero, tiny, huge and NaN arguments take
+// the library path.
+__device__ __forceinline__ double crlk_atan2(double y, double x, const double *tab)
+{
+    const double ay = fabs(y), ax = fabs(x);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    if (!(mx > 1e-280 && mx < 1e280)) return atan2(y, x);
+    const double r = crlk_rcp_pos(mx);
+    double q = mn * r;
+    q = fma(fma(-mx, q, mn), r, q);
+    const int k = __double2int_rn(q * 16.0);
+    const double t = fma(-(double)k, 0.0625, q);
+    const double *a = tab + k * (CRLK_ATAN_DEG + 1);
+    double p = a[CRLK_ATAN_DEG];
+#pragma unroll
+    for (int n = CRLK_ATAN_DEG - 1; n >= 0; n--) p = fma(p, t, a[n]);
+    if (ay > ax) p = 1.5707963267948966 - p;
+    if (x < 0.0) p = 3.141592653589793 - p;
+    return copysign(p, y);
+}
+
 // ------------------------------------------------------------------ geometry
 
 struct RobotPose {

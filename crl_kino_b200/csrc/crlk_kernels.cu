@@ -615,6 +615,34 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
 #define DWA_WIDE_THREADS 768
 #define PW_BLOCK 128
 
+__device__ __constant__ unsigned long long c_atan_bits[CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1)] = CRLK_ATAN_TAB_INIT;
+
+// copy the atan coefficient table into shared memory (call before the first barrier of the kernel)
+__device__ __forceinline__ void load_atan_table(double *dst)
+{
+    for (int i = threadIdx.x; i < CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1); i += blockDim.x)
+        dst[i] = __longlong_as_double((long long)c_atan_bits[i]);
+}
+
+__global__ void k_debug_atan2(const double *__restrict__ y, const double *__restrict__ x, int n, double *out)
+{
+    __shared__ double tab[CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1)];
+    load_atan_table(tab);
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = crlk_atan2(y[i], x[i], tab);
+}
+
+// Test hook: the rollout loop's atan2 over n argument pairs (dev f64[n] each).
+extern "C" int crlk_debug_atan2(const double *y, const double *x, int32_t n, double *out, void *stream)
+{
+    CRLK_REQUIRE(n >= 0 && (n == 0 || (y && x && out)), "NULL array");
+    if (n == 0) return CRLK_OK;
+    k_debug_atan2<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, x, n, out);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
 struct DwaSmem {
     double *c0, *c1;
     double *vtab, *vlast, *c2n;
@@ -630,6 +658,7 @@ struct DwaSmem {
     double *hdr;                      // [8]  v_hi v_lo w_hi w_lo of the current window
     int *ihdr;                        // [4]  nv nw
     RobotPose *pose;                  // footprint of the state the next validity test looks at
+    double *atab;                     // atan coefficient table (crlk_atan2)
     double *scal;                     // [16]
     int *iscal;                       // [8]: 0 n_leaves, 1 opt idx, 2 near tie, 3 cached R, 4 n_levels, 5 n_nodes
     int *queue;                       // [1024] scratch for the collision survivor list
@@ -672,6 +701,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_hd = take(sizeof(double) * 8);
     size_t o_ih = take(sizeof(int) * 4);
     size_t o_po = take(sizeof(RobotPose));
+    size_t o_at = take(sizeof(double) * CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1));
     size_t o_sc = take(sizeof(double) * 16);
     size_t o_is = take(sizeof(int) * 8);
     size_t o_q = take(sizeof(int) * 1024);
@@ -689,6 +719,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->red_i = (int *)(base + o_ri);
         s->red2_v = (double *)(base + o_r2); s->hdr = (double *)(base + o_hd);
         s->ihdr = (int *)(base + o_ih); s->pose = (RobotPose *)(base + o_po);
+        s->atab = (double *)(base + o_at);
         s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
         s->queue = (int *)(base + o_q);
         s->spos = spos; s->rmax = rmax; s->nmax = nmax;
@@ -908,7 +939,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             x = x + vt[k] * wc[k] * dt;
             y = y + vt[k] * ws[k] * dt;
         }
-        double ang = atan2(gy - y, gx - x);
+        double ang = crlk_atan2(gy - y, gx - x, sm.atab);
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
         return pymin(c0, CRLK_TWO_PI - c0);
     };
@@ -1142,6 +1173,7 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5];
     if (threadIdx.x == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
+    load_atan_table(sm.atab);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
@@ -1170,13 +1202,14 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
     }
 }
 
-// Launch-shape choice: with fewer work items than ~2 throughput-shaped waves (148 SMs x 3 CTAs)
-// the launch is bound by its longest dependent chain, not by total work.  CRLK_DWA_WIDE=0/1 forces.
+// Launch-shape choice.  Measured on B200 (profiles/r1g_phases_wide.txt): the wide shape halves the
+// rollout phase but every other phase of a control step gets slower, so it only wins when there
+// are fewer work items than SMs; CRLK_DWA_WIDE=0/1 forces a shape.
 static bool dwa_use_wide(int n_items)
 {
     static const char *env = getenv("CRLK_DWA_WIDE");
     if (env) return atoi(env) != 0;
-    return n_items <= 2 * 148 * DWA_MIN_BLOCKS * 2;
+    return n_items <= 148;
 }
 
 static int set_smem_attr(const void *fn, size_t bytes)
@@ -1348,6 +1381,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
     if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
+    load_atan_table(sm.atab);
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
         __syncthreads();
@@ -1502,6 +1536,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
     __shared__ int s_q;
     const int tid = threadIdx.x;
     if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
+    load_atan_table(sm.atab);
     for (;;) {
         __syncthreads();
         if (tid == 0) s_q = atomicAdd(work_counter, 1);

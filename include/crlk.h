@@ -298,6 +298,10 @@ int crlk_gym_step(const CrlkEnv *env, double *states, const double *goals, int32
                   double *info, double *reward, double *obs64, float *obs32, int32_t ld32,
                   uint8_t *near_boundary, void *stream);
 
+/* Test hook: the atan2 of the rollout scoring loop (dwa.py:58 `np.arctan2`), evaluated for n
+ * argument pairs; y, x, out dev f64[n].  The kernels use a table-driven atan2 (<= 1.5 ulp). */
+int crlk_debug_atan2(const double *y, const double *x, int32_t n, double *out, void *stream);
+
 /* ---- whole-query planning on the device: RRT.planning (planner/rrt.py:51-89), DWA steering ---- */
 
 typedef struct {

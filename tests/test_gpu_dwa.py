@@ -92,3 +92,35 @@ def test_dwa_clearance_vs_oracle_dense_map():
     bad = (np_(r["opt_idx"]) != ref["opt_idx"]) & ~tie
     assert not bad.any()
     np.testing.assert_allclose(np_(r["opt_cost"])[~tie], ref["opt_cost"][~tie], rtol=1e-8)
+
+
+def test_rollout_atan2_accuracy():
+    """The table-driven atan2 of the rollout loop (crlk_atan2) against numpy's arctan2 (the
+    reference's, dwa.py:58) in units in the last place, over the argument ranges the planner
+    produces plus axis / diagonal / tiny / zero cases."""
+    import ctypes as C
+    import torch
+    from crl_kino_b200._lib import check, lib
+    rng = np.random.default_rng(0)
+    n = 400000
+    y = rng.uniform(-45, 45, n)
+    x = rng.uniform(-45, 45, n)
+    y[:50000] = rng.uniform(-1e-4, 1e-4, 50000)                 # nearly along the x axis
+    x[50000:100000] = rng.uniform(-1e-7, 1e-7, 50000)           # nearly along the y axis
+    k = rng.integers(0, 17, 50000)
+    y[100000:150000] = x[100000:150000] * (k / 16.0) * rng.choice([-1, 1], 50000)   # interval boundaries
+    special = np.array([[0.0, 1.0], [0.0, -1.0], [1.0, 0.0], [-1.0, 0.0], [0.0, 0.0], [-0.0, 1.0], [1e-300, 1e-300],
+                        [3.0, 3.0], [-3.0, 3.0], [3.0, -3.0], [-3.0, -3.0], [1e-310, 1.0], [5.0, 1e300]])
+    y[:len(special)] = special[:, 0]
+    x[:len(special)] = special[:, 1]
+    dy, dx = torch.as_tensor(y).cuda(), torch.as_tensor(x).cuda()
+    out = torch.empty_like(dy)
+    check(lib().crlk_debug_atan2(C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()), n,
+                                 C.c_void_p(out.data_ptr()), None))
+    got = out.cpu().numpy()
+    ref = np.arctan2(y, x)
+    ulp = np.spacing(np.abs(ref))
+    err = np.abs(got - ref) / np.where(ulp > 0, ulp, 1.0)
+    assert np.all(np.signbit(got) == np.signbit(ref))
+    assert err.max() <= 3.0, f"worst error {err.max()} ulp at y={y[err.argmax()]}, x={x[err.argmax()]}"
+    assert np.mean(err <= 1.0) > 0.95
