@@ -106,11 +106,13 @@ __device__ __forceinline__ double crlk_rcp_pos(double a)
 // device by tests/test_gpu_dwa.py) -- the library's bound is 2 ulp, numpy's own SIMD arctan2
 // differs from libm in the last bit for 8 % of inputs.  Zero, tiny, huge and NaN arguments take
 // the library path.
+static __device__ __noinline__ double crlk_atan2_special(double y, double x) { return atan2(y, x); }
+
 __device__ __forceinline__ double crlk_atan2(double y, double x, const double *tab)
 {
     const double ay = fabs(y), ax = fabs(x);
     const double mx = fmax(ax, ay), mn = fmin(ax, ay);
-    if (!(mx > 1e-280 && mx < 1e280)) return atan2(y, x);
+    if (!(mx > 1e-280 && mx < 1e280)) return crlk_atan2_special(y, x);
     const double r = crlk_rcp_pos(mx);
     double q = mn * r;
     q = fma(fma(-mx, q, mn), r, q);
@@ -396,26 +398,4 @@ __device__ __forceinline__ void warp_argmin(double &v, int &i)
         int oi = __shfl_xor_sync(0xffffffffu, i, o);
         if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
     }
-}
-
-// numpy pairwise summation (umath DOUBLE_pairwise_sum) leaf: n <= 128.
-template <class F>
-__device__ __forceinline__ double np_leaf_sum(F f, int off, int n)
-{
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; i++) res += f(off + i);
-        return res;
-    }
-    double r0 = f(off), r1 = f(off + 1), r2 = f(off + 2), r3 = f(off + 3);
-    double r4 = f(off + 4), r5 = f(off + 5), r6 = f(off + 6), r7 = f(off + 7);
-    int i;
-    int lim = n - (n % 8);
-    for (i = 8; i < lim; i += 8) {
-        r0 += f(off + i);     r1 += f(off + i + 1); r2 += f(off + i + 2); r3 += f(off + i + 3);
-        r4 += f(off + i + 4); r5 += f(off + i + 5); r6 += f(off + i + 6); r7 += f(off + i + 7);
-    }
-    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-    for (; i < n; i++) res += f(off + i);
-    return res;
 }

@@ -647,14 +647,10 @@ struct DwaSmem {
     double *c0, *c1;
     double *vtab, *vlast, *c2n;
     double *wcos, *wsin, *wth, *wom;
-    // numpy pairwise-sum recursion tree over R elements (rebuilt only when R changes)
-    int *nd_off, *nd_len, *nd_left;   // [nmax] element range; first child id (-1 = leaf)
-    int *leaf_ids;                    // [nmax] ids of the leaf nodes
-    double *nd_val;                   // [3][nmax] per-column node sums
-    int *lvl_start;                   // [PW_MAX_LEVELS + 1]
     double *red_v, *red_s;            // [32] screened minimum / runner-up per warp
     int *red_i;                       // [32]
-    double *red2_v;                   // [32] exact minimum per warp
+    double *red2_v;                   // [32] third column-sum partial per warp
+    double *red3_v, *red3_s;          // [32] minimum / runner-up per warp
     double *hdr;                      // [8]  v_hi v_lo w_hi w_lo of the current window
     int *ihdr;                        // [4]  nv nw
     RobotPose *pose;                  // footprint of the state the next validity test looks at
@@ -688,16 +684,11 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_wsin = take(sizeof(double) * d.nw_max * spos);
     size_t o_wth = take(sizeof(double) * d.nw_max * d.n_outer);
     size_t o_wom = take(sizeof(double) * d.nw_max);
-    size_t o_noff = take(sizeof(int) * nmax);
-    size_t o_nlen = take(sizeof(int) * nmax);
-    size_t o_nleft = take(sizeof(int) * nmax);
-    size_t o_lids = take(sizeof(int) * nmax);
-    size_t o_nval = take(sizeof(double) * 3 * nmax);
-    size_t o_lvl = take(sizeof(int) * (PW_MAX_LEVELS + 1));
     size_t o_rv = take(sizeof(double) * 32);
     size_t o_rs = take(sizeof(double) * 32);
     size_t o_ri = take(sizeof(int) * 32);
     size_t o_r2 = take(sizeof(double) * 32);
+    size_t o_r3 = take(sizeof(double) * 64);
     size_t o_hd = take(sizeof(double) * 8);
     size_t o_ih = take(sizeof(int) * 4);
     size_t o_po = take(sizeof(RobotPose));
@@ -712,12 +703,10 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->wcos = (double *)(base + o_wcos); s->wsin = (double *)(base + o_wsin);
         s->wth = (double *)(base + o_wth);
         s->wom = (double *)(base + o_wom);
-        s->nd_off = (int *)(base + o_noff); s->nd_len = (int *)(base + o_nlen);
-        s->nd_left = (int *)(base + o_nleft); s->leaf_ids = (int *)(base + o_lids);
-        s->nd_val = (double *)(base + o_nval); s->lvl_start = (int *)(base + o_lvl);
         s->red_v = (double *)(base + o_rv); s->red_s = (double *)(base + o_rs);
         s->red_i = (int *)(base + o_ri);
         s->red2_v = (double *)(base + o_r2); s->hdr = (double *)(base + o_hd);
+        s->red3_v = (double *)(base + o_r3); s->red3_s = s->red3_v + 32;
         s->ihdr = (int *)(base + o_ih); s->pose = (RobotPose *)(base + o_po);
         s->atab = (double *)(base + o_at);
         s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
@@ -759,77 +748,6 @@ int crlk_make_dwa(const CrlkEnv *env, const CrlkDwaParams *in, DwaP *d)
     return CRLK_OK;
 }
 
-// numpy's pairwise summation (umath DOUBLE_pairwise_sum) splits n > 128 elements
-// into (n2, n - n2), n2 = (n / 2) rounded down to a multiple of 8, and sums
-// blocks of <= 128 with 8 interleaved accumulators.  The recursion tree depends
-// only on n, so one warp builds it breadth-first (children of a node are
-// adjacent, levels are contiguous) and it is cached until n changes.
-__device__ void pw_build_tree_warp(int n, const DwaSmem &sm)
-{
-    const int lane = threadIdx.x & 31;
-    if (lane == 0) { sm.nd_off[0] = 0; sm.nd_len[0] = n; sm.lvl_start[0] = 0; sm.lvl_start[1] = 1; }
-    __syncwarp();
-    int s = 0, e = 1, depth = 0, n_leaves = 0;
-    for (;;) {
-        int next = e;
-        for (int base = s; base < e; base += 32) {
-            int node = base + lane;
-            int len = (node < e) ? sm.nd_len[node] : 0;
-            bool split = len > PW_BLOCK;
-            bool leaf = (node < e) && !split;
-            unsigned ms = __ballot_sync(0xffffffffu, split);
-            unsigned ml = __ballot_sync(0xffffffffu, leaf);
-            unsigned lt = (1u << lane) - 1u;
-            if (split) {
-                int pos = next + 2 * __popc(ms & lt);
-                int off = sm.nd_off[node];
-                int n2 = len / 2;
-                n2 -= n2 % 8;
-                sm.nd_left[node] = pos;
-                sm.nd_off[pos] = off;          sm.nd_len[pos] = n2;
-                sm.nd_off[pos + 1] = off + n2; sm.nd_len[pos + 1] = len - n2;
-            } else if (leaf) {
-                sm.nd_left[node] = -1;
-                sm.leaf_ids[n_leaves + __popc(ml & lt)] = node;
-            }
-            next += 2 * __popc(ms);
-            n_leaves += __popc(ml);
-        }
-        __syncwarp();
-        depth++;
-        if (next == e || depth >= PW_MAX_LEVELS) break;
-        s = e; e = next;
-        if (lane == 0) sm.lvl_start[depth + 1] = e;
-        __syncwarp();
-    }
-    if (lane == 0) { sm.iscal[0] = n_leaves; sm.iscal[3] = n; sm.iscal[4] = depth; sm.iscal[5] = e; }
-}
-
-// One <= 128-element block by 8 cooperating lanes (sub = lane & 7): lane k owns
-// accumulator r[k]; the combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and the
-// sequential remainder follow numpy's order exactly.  Result valid where sub == 0.
-template <class F>
-__device__ __forceinline__ double np_leaf_sum8(F f, int off, int n, int sub)
-{
-    double res;
-    if (n < 8) {
-        res = 0.0;
-        if (sub == 0)
-            for (int i = 0; i < n; i++) res += f(off + i);
-        return res;
-    }
-    const int lim = n - (n % 8);
-    double r = f(off + sub);
-    for (int i = 8 + sub; i < lim; i += 8) r += f(off + i);
-    const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);   // the 8 cooperating lanes
-    double t1 = r + __shfl_down_sync(gm, r, 1, 8);
-    double t2 = t1 + __shfl_down_sync(gm, t1, 2, 8);
-    res = t2 + __shfl_down_sync(gm, t2, 4, 8);
-    if (sub == 0)
-        for (int i = lim; i < n; i++) res += f(off + i);
-    return res;
-}
-
 #ifdef CRLK_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[16];
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
@@ -846,7 +764,8 @@ extern "C" int crlk_debug_phase_cycles(unsigned long long *out16, int reset)
 #endif
 
 struct DwaResult {
-    double v, w, cost;
+    double v, w;
+    double S0, S1, S2, v_hi;   // column sums and window top: what the reported cost is made of
     int idx, R;
     int near_tie;
 };
@@ -860,7 +779,17 @@ __device__ __forceinline__ double clearance_thread(const EnvP &e, const ObsSet &
 
 // DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
 // doubles) and the goal must be block-uniform.  Every thread returns the result.
-template <int T, class Epi>
+// Executed control steps whose duration differs from the DWA's dt (never in the planners, which
+// use 0.2 s for both): the general path, kept out of line so it does not bloat the hot kernels.
+static __device__ __noinline__ void advance_state_general(const EnvP &e, const double *from, double cv, double cw,
+                                                          int n_sub_step, double *s, RobotPose *pose)
+{
+    for (int c = 0; c < 5; c++) s[c] = from[c];
+    motion_velocity_dev(e, s, cv, cw, n_sub_step);
+    robot_pose_setup(e, s[0], s[1], s[2], *pose);
+}
+
+template <int T, bool CLR, class Epi>
 __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSet &os,
                                        const double *st, double gx, double gy,
                                        const DwaSmem &sm, Epi epilogue)
@@ -921,14 +850,14 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         if ((ks + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (ks + 1) / d.n_sub - 1] = th;
         if (ks + 1 == d.n_sub) sm.wom[j] = cur;      // omega after the first dt step
     }
-    if (warp == 3 && sm.iscal[3] != R) pw_build_tree_warp(R, sm);   // warps 3-4 have no chain work
     // clearance of the shared first row (dwa.py:65-67, i = 0)
     double clr0 = CRLK_CLEARANCE_CAP;
-    if (d.use_clearance) clr0 = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
+    if (CLR) clr0 = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
     __syncthreads();
     PHASE_MARK(1);
 
-    // rollouts: heading cost from trajectory row 1 (dwa.py:58-62)
+    // rollouts: heading cost from trajectory row 1 (dwa.py:58-62); every thread also keeps the
+    // running sums of its cost columns (dwa.py:76-78 divides each column by its sum)
     const int di = T / nw, dj = T - di * nw;     // r += T  <=>  (i, j) += (di, dj) with carry
     int ri = tid / nw, rj = tid - ri * nw;
     auto heading_cost = [&](int i, int j, double &x, double &y) {
@@ -943,7 +872,8 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
         return pymin(c0, CRLK_TWO_PI - c0);
     };
-    if (!d.use_clearance) {
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    if (!CLR) {
         // two independent rollouts per iteration: the FP64 dependency chains overlap
         int r = tid;
         for (; r + T < R; r += 2 * T) {
@@ -958,10 +888,14 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             double cb = heading_cost(i1, j1, xb, yb);
             sm.c0[r] = ca;
             sm.c0[r + T] = cb;
+            acc0 += ca;
+            acc0 += cb;
         }
         if (r < R) {
             double xa, ya;
-            sm.c0[r] = heading_cost(ri, rj, xa, ya);
+            double ca = heading_cost(ri, rj, xa, ya);
+            sm.c0[r] = ca;
+            acc0 += ca;
         }
     } else {
         for (int r = tid; r < R; r += T) {
@@ -969,7 +903,9 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             ri += di; rj += dj;
             if (rj >= nw) { rj -= nw; ri++; }
             double x, y;
-            sm.c0[r] = heading_cost(i, j, x, y);
+            double ca = heading_cost(i, j, x, y);
+            sm.c0[r] = ca;
+            acc0 += ca;
             const double *vt = sm.vtab + i * spos;
             const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
             double min_dis = pymin(clr0, 100.0);
@@ -985,158 +921,105 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                     min_dis = pymin(dis, min_dis);
                 }
             }
-            sm.c1[r] = 1.0 / min_dis;
+            double cc = 1.0 / min_dis;
+            sm.c1[r] = cc;
+            acc1 += cc;
         }
     }
+    // speed column (dwa.py:72): v_hi - v_last depends on the v command only and repeats nw times
+    for (int i = tid; i < nv; i += T) acc2 += (double)nw * (v_hi - sm.vlast[i]);
+    // Column sums.  numpy adds each column in its pairwise order; here every thread adds its own
+    // terms, then warps and the block combine them -- a different association, so a sum may differ
+    // from numpy's in the last bits (relative 1e-15).  That can only reorder two rollouts whose
+    // costs already agree to ~1e-15, far inside the 1e-9 band the near-tie flag reports.
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+        if (CLR) acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    }
+    if (lane == 0) { sm.red_v[warp] = acc0; sm.red_s[warp] = acc2; sm.red2_v[warp] = acc1; }
     __syncthreads();
     PHASE_MARK(2);
-
-    // column sums in numpy's pairwise order (dwa.py:76-78): every leaf block of
-    // every column by 8 lanes, then the tree levels bottom-up (one warp per column)
-    {
-        const int L = sm.iscal[0];
-        const int sub = tid & 7;
-        const double *c0 = sm.c0, *c1 = sm.c1, *vl = sm.vlast;
-        // q / nw for q < 2^14, nw < 2^7 as one multiply-high
-        const unsigned magic = 0xffffffffu / (unsigned)nw + 1u;
-        // the constant obstacle column (dwa.py:64-69 disabled) sums to a function of R alone
-        const bool skip_c1 = !d.use_clearance && sm.iscal[6] == R;
-        const int ncol = skip_c1 ? 2 : 3;
-        for (int task = tid >> 3; task < ncol * L; task += T >> 3) {
-            int col = task / L, node = sm.leaf_ids[task - col * L];
-            if (skip_c1 && col == 1) col = 2;
-            int off = sm.nd_off[node], n = sm.nd_len[node];
-            double sres;
-            if (col == 0) {
-                sres = np_leaf_sum8([&](int q) { return c0[q]; }, off, n, sub);
-            } else if (col == 1) {
-                if (d.use_clearance) sres = np_leaf_sum8([&](int q) { return c1[q]; }, off, n, sub);
-                else sres = np_leaf_sum8([&](int) { return 1.0 / 100.0; }, off, n, sub);
-            } else {
-                sres = np_leaf_sum8([&](int q) { return v_hi - vl[__umulhi((unsigned)q, magic)]; }, off, n, sub);
-            }
-            if (sub == 0) sm.nd_val[col * sm.nmax + node] = sres;
-        }
-        __syncthreads();
-        PHASE_MARK(3);
-        if (warp < 3) {
-            double *val = sm.nd_val + warp * sm.nmax;
-            for (int lv = sm.iscal[4] - 1; lv >= 0; lv--) {
-                int e = sm.lvl_start[lv + 1];
-                for (int node = sm.lvl_start[lv] + lane; node < e; node += 32) {
-                    int l = sm.nd_left[node];
-                    if (l >= 0) val[node] = val[l] + val[l + 1];
-                }
-                __syncwarp();
-            }
-            if (lane == 0) {
-                if (warp == 1 && !d.use_clearance) {
-                    if (sm.iscal[6] == R) sm.scal[1] = sm.scal[9];           // cached
-                    else { sm.scal[1] = val[0]; sm.scal[9] = val[0]; sm.iscal[7] = R; }
-                } else {
-                    sm.scal[warp] = val[0];
-                }
-            }
-        }
+    double S0 = (lane < T / 32) ? sm.red_v[lane] : 0.0;
+    double S2 = (lane < T / 32) ? sm.red_s[lane] : 0.0;
+    double S1 = (CLR && lane < T / 32) ? sm.red2_v[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        S0 += __shfl_xor_sync(0xffffffffu, S0, o);
+        S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+        if (CLR) S1 += __shfl_xor_sync(0xffffffffu, S1, o);
     }
-    __syncthreads();
-    PHASE_MARK(4);
-    if (tid == 0 && !d.use_clearance) sm.iscal[6] = sm.iscal[7];
-    const double S0 = sm.scal[0], S1 = sm.scal[1], S2 = sm.scal[2];
-    // weighted sum and first argmin (dwa.py:79-82).  Screen: the normalising
-    // divisions replaced by reciprocal multiplies (a few ulp off); every rollout
-    // within 1e-12 relative of the screened minimum is then re-scored with the
-    // reference's exact operations, so the winner is the exact first minimum.
+    if (!CLR) S1 = (double)R * (1.0 / 100.0);        // the constant obstacle column (dwa.py:64-69 disabled)
+    // weighted sum and first argmin (dwa.py:79-82), one pass: the normalising divisions become
+    // reciprocal multiplies (a few ulp off the reference's quotients, again only visible to costs
+    // that agree to ~1e-15); equal inputs give equal costs, so exact ties keep the first index.
     const double inv0 = (S0 != 0.0) ? 1.0 / S0 : 1.0;
     const double inv1 = (S1 != 0.0) ? 1.0 / S1 : 1.0;
     const double inv2 = (S2 != 0.0) ? 1.0 / S2 : 1.0;
     const double c1n_const = (S1 != 0.0) ? (1.0 / 100.0) / S1 : (1.0 / 100.0);
-    auto approx_cost = [&](int r, int i) {
-        double c1a = d.use_clearance ? sm.c1[r] * inv1 : c1n_const;
+    auto cost_of = [&](int r, int i) {
+        double c1a = CLR ? sm.c1[r] * inv1 : c1n_const;
         return d.g_goal * (sm.c0[r] * inv0) + d.g_ob * c1a + d.g_speed * ((v_hi - sm.vlast[i]) * inv2);
     };
-    auto exact_cost = [&](int r, int i) {
-        double c0n = (S0 != 0.0) ? sm.c0[r] / S0 : sm.c0[r];
-        double c1n = c1n_const;
-        if (d.use_clearance) c1n = (S1 != 0.0) ? sm.c1[r] / S1 : sm.c1[r];
-        double c2 = v_hi - sm.vlast[i];
-        double c2n = (S2 != 0.0) ? c2 / S2 : c2;
-        return d.g_goal * c0n + d.g_ob * c1n + d.g_speed * c2n;
-    };
-    double abest = CUDART_INF, asecond = CUDART_INF;
-    int abi = 0x7fffffff, abv = 0;
+    double best = CUDART_INF, second = CUDART_INF;
+    int bi = 0x7fffffff;            // bits 0-15 rollout index, bits 16-30 its v index (saves an integer division)
     ri = tid / nw; rj = tid - ri * nw;
     for (int r = tid; r < R; r += T) {
         const int i = ri;
         ri += di; rj += dj;
         if (rj >= nw) { rj -= nw; ri++; }
-        double c = approx_cost(r, i);
-        if (c < abest) { asecond = abest; abest = c; abi = r; abv = i; }
-        else if (c < asecond) asecond = c;
+        double c = cost_of(r, i);
+        if (c < best) { second = best; best = c; bi = r | (i << 16); }       // r ascends: the first minimum stays
+        else if (c < second) second = c;
     }
-    {   // block minimum of the screened costs and the runner-up (near_tie report)
-        double wb = abest, ws2 = asecond;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, wb, o);
-            double os = __shfl_xor_sync(0xffffffffu, ws2, o);
-            ws2 = fmin(fmin(ws2, os), fmax(wb, ob));
-            wb = fmin(wb, ob);
-        }
-        if (lane == 0) { sm.red_v[warp] = wb; sm.red_s[warp] = ws2; }
-    }
-    __syncthreads();
-    PHASE_MARK(5);
-    // block minimum and runner-up from the per-warp pairs: every warp reduces them with shuffles
-    double m_a = (lane < T / 32) ? sm.red_v[lane] : CUDART_INF;
-    double s_a = (lane < T / 32) ? sm.red_s[lane] : CUDART_INF;
+    // (minimum, its first index, runner-up) across the warp, then across the block by warp 0
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, m_a, o);
-        double os2 = __shfl_xor_sync(0xffffffffu, s_a, o);
-        s_a = fmin(fmin(s_a, os2), fmax(m_a, ob));
-        m_a = fmin(m_a, ob);
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        double os2 = __shfl_xor_sync(0xffffffffu, second, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        second = fmin(fmin(second, os2), fmax(best, ob));
+        if (ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff))) { best = ob; bi = oi; }
     }
-    const double lim = m_a + fabs(m_a) * 1e-12;
-    double best = CUDART_INF;
-    int bi = 0x7fffffff;
-    if (abest <= lim) {
-        if (asecond <= lim) {           // several candidates in this thread: rescan them all
-            ri = tid / nw; rj = tid - ri * nw;
-            for (int r = tid; r < R; r += T) {
-                const int i = ri;
-                ri += di; rj += dj;
-                if (rj >= nw) { rj -= nw; ri++; }
-                if (approx_cost(r, i) <= lim) {
-                    double c = exact_cost(r, i);
-                    if (c < best) { best = c; bi = r; }
-                }
+    if (lane == 0) { sm.red3_v[warp] = best; sm.red3_s[warp] = second; sm.red_i[warp] = bi; }
+    __syncthreads();
+    PHASE_MARK(5);
+    if (T / 32 <= 8) {
+        // few warps: thread 0 walks the per-warp results itself (measured faster than a shuffle tree here)
+        if (tid == 0) {
+            best = sm.red3_v[0]; second = sm.red3_s[0]; bi = sm.red_i[0];
+#pragma unroll
+            for (int w = 1; w < T / 32; w++) {
+                double ob = sm.red3_v[w], os2 = sm.red3_s[w];
+                int oi = sm.red_i[w];
+                second = fmin(fmin(second, os2), fmax(best, ob));
+                if (ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff))) { best = ob; bi = oi; }
             }
-        } else {
-            best = exact_cost(abi, abv);
-            bi = abi;
+        }
+    } else if (warp == 0) {
+        best = (lane < T / 32) ? sm.red3_v[lane] : CUDART_INF;
+        second = (lane < T / 32) ? sm.red3_s[lane] : CUDART_INF;
+        bi = (lane < T / 32) ? sm.red_i[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            double os2 = __shfl_xor_sync(0xffffffffu, second, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            second = fmin(fmin(second, os2), fmax(best, ob));
+            if (ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff))) { best = ob; bi = oi; }
         }
     }
-    warp_argmin(best, bi);
-    if (lane == 0) { sm.red2_v[warp] = best; sm.red_i[warp] = bi; }
-    __syncthreads();
-    PHASE_MARK(6);
-    if (warp == 0) {
-        double b = (lane < T / 32) ? sm.red2_v[lane] : CUDART_INF;
-        int ix = (lane < T / 32) ? sm.red_i[lane] : 0x7fffffff;
-        warp_argmin(b, ix);
-        best = b; bi = ix;
-    }
+    PHASE_MARK(3);
     if (tid == 0) {
-        double b = best;
-        int ix = bi;
-        int i = ix / nw, j = ix - i * nw;
+        const int ix = bi & 0xffff;
+        const int i = bi >> 16, j = ix - i * nw;
         sm.scal[4] = arange_at(v_lo, v1, vd, i);
         sm.scal[5] = arange_at(w_lo, w1, wd, j);
-        sm.scal[6] = b;
         sm.iscal[1] = ix;
-        double gap = s_a - m_a;
-        sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(m_a)) ? 1 : 0;
+        double gap = second - best;
+        sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(best)) ? 1 : 0;
+        PHASE_MARK(4);
         // trajectory row 1 of the winner (= motion_velocity(state, opt_v, d.dt), same operations)
         double row1[5];
         {
@@ -1150,18 +1033,21 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             row1[0] = x; row1[1] = y; row1[2] = sm.wth[j * d.n_outer];
             row1[3] = vt[d.n_sub - 1]; row1[4] = sm.wom[j];
         }
+        PHASE_MARK(6);
         // thread 0 only, before the closing barrier; also gets cos / sin of row 1's heading
         epilogue(sm.scal[4], sm.scal[5], ix, row1, sm.wcos[j * spos + d.n_sub - 1], sm.wsin[j * spos + d.n_sub - 1]);
     }
+    PHASE_MARK(9);
     __syncthreads();
     PHASE_MARK(7);
     DwaResult res;
-    res.v = sm.scal[4]; res.w = sm.scal[5]; res.cost = sm.scal[6];
+    res.v = sm.scal[4]; res.w = sm.scal[5];
+    res.S0 = S0; res.S1 = S1; res.S2 = S2; res.v_hi = v_hi;
     res.idx = sm.iscal[1]; res.near_tie = sm.iscal[2]; res.R = R;
     return res;
 }
 
-template <int T, int MINB>
+template <int T, int MINB, bool CLR>
 __global__ void __launch_bounds__(T, MINB)
 k_dwa_control(EnvP e, DwaP d, ObsSet os,
               const double *__restrict__ states, const double *__restrict__ goals, int goal_stride,
@@ -1172,20 +1058,29 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5];
-    if (threadIdx.x == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
     load_atan_table(sm.atab);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
         __syncthreads();
         double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
-        DwaResult r = dwa_control_block<T>(e, d, os, s_state, gx, gy, sm,
-                                           [](double, double, int, const double *, double, double) {});
+        DwaResult r = dwa_control_block<T, CLR>(e, d, os, s_state, gx, gy, sm,
+                                                [](double, double, int, const double *, double, double) {});
         if (threadIdx.x == 0) {
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
             if (opt_idx) opt_idx[b] = r.idx;
-            if (opt_cost) opt_cost[b] = r.cost;
+            if (opt_cost) {
+                // the winner's cost with the reference's divisions (dwa.py:76-81)
+                const int nw = (r.R > 0 && sm.ihdr[1] > 0) ? sm.ihdr[1] : 1;
+                const int i = r.idx / nw;
+                double c0n = (r.S0 != 0.0) ? sm.c0[r.idx] / r.S0 : sm.c0[r.idx];
+                double c1 = CLR ? sm.c1[r.idx] : 1.0 / 100.0;
+                double c1n = (r.S1 != 0.0) ? c1 / r.S1 : c1;
+                double c2 = r.v_hi - sm.vlast[i];
+                double c2n = (r.S2 != 0.0) ? c2 / r.S2 : c2;
+                opt_cost[b] = d.g_goal * c0n + d.g_ob * c1n + d.g_speed * c2n;
+            }
             if (n_rollouts) n_rollouts[b] = r.R;
             if (near_tie) near_tie[b] = (uint8_t)r.near_tie;
             if (opt_traj) {   // dwa.py:35-43 for the winner
@@ -1247,19 +1142,13 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
     CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
     if (B == 0) return CRLK_OK;
     size_t smem = crlk_dwa_smem_bytes(d);
-    if (dwa_use_wide(B)) {
-        rc = set_smem_attr((const void *)k_dwa_control<DWA_WIDE_THREADS, 1>, smem);
-        if (rc) return rc;
-        k_dwa_control<DWA_WIDE_THREADS, 1><<<B, DWA_WIDE_THREADS, smem, (cudaStream_t)stream>>>(
-            env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
-            opt_traj, n_rollouts, near_tie);
-    } else {
-        rc = set_smem_attr((const void *)k_dwa_control<DWA_THREADS, DWA_MIN_BLOCKS>, smem);
-        if (rc) return rc;
-        k_dwa_control<DWA_THREADS, DWA_MIN_BLOCKS><<<B, DWA_THREADS, smem, (cudaStream_t)stream>>>(
-            env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost,
-            opt_traj, n_rollouts, near_tie);
-    }
+    const bool wide = dwa_use_wide(B);
+    auto kern = d.use_clearance ? (wide ? k_dwa_control<DWA_WIDE_THREADS, 1, true> : k_dwa_control<DWA_THREADS, DWA_MIN_BLOCKS, true>)
+                                : (wide ? k_dwa_control<DWA_WIDE_THREADS, 1, false> : k_dwa_control<DWA_THREADS, DWA_MIN_BLOCKS, false>);
+    rc = set_smem_attr((const void *)kern, smem);
+    if (rc) return rc;
+    kern<<<B, wide ? DWA_WIDE_THREADS : DWA_THREADS, smem, (cudaStream_t)stream>>>(
+        env->p, d, env->os, states, goals, goal_stride, B, opt_v, opt_idx, opt_cost, opt_traj, n_rollouts, near_tie);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -1311,7 +1200,7 @@ struct ExtResult {
 // step) is called by EVERY thread (uniformly) when a node is emitted at `step`
 // with the node's state in s_state; it returns false to stop the extension
 // (capacity exhausted).  Every thread returns the same result.
-template <int T, class OnNode>
+template <int T, bool CLR, class OnNode>
 __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &x, const ObsSet &os,
                                       const DwaSmem &sm, double *s_state, double gx,
                                       double gy, double *path, int *ctrl_idx, OnNode on_node)
@@ -1322,7 +1211,7 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
         // rrt.py:116-118: control, then thread 0 advances the state inside the control block's
         // closing section: s_state (nobody reads it any more) and the footprint of the new state
         // for the validity test, both visible after the block's closing barrier
-        DwaResult r = dwa_control_block<T>(e, d, os, s_state, gx, gy, sm,
+        DwaResult r = dwa_control_block<T, CLR>(e, d, os, s_state, gx, gy, sm,
             [&](double cv, double cw, int ix, const double *row1, double cs1, double sn1) {
                 double s[5];
                 if (x.n_sub_step == d.n_sub) {
@@ -1331,9 +1220,7 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
                     for (int c = 0; c < 5; c++) s[c] = row1[c];
                     robot_pose_from_cs(e, s[0], s[1], cs1, sn1, *sm.pose);
                 } else {
-                    for (int c = 0; c < 5; c++) s[c] = s_state[c];
-                    motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
-                    robot_pose_setup(e, s[0], s[1], s[2], *sm.pose);
+                    advance_state_general(e, s_state, cv, cw, x.n_sub_step, s, sm.pose);
                 }
                 for (int c = 0; c < 5; c++) s_state[c] = s[c];
                 if (path)
@@ -1365,7 +1252,7 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
     return res;
 }
 
-template <int T, int MINB>
+template <int T, int MINB, bool CLR>
 __global__ void __launch_bounds__(T, MINB)
 k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
              const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
@@ -1380,7 +1267,6 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     __shared__ int s_q;
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
-    if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
     load_atan_table(sm.atab);
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
@@ -1399,7 +1285,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
         if (tid < 5) s_state[tid] = from_states[5 * (size_t)q + tid];
         __syncthreads();
         const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
-        ExtResult r = extend_dwa_block<T>(e, d, x, os, sm, s_state, gx, gy,
+        ExtResult r = extend_dwa_block<T, CLR>(e, d, x, os, sm, s_state, gx, gy,
                                        path + (size_t)q * x.n_max_extend * 5,
                                        ctrl_idx ? ctrl_idx + (size_t)q * x.n_max_extend : nullptr,
                                        [&](int kn, int step) {
@@ -1460,7 +1346,8 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
                  "NULL array");
     size_t smem = crlk_dwa_smem_bytes(d);
     const bool wide = dwa_use_wide(Q);
-    auto kern = wide ? k_extend_dwa<DWA_WIDE_THREADS, 1> : k_extend_dwa<DWA_THREADS, DWA_MIN_BLOCKS>;
+    auto kern = d.use_clearance ? (wide ? k_extend_dwa<DWA_WIDE_THREADS, 1, true> : k_extend_dwa<DWA_THREADS, DWA_MIN_BLOCKS, true>)
+                                : (wide ? k_extend_dwa<DWA_WIDE_THREADS, 1, false> : k_extend_dwa<DWA_THREADS, DWA_MIN_BLOCKS, false>);
     const int threads = wide ? DWA_WIDE_THREADS : DWA_THREADS;
     rc = set_smem_attr((const void *)kern, smem);
     if (rc) return rc;
@@ -1522,7 +1409,7 @@ __device__ __forceinline__ void nearest_block(const double *xs, const double *ys
 // CTAs pull queries from an atomic counter (queries differ widely in length).
 // The tree is the same SoA forest crlk_rrt_append maintains; sampling stays a
 // pre-drawn per-query stream (the reference's RNG order is host state).
-template <int T, int MINB>
+template <int T, int MINB, bool CLR>
 __global__ void __launch_bounds__(T, MINB)
 k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
            const double *__restrict__ goals, const double *__restrict__ streams, int Q, int *iters_out,
@@ -1535,7 +1422,6 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
     __shared__ double s_state[5];
     __shared__ int s_q;
     const int tid = threadIdx.x;
-    if (tid == 0) { sm.iscal[3] = -1; sm.iscal[6] = -1; }   // nothing cached yet
     load_atan_table(sm.atab);
     for (;;) {
         __syncthreads();
@@ -1560,7 +1446,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
             __syncthreads();
             double *prow = f.pool ? f.pool + ((size_t)f.pool_cap * q + pool_used) * 5 : nullptr;
             int prev_step = 0;
-            ExtResult r = extend_dwa_block<T>(e, d, x, os, sm, s_state, tx, ty, prow, nullptr,
+            ExtResult r = extend_dwa_block<T, CLR>(e, d, x, os, sm, s_state, tx, ty, prow, nullptr,
                 [&](int kn, int step) {
                     if (n >= f.stride) { over = true; return false; }
                     if (tid < 5) f.states[(tb + n) * 5 + tid] = s_state[tid];
@@ -1659,7 +1545,8 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
     pp.goal_radius = plan->goal_radius; pp.retry_radius = plan->retry_radius;
     size_t smem = crlk_dwa_smem_bytes(d);
     const bool wide = dwa_use_wide(Q);
-    auto kern = wide ? k_plan_dwa<DWA_WIDE_THREADS, 1> : k_plan_dwa<DWA_THREADS, DWA_MIN_BLOCKS>;
+    auto kern = d.use_clearance ? (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, true> : k_plan_dwa<DWA_THREADS, DWA_MIN_BLOCKS, true>)
+                                : (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, false> : k_plan_dwa<DWA_THREADS, DWA_MIN_BLOCKS, false>);
     const int threads = wide ? DWA_WIDE_THREADS : DWA_THREADS;
     rc = set_smem_attr((const void *)kern, smem);
     if (rc) return rc;

@@ -1,5 +1,5 @@
 # A/B of the two DWA launch shapes: parity tests, bench, per-phase cycles.
-for w in 1 0; do
+for w in 0; do
   echo "== WIDE=$w"
   CRLK_DWA_WIDE=$w timeout 600 python -m pytest tests/test_gpu_dwa.py tests/test_gpu_extend.py tests/test_gpu_batched_rrt.py -x -q -m gpu 2>&1 | tail -3
   CRLK_DWA_WIDE=$w timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_wide$w.json 2>gpurun_out/bench_wide$w.err

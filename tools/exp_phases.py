@@ -12,7 +12,7 @@ rng = np.random.default_rng(0)
 clr = lambda c: env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
 cand = free_states(clr, rng, 4000, 2.5); cand[:, 3:] = 0
 tg = cand.copy(); ang = rng.uniform(-np.pi, np.pi, len(cand)); tg[:, 0] += 15*np.cos(ang); tg[:, 1] += 15*np.sin(ang)
-names = ["wait-prev", "tables+tree", "rollouts", "leaf sums", "combine", "approx", "exact", "final+motion", "collision"]
+names = ["wait-prev", "tables", "rollouts+sums", "f:warp0-reduce", "f:cost", "costs+argmin", "f:row1", "f:closing-barrier", "collision", "f:epilogue"]
 raw = ctypes.CDLL(lib()._name)
 for Q in (1, 444, 1776):
     f, g = ops.as_dev(cand[:Q]), ops.as_dev(tg[:Q])
@@ -22,6 +22,6 @@ for Q in (1, 444, 1776):
     out = ops.extend_dwa(env.handle, dp, xp, f, g); torch.cuda.synchronize()
     raw.crlk_debug_phase_cycles(buf, 1)
     steps = int(out["n_steps"].sum().item())
-    tot = sum(buf[:9])
+    tot = sum(buf[:10])
     print(f"Q={Q} control steps={steps} cycles/step={tot/steps:.0f} ({tot/steps/1.965e3:.1f} us)")
     print("   " + "  ".join(f"{n}={buf[i]/steps:.0f}" for i, n in enumerate(names)))
