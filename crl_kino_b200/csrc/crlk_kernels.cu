@@ -1489,18 +1489,24 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
             nearest_block<T>(tx64, ty64, 0, n, sx, sy, sm.red_v, sm.red_i, idx, dist);   // rrt.py:68
             if (!(dist >= pp.d_min && dist < pp.d_max)) continue;                     // rrt.py:69
             iters++;
-            const int n0 = n;
-            steer(idx, sx, sy);                                                       // rrt.py:72
-            if (n > n0) {
-                if (last_at_goal()) { reached = true; break; }                        // rrt.py:75
+            // pass 0: the extension toward the sample (rrt.py:72); pass 1: the retry toward the goal
+            // from the new node nearest to it (rrt.py:78-80).  One call site keeps one copy of the
+            // extension code in the kernel.
+            int from = idx;
+            double tx = sx, ty = sy;
+            for (int pass = 0; pass < 2; pass++) {
+                const int n0 = n;
+                steer(from, tx, ty);
+                if (pass == 0 && n == n0) break;                                      // rrt.py:74
+                if (last_at_goal()) { reached = true; break; }                        // rrt.py:75, :81
+                if (pass == 1) break;
                 int best;
                 double bd;
                 nearest_block<T>(tx64, ty64, n0, n, gx, gy, sm.red_v, sm.red_i, best, bd);   // rrt.py:78
-                if (bd < pp.retry_radius && !over) {
-                    steer(best, gx, gy);                                              // rrt.py:80
-                    if (last_at_goal()) { reached = true; break; }                    // rrt.py:81
-                }
+                if (!(bd < pp.retry_radius) || over) break;                           // rrt.py:79
+                from = best; tx = gx; ty = gy;
             }
+            if (reached) break;
         }
         if (tid == 0) {
             f.n_nodes[q] = n;
