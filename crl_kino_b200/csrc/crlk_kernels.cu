@@ -608,11 +608,21 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
 //   latency:    768 threads, 1 CTA per SM (same 85-register budget) -- few extensions per SM, the
 //               launch time is the longest chain of dependent control steps, so each step gets
 //               three times the threads.
+#ifndef DWA_THREADS
 #define DWA_THREADS 256
+#endif
 #ifndef DWA_MIN_BLOCKS
-#define DWA_MIN_BLOCKS 3
+#define DWA_MIN_BLOCKS 2
 #endif
 #define DWA_WIDE_THREADS 768
+// The whole-query planner kernel interleaves many short serial sections (sample test, tree scan,
+// node append) with the control steps, so it prefers more, smaller CTAs per SM (measured).
+#ifndef PLAN_THREADS
+#define PLAN_THREADS 128
+#endif
+#ifndef PLAN_MIN_BLOCKS
+#define PLAN_MIN_BLOCKS 4
+#endif
 #define PW_BLOCK 128
 
 __device__ __constant__ unsigned long long c_atan_bits[CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1)] = CRLK_ATAN_TAB_INIT;
@@ -1551,9 +1561,9 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
     pp.goal_radius = plan->goal_radius; pp.retry_radius = plan->retry_radius;
     size_t smem = crlk_dwa_smem_bytes(d);
     const bool wide = dwa_use_wide(Q);
-    auto kern = d.use_clearance ? (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, true> : k_plan_dwa<DWA_THREADS, DWA_MIN_BLOCKS, true>)
-                                : (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, false> : k_plan_dwa<DWA_THREADS, DWA_MIN_BLOCKS, false>);
-    const int threads = wide ? DWA_WIDE_THREADS : DWA_THREADS;
+    auto kern = d.use_clearance ? (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, true> : k_plan_dwa<PLAN_THREADS, PLAN_MIN_BLOCKS, true>)
+                                : (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, false> : k_plan_dwa<PLAN_THREADS, PLAN_MIN_BLOCKS, false>);
+    const int threads = wide ? DWA_WIDE_THREADS : PLAN_THREADS;
     rc = set_smem_attr((const void *)kern, smem);
     if (rc) return rc;
     int dev = env->device, sms = 148, per_sm = 1;
