@@ -600,10 +600,20 @@ static size_t rl_carve(const CrlkPolicy *p, int Q, unsigned char *base, RlWs *w)
     return off;
 }
 
+// Large batches are run as two halves on two streams (see crlk_extend_rl).
+static int rl_splits(int Q)
+{
+    static const char *env = getenv("CRLK_RL_SPLIT");
+    if (env) return atoi(env) >= 2 ? 2 : 1;
+    return Q >= 2048 ? 2 : 1;
+}
+
 extern "C" int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q)
 {
     if (!p || Q <= 0) return 0;
-    return (int64_t)rl_carve(p, Q, nullptr, nullptr);
+    int64_t one = (int64_t)rl_carve(p, Q, nullptr, nullptr);
+    int64_t two = 2 * (int64_t)rl_carve(p, (Q + 1) / 2, nullptr, nullptr) + 512;
+    return one > two ? one : two;
 }
 
 // count[] is zeroed before this launch; the active queries become step 1's row list.
@@ -730,6 +740,23 @@ __global__ void k_advance_cursor(int *cursor, const int *__restrict__ n_steps, c
     if (q < Q && (!active || active[q])) cursor[q] += n_steps[q];
 }
 
+struct RlSide { cudaStream_t stream; cudaEvent_t fork, join; };
+static RlSide g_rl_side[64];
+
+// The second stream of the split RL extend and its fork / join events, per device.
+static int rl_side(int device, RlSide **out)
+{
+    CRLK_REQUIRE(device >= 0 && device < 64, "device index");
+    RlSide *s = &g_rl_side[device];
+    if (!s->stream) {
+        CRLK_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CRLK_CUDA(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+        CRLK_CUDA(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
+    }
+    *out = s;
+    return CRLK_OK;
+}
+
 extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
                               const double *from_states, const double *targets, int32_t Q,
                               const float *noise, int32_t noise_rows, int32_t *noise_cursor, float eps,
@@ -750,35 +777,71 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
     CRLK_REQUIRE(!noise || noise_rows >= (noise_cursor ? 1 : x.n_max_extend), "noise_rows too small");
     CRLK_REQUIRE(x.n_max_extend + 2 <= 4096, "n_max_extend too large");
     cudaStream_t st = (cudaStream_t)stream;
-    RlWs w;
-    rl_carve(p, Q, (unsigned char *)workspace, &w);
+    const int per = x.n_max_extend / x.n_tree + 1;
     // Every step runs on the COMPACTED batch of queries that are still extending:
     // k_rl_step appends the survivors to the next step's row list and counts them on the
     // device; the observation, GEMM and head kernels read that count (no host sync) and
     // skip the rows / row tiles past it.
-    CRLK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * (x.n_max_extend + 2), st));
-    k_rl_init<<<(Q + 127) / 128, 128, 0, st>>>(from_states, active, Q, w.state, w.nn, w.list[0], w.count,
-                                              n_steps, status, n_nodes, flags);
-    CRLK_LAUNCH_CHECK();
+    // Large batches are cut into two halves that advance on two streams, launches interleaved
+    // step by step: while one half's GEMMs hold the tensor pipe, the other half's observation /
+    // motion / collision kernels use the rest of the SM.  Queries are independent, so the split
+    // changes no result.
+    const int ns = rl_splits(Q);
+    RlSide *side = nullptr;
+    if (ns == 2) {
+        rc = rl_side(env->device, &side);
+        if (rc) return rc;
+        CRLK_CUDA(cudaEventRecord(side->fork, st));
+        CRLK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    }
+    struct Half { int q0, n; cudaStream_t s; RlWs w; void *planes; int Mpad, Kp; } h[2];
     const bool tc = policy_uses_tc(p);
-    void *planes = nullptr;
-    int Mpad = 0, Kp = 0;
-    if (tc) crlk_tc_input_planes(p->tc, w.mlp, Q, &planes, &Mpad, &Kp);
-    for (int k = 1; k <= x.n_max_extend; k++) {
-        const int *list = w.list[(k - 1) & 1], *cnt = w.count + (k - 1);
-        // observation of the current state (rrt_rl.py:34 / differential_gym.py:141): straight
-        // into the bf16 operand planes of the first layer on the tensor-core path
-        rc = crlk_local_obs_compact(env, w.state, targets, 5, Q, list, cnt, tc ? nullptr : w.obs, 736,
-                                    planes, Mpad, Kp, stream);
-        if (rc) return rc;
-        // action = policy(obs) (rrt_rl.py:41); only the four goal / velocity inputs have low planes
-        rc = policy_forward_impl(p, tc ? nullptr : w.obs, 736, noise, (long long)noise_rows * 2, noise_cursor,
-                                 k - 1, eps, Q, w.act, w.mlp, st, cnt, list, 1);
-        if (rc) return rc;
-        k_rl_step<<<(Q + 7) / 8, 256, 0, st>>>(env->p, x, env->os, targets, w.act, k, Q, list, cnt,
-                                              w.list[k & 1], w.count + k, w.state, w.nn, path, n_steps,
-                                              status, node_step, n_nodes, actions, flags);
+    unsigned char *wsb = (unsigned char *)workspace;
+    for (int i = 0; i < ns; i++) {
+        h[i].q0 = (ns == 1) ? 0 : i * ((Q + 1) / 2);
+        h[i].n = (ns == 1) ? Q : (i == 0 ? (Q + 1) / 2 : Q - (Q + 1) / 2);
+        h[i].s = (i == 0) ? st : side->stream;
+        size_t used = rl_carve(p, h[i].n, wsb, &h[i].w);
+        wsb += (used + 255) & ~(size_t)255;
+        h[i].planes = nullptr; h[i].Mpad = 0; h[i].Kp = 0;
+        if (tc) crlk_tc_input_planes(p->tc, h[i].w.mlp, h[i].n, &h[i].planes, &h[i].Mpad, &h[i].Kp);
+        const int q0 = h[i].q0, n = h[i].n;
+        CRLK_CUDA(cudaMemsetAsync(h[i].w.count, 0, sizeof(int) * (x.n_max_extend + 2), h[i].s));
+        k_rl_init<<<(n + 127) / 128, 128, 0, h[i].s>>>(from_states + 5 * (size_t)q0, active ? active + q0 : nullptr, n,
+                                                      h[i].w.state, h[i].w.nn, h[i].w.list[0], h[i].w.count,
+                                                      n_steps + q0, status + q0, n_nodes + q0,
+                                                      flags ? flags + q0 : nullptr);
         CRLK_LAUNCH_CHECK();
+    }
+    for (int k = 1; k <= x.n_max_extend; k++) {
+        for (int i = 0; i < ns; i++) {
+            const int q0 = h[i].q0, n = h[i].n;
+            RlWs &w = h[i].w;
+            const int *list = w.list[(k - 1) & 1], *cnt = w.count + (k - 1);
+            const double *tg = targets + 5 * (size_t)q0;
+            // observation of the current state (rrt_rl.py:34 / differential_gym.py:141): straight
+            // into the bf16 operand planes of the first layer on the tensor-core path
+            rc = crlk_local_obs_compact(env, w.state, tg, 5, n, list, cnt, tc ? nullptr : w.obs, 736,
+                                        h[i].planes, h[i].Mpad, h[i].Kp, (void *)h[i].s);
+            if (rc) return rc;
+            // action = policy(obs) (rrt_rl.py:41); only the four goal / velocity inputs have low planes
+            rc = policy_forward_impl(p, tc ? nullptr : w.obs, 736,
+                                     noise ? noise + (size_t)q0 * noise_rows * 2 : nullptr,
+                                     (long long)noise_rows * 2, noise_cursor ? noise_cursor + q0 : nullptr,
+                                     k - 1, eps, n, w.act, w.mlp, h[i].s, cnt, list, 1);
+            if (rc) return rc;
+            k_rl_step<<<(n + 7) / 8, 256, 0, h[i].s>>>(env->p, x, env->os, tg, w.act, k, n, list, cnt,
+                                                      w.list[k & 1], w.count + k, w.state, w.nn,
+                                                      path + (size_t)q0 * x.n_max_extend * 5, n_steps + q0,
+                                                      status + q0, node_step + (size_t)q0 * per, n_nodes + q0,
+                                                      actions ? actions + (size_t)q0 * x.n_max_extend * 2 : nullptr,
+                                                      flags ? flags + q0 : nullptr);
+            CRLK_LAUNCH_CHECK();
+        }
+    }
+    if (ns == 2) {
+        CRLK_CUDA(cudaEventRecord(side->join, side->stream));
+        CRLK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     }
     if (noise && noise_cursor) {
         k_advance_cursor<<<(Q + 127) / 128, 128, 0, st>>>(noise_cursor, n_steps, active, Q);

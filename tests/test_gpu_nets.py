@@ -125,3 +125,45 @@ def test_extend_rl_vs_oracle_teacher_forced():
                 assert code == 0
         if np_(out["flags"])[q] == 0:
             assert code == np_(out["status"])[q] or (code == 0 and ns[q] == 50)
+
+
+def test_extend_rl_large_batch_split_is_invisible():
+    """Batches >= 2048 run as two halves on two streams over compacted row lists: every output must
+    be bit-identical to running the same queries in small unsplit chunks (queries are independent),
+    with exploration noise, an active mask and a noise cursor in play."""
+    import torch
+    from crl_kino_b200 import ops
+    from crl_kino_b200.workloads import dense_map, free_states
+    rects = dense_map(n_cells=3000, seed=6)
+    env, o = make_envs(rects)
+    pol = _policy(3)
+    rng = np.random.default_rng(4)
+    Q = 2304 + 37
+    froms = free_states(lambda c: o.valid_state_batch(c)[1], rng, Q, 0.3, moving=True)
+    targets = free_states(lambda c: o.valid_state_batch(c)[1], rng, Q, 0.3)
+    noise = torch.as_tensor(rng.standard_normal((Q, 64, 2)).astype(np.float32)).cuda()
+    active = torch.as_tensor((rng.uniform(size=Q) < 0.9).astype(np.uint8)).cuda()
+    cur0 = torch.as_tensor(rng.integers(0, 10, Q).astype(np.int32)).cuda()
+    xp = ops.extend_params()
+
+    def run(lo, hi):
+        cur = cur0[lo:hi].clone()
+        out = ops.extend_rl(env.handle, pol.actor.handle, xp, froms[lo:hi], targets[lo:hi], noise[lo:hi].contiguous(),
+                            0.05, active=active[lo:hi].contiguous(), want_actions=True, noise_cursor=cur)
+        torch.cuda.synchronize()
+        return {k: np_(v) for k, v in out.items() if k in ("path", "n_steps", "status", "node_step", "n_nodes",
+                                                           "actions", "flags")}, np_(cur)
+    whole, cur_w = run(0, Q)
+    lo = 0
+    for hi in list(range(700, Q, 700)) + [Q]:
+        part, cur_p = run(lo, hi)
+        ns = part["n_steps"]
+        for k in ("n_steps", "status", "n_nodes", "flags"):
+            assert np.array_equal(whole[k][lo:hi], part[k]), k
+        assert np.array_equal(cur_w[lo:hi], cur_p)
+        for q in range(hi - lo):                                  # rows past n_steps are not written
+            assert np.array_equal(whole["path"][lo + q, :ns[q]], part["path"][q, :ns[q]])
+            assert np.array_equal(whole["actions"][lo + q, :ns[q]], part["actions"][q, :ns[q]])
+            assert np.array_equal(whole["node_step"][lo + q, :part["n_nodes"][q]], part["node_step"][q, :part["n_nodes"][q]])
+        lo = hi
+    assert (whole["n_steps"][np_(active) == 0] == 0).all() and whole["n_steps"].max() > 10
