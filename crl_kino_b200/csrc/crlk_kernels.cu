@@ -1325,15 +1325,26 @@ int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x)
     return CRLK_OK;
 }
 
-static int *g_work_counter[64] = {nullptr};
+// Work counters of the persistent kernels: a ring of 4-byte slots per device, one fresh slot per
+// launch (zeroed on the launch's stream), so launches on different streams never share a counter.
+#define WORK_RING 4096
+static int *g_work_ring[64] = {nullptr};
+static unsigned g_work_next[64] = {0};
 
-// A per-device 4-byte counter used by the persistent extend kernels.
 static int get_work_counter(int device, int **out, cudaStream_t stream)
 {
     CRLK_REQUIRE(device >= 0 && device < 64, "device index");
-    if (!g_work_counter[device]) CRLK_CUDA(cudaMalloc(&g_work_counter[device], 256));
-    CRLK_CUDA(cudaMemsetAsync(g_work_counter[device], 0, 256, stream));
-    *out = g_work_counter[device];
+    if (!g_work_ring[device]) {
+        int *p = nullptr;
+        CRLK_CUDA(cudaMalloc(&p, sizeof(int) * WORK_RING));
+        int *expected = nullptr;
+        if (!__atomic_compare_exchange_n(&g_work_ring[device], &expected, p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE))
+            cudaFree(p);                   // another thread installed the ring first
+    }
+    unsigned slot = __atomic_fetch_add(&g_work_next[device], 1u, __ATOMIC_RELAXED) % WORK_RING;
+    int *c = g_work_ring[device] + slot;
+    CRLK_CUDA(cudaMemsetAsync(c, 0, sizeof(int), stream));
+    *out = c;
     return CRLK_OK;
 }
 

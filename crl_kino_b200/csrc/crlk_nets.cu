@@ -740,8 +740,10 @@ __global__ void k_advance_cursor(int *cursor, const int *__restrict__ n_steps, c
     if (q < Q && (!active || active[q])) cursor[q] += n_steps[q];
 }
 
+#include <mutex>
 struct RlSide { cudaStream_t stream; cudaEvent_t fork, join; };
 static RlSide g_rl_side[64];
+static std::mutex g_rl_mutex[64];      // the fork / launch / join sequence of one device is not re-entrant
 
 // The second stream of the split RL extend and its fork / join events, per device.
 static int rl_side(int device, RlSide **out)
@@ -788,7 +790,10 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
     // changes no result.
     const int ns = rl_splits(Q);
     RlSide *side = nullptr;
+    std::unique_lock<std::mutex> guard;
     if (ns == 2) {
+        CRLK_REQUIRE(env->device >= 0 && env->device < 64, "device index");
+        guard = std::unique_lock<std::mutex>(g_rl_mutex[env->device]);
         rc = rl_side(env->device, &side);
         if (rc) return rc;
         CRLK_CUDA(cudaEventRecord(side->fork, st));
