@@ -292,6 +292,53 @@ def mlp_roofline(peaks):
                     "tensor pipe does 6x this work", "policy_samples_per_sec": B / (ms * 1e-3)}
 
 
+def sub_rates(env, dwa, peaks):
+    """SURVEY 8d sub-rates on the cfg4 map, each kernel alone on resident inputs (CUDA events):
+    validity checks, clearances, local observations, estimator / classifier evaluations, DWA control
+    calls (rollouts) per second, with their algorithmic work figures."""
+    import torch
+    from crl_kino_b200 import ops
+    from crl_kino_b200.workloads import random_states
+    rng = np.random.default_rng(17)
+    M = len(env.rects)
+    B = 1 << 17
+    states = ops.as_dev(random_states(rng, B, moving=True))
+    goals = ops.as_dev(random_states(rng, B))
+    out = {}
+    ms = timed(lambda: ops.valid_state(env.handle, states), 10)
+    out["valid_state_checks_per_sec"] = B / (ms * 1e-3)
+    out["pose_obstacle_pairs_per_sec_algorithmic"] = B * M / (ms * 1e-3)      # 860 FP ops each, brute force
+    ms = timed(lambda: ops.valid_state(env.handle, states, want_clearance=True), 10)
+    out["clearances_per_sec"] = B / (ms * 1e-3)
+    Bo = 1 << 14
+    ms = timed(lambda: ops.local_obs(env.handle, states[:Bo], goals[:Bo], want64=False, want32=True), 10)
+    out["local_observations_per_sec"] = Bo / (ms * 1e-3)
+    out["map_point_tests_per_sec_algorithmic"] = Bo * 729.0 * M / (ms * 1e-3)
+    try:
+        from crl_kino_b200.estimator import load_estimator
+        w = np.load(os.path.join(ROOT, "tests", "golden", "estimator_weights.npz"))
+        est, cls = load_estimator({k[4:]: w[k] for k in w.files if k.startswith("est.")},
+                                  {k[4:]: w[k] for k in w.files if k.startswith("cls.")})
+        _, o32, _ = ops.local_obs(env.handle, states[:Bo], goals[:Bo], want64=False, want32=True)
+        ms = timed(lambda: ops.estimator_forward(est.pair.handle, o32), 10)
+        out["estimator_pairs_per_sec"] = Bo / (ms * 1e-3)
+        out["estimator_tflops_algorithmic"] = 2 * 1.158038e6 * Bo / (ms * 1e-3) / 1e12     # 2 nets x 579,019 MAC x 2
+    except Exception as e:                                                     # weights file not present
+        out["estimator"] = f"skipped: {e}"
+    Bd = 4096
+    free = states[:Bd].clone()
+    free[:, 3] = 0.4
+    free[:, 4] = 0.0
+    r = ops.dwa_control(env.handle, dwa.params(), free, goals[:Bd])
+    ms = timed(lambda: ops.dwa_control(env.handle, dwa.params(), free, goals[:Bd]), 5)
+    n_roll = float(r["n_rollouts"].double().sum().item()) if isinstance(r, dict) and "n_rollouts" in r else None
+    out["dwa_controls_per_sec"] = Bd / (ms * 1e-3)
+    if n_roll:
+        out["rollouts_per_sec"] = n_roll / (ms * 1e-3)
+        out["rollout_tflops_algorithmic"] = M_FLOP_ROLLOUT * n_roll / (ms * 1e-3) / 1e12
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -439,6 +486,7 @@ def run_ours(args):
                                                 "identical_results": plan["lockstep_identical"],
                                                 "note": "BatchedRRT: five launches per round, wall clock"}
             line["rooflines_other_kernels"] = [nearest_roofline(peaks), mlp_roofline(peaks)]
+            line["sub_rates"] = sub_rates(env, dwa, peaks)
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, rects, forest, batches[W])
             if plan is not None:

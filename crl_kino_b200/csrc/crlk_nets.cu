@@ -280,70 +280,118 @@ extern "C" int crlk_estimator_destroy(CrlkEstimator *e)
     return CRLK_OK;
 }
 
-// conv3x3(pad 1) + ReLU + maxpool2 from in[CI][H][H] to out[CO][H/2][H/2] (shared memory).
-template <int CI, int CO, int H>
-__device__ __forceinline__ void conv_relu_pool(const float *__restrict__ w, const float *__restrict__ b,
+// Activations of one sample in shared memory, every map stored with a one-pixel zero border so
+// that the 3x3 taps need no bounds tests (a zero tap adds exactly nothing: fma(0, w, acc) == acc).
+#define CNN_IN_W 29      // 27 + 2
+#define CNN_A_W 15       // 13 + 2
+#define CNN_B_W 8        //  6 + 2
+#define CNN_C_W 5        //  3 + 2
+struct CnnSmem {
+    float in[CNN_IN_W * CNN_IN_W];
+    float a[8 * CNN_A_W * CNN_A_W];
+    float b[16 * CNN_B_W * CNN_B_W];
+    float c[32 * CNN_C_W * CNN_C_W];
+    float d[64];
+};
+
+__device__ __forceinline__ void cnn_zero(CnnSmem &s)
+{
+    float *p = reinterpret_cast<float *>(&s);
+    for (int i = threadIdx.x; i < (int)(sizeof(CnnSmem) / sizeof(float)); i += CNN_THREADS) p[i] = 0.f;
+}
+
+// conv3x3(pad 1) + ReLU + maxpool2 (floor) from the bordered map in[CI][HP][HP] to the bordered map
+// out[CO][OP][OP].  One task = (output channel, pooled row): the thread keeps the 2 x XT
+// pre-pool outputs of that row pair in registers and walks the input channels, loading each
+// channel's 4 x (XT + 2) input window and 9 weights once (216 FMA per 65 loads for conv2) --
+// instead of one load pair per FMA and a single dependent accumulator.  Per accumulator the
+// additions run in the same order as before (bias, then channel, ky, kx ascending).
+template <int CI, int CO, int HP, int XT, int OP>
+__device__ __forceinline__ void conv_pool_rows(const float *__restrict__ w, const float *__restrict__ bias,
                                                const float *in, float *out)
 {
-    constexpr int P = H / 2;
-    for (int o = threadIdx.x; o < CO * P * P; o += CNN_THREADS) {
-        int co = o / (P * P), r = o - co * P * P, py = r / P, px = r - py * P;
-        float best = -CUDART_INF_F;
+    constexpr int NPR = XT / 2;                    // pooled rows = pooled columns
+    for (int task = threadIdx.x; task < CO * NPR; task += CNN_THREADS) {
+        const int co = task / NPR, pr = task - co * NPR;
+        float acc[2][XT];
+        const float b0 = __ldg(&bias[co]);
 #pragma unroll
-        for (int sy = 0; sy < 2; sy++)
+        for (int r = 0; r < 2; r++)
 #pragma unroll
-            for (int sx = 0; sx < 2; sx++) {
-                int y = 2 * py + sy, x = 2 * px + sx;
-                float acc = __ldg(&b[co]);
-                for (int ci = 0; ci < CI; ci++) {
-                    const float *wp = w + (co * CI + ci) * 9;
-                    const float *ip = in + ci * H * H;
+            for (int x = 0; x < XT; x++) acc[r][x] = b0;
+        for (int ci = 0; ci < CI; ci++) {
+            const float *wp = w + (co * CI + ci) * 9;
+            float wv[9];
 #pragma unroll
-                    for (int ky = 0; ky < 3; ky++) {
-                        int yy = y + ky - 1;
-                        if (yy < 0 || yy >= H) continue;
+            for (int k = 0; k < 9; k++) wv[k] = __ldg(&wp[k]);
+            const float *ip = in + ci * HP * HP + (2 * pr) * HP;     // bordered rows 2pr .. 2pr + 3
 #pragma unroll
-                        for (int kx = 0; kx < 3; kx++) {
-                            int xx = x + kx - 1;
-                            if (xx < 0 || xx >= H) continue;
-                            acc = fmaf(ip[yy * H + xx], __ldg(&wp[ky * 3 + kx]), acc);
-                        }
-                    }
+            for (int r = 0; r < 2; r++) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++) {
+                    float row[XT + 2];
+#pragma unroll
+                    for (int x = 0; x < XT + 2; x++) row[x] = ip[(r + ky) * HP + x];
+#pragma unroll
+                    for (int x = 0; x < XT; x++)
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) acc[r][x] = fmaf(row[x + kx], wv[ky * 3 + kx], acc[r][x]);
                 }
-                best = fmaxf(best, acc);
             }
-        out[o] = fmaxf(best, 0.f);
+        }
+        float *op = out + co * OP * OP + (pr + 1) * OP + 1;
+#pragma unroll
+        for (int px = 0; px < NPR; px++) {
+            float m = fmaxf(fmaxf(acc[0][2 * px], acc[0][2 * px + 1]), fmaxf(acc[1][2 * px], acc[1][2 * px + 1]));
+            op[px] = fmaxf(m, 0.f);
+        }
     }
 }
 
-
-// conv4 (32 -> 64, 3x3, pad 1) + ReLU + global average pool over the 3 x 3 map
+// conv4 (32 -> 64, 3x3, pad 1) + ReLU + global average pool over the 3 x 3 map: one output channel
+// per thread, nine accumulators.
 __device__ __forceinline__ void conv4_avgpool(const float *__restrict__ P, const float *s_c, float *s_d)
 {
     for (int co = threadIdx.x; co < 64; co += CNN_THREADS) {
+        float acc[9];
+        const float b0 = __ldg(&P[O_B4 + co]);
+#pragma unroll
+        for (int k = 0; k < 9; k++) acc[k] = b0;
+        for (int ci = 0; ci < 32; ci++) {
+            const float *wp = P + O_W4 + (co * 32 + ci) * 9;
+            float wv[9], iv[CNN_C_W * CNN_C_W];
+#pragma unroll
+            for (int k = 0; k < 9; k++) wv[k] = __ldg(&wp[k]);
+#pragma unroll
+            for (int k = 0; k < CNN_C_W * CNN_C_W; k++) iv[k] = s_c[ci * CNN_C_W * CNN_C_W + k];
+#pragma unroll
+            for (int y = 0; y < 3; y++)
+#pragma unroll
+                for (int x = 0; x < 3; x++)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++)
+                            acc[y * 3 + x] = fmaf(iv[(y + ky) * CNN_C_W + x + kx], wv[ky * 3 + kx], acc[y * 3 + x]);
+        }
         float sum = 0.f;
-        for (int y = 0; y < 3; y++)
-            for (int x = 0; x < 3; x++) {
-                float acc = __ldg(&P[O_B4 + co]);
-                for (int ci = 0; ci < 32; ci++) {
-                    const float *wp = P + O_W4 + (co * 32 + ci) * 9;
-                    const float *ip = s_c + ci * 9;
 #pragma unroll
-                    for (int ky = 0; ky < 3; ky++) {
-                        int yy = y + ky - 1;
-                        if (yy < 0 || yy >= 3) continue;
-#pragma unroll
-                        for (int kx = 0; kx < 3; kx++) {
-                            int xx = x + kx - 1;
-                            if (xx < 0 || xx >= 3) continue;
-                            acc = fmaf(ip[yy * 3 + xx], __ldg(&wp[ky * 3 + kx]), acc);
-                        }
-                    }
-                }
-                sum += fmaxf(acc, 0.f);
-            }
+        for (int k = 0; k < 9; k++) sum += fmaxf(acc[k], 0.f);
         s_d[co] = sum / 9.0f;
     }
+}
+
+// All four convolution stages of one net over the sample in s.in; features land in s.d.
+__device__ __forceinline__ void cnn_features(const float *__restrict__ P, CnnSmem &s)
+{
+    conv_pool_rows<1, 8, CNN_IN_W, 26, CNN_A_W>(P + O_W1, P + O_B1, s.in, s.a);     // 27 -> 13
+    __syncthreads();
+    conv_pool_rows<8, 16, CNN_A_W, 12, CNN_B_W>(P + O_W2, P + O_B2, s.a, s.b);      // 13 -> 6
+    __syncthreads();
+    conv_pool_rows<16, 32, CNN_B_W, 6, CNN_C_W>(P + O_W3, P + O_B3, s.b, s.c);      //  6 -> 3
+    __syncthreads();
+    conv4_avgpool(P, s.c, s.d);
+    __syncthreads();
 }
 
 // Linear(67 -> 1) over [features(64), ext(3)] by the first warp; result in lane 0.
@@ -366,25 +414,20 @@ __global__ void __launch_bounds__(CNN_THREADS)
 k_estimator(const float *__restrict__ params, const float *__restrict__ obs, int ld_obs, int B,
             float *__restrict__ est, float *__restrict__ prob)
 {
-    __shared__ float s_in[27 * 27];
-    __shared__ float s_a[8 * 13 * 13];
-    __shared__ float s_b[16 * 6 * 6];
-    __shared__ float s_c[32 * 3 * 3];
-    __shared__ float s_d[64];
+    __shared__ CnnSmem sm;
     const int b = blockIdx.x, net = blockIdx.y;
     if (b >= B) return;
     const float *P = params + (size_t)net * CNN_PARAMS;
     const float *o = obs + (size_t)b * ld_obs;
-    for (int i = threadIdx.x; i < 729; i += CNN_THREADS) s_in[i] = o[4 + i];
+    cnn_zero(sm);
     __syncthreads();
-    conv_relu_pool<1, 8, 27>(P + O_W1, P + O_B1, s_in, s_a);
+    for (int i = threadIdx.x; i < 729; i += CNN_THREADS) {
+        int y = i / 27, x = i - y * 27;
+        sm.in[(y + 1) * CNN_IN_W + x + 1] = o[4 + i];
+    }
     __syncthreads();
-    conv_relu_pool<8, 16, 13>(P + O_W2, P + O_B2, s_a, s_b);
-    __syncthreads();
-    conv_relu_pool<16, 32, 6>(P + O_W3, P + O_B3, s_b, s_c);
-    __syncthreads();
-    conv4_avgpool(P, s_c, s_d);
-    __syncthreads();
+    cnn_features(P, sm);
+    const float *s_d = sm.d;
     if (threadIdx.x < 32) {
         // ext = [||goal_body||, v, omega] (rrt_rl_estimator.py:59-62), float32
         float gx = o[0], gy = o[1];
@@ -436,14 +479,12 @@ k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const
                   long long stride, int max_nodes, const double *__restrict__ targets,
                   const int *__restrict__ skip, long long rows, float *__restrict__ est, float *__restrict__ prob)
 {
-    __shared__ float s_in[27 * 27];
-    __shared__ float s_a[8 * 13 * 13];
-    __shared__ float s_b[16 * 6 * 6];
-    __shared__ float s_c[32 * 3 * 3];
-    __shared__ float s_d[64];
+    __shared__ CnnSmem sm;
     __shared__ float s_ext[4];
     const long long row = blockIdx.x;
     if (row >= rows || skip[row]) return;
+    cnn_zero(sm);
+    __syncthreads();
     const int q = (int)(row / max_nodes), nidx = (int)(row - (long long)q * max_nodes);
     const double *st = states + ((size_t)stride * q + nidx) * 5;
     const double x = st[0], y = st[1];
@@ -455,7 +496,7 @@ k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const
         double px, py;
         body_to_world(cs, sn, x, y, arange_at(og.ba0, og.ba1, og.bad, ib), arange_at(og.lr0, og.lr1, og.lrd, il),
                       px, py);
-        s_in[p] = local_map_occupied<false>(os, px, py, nearp) ? 0.f : 1.f;
+        sm.in[(ib + 1) * CNN_IN_W + il + 1] = local_map_occupied<false>(os, px, py, nearp) ? 0.f : 1.f;
     }
     if (threadIdx.x == 0) {
         double qx = __dadd_rn(targets[5 * (size_t)q], -x), qy = __dadd_rn(targets[5 * (size_t)q + 1], -y);
@@ -468,16 +509,9 @@ k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const
     __syncthreads();
     for (int net = 0; net < 2; net++) {
         const float *P = params + (size_t)net * CNN_PARAMS;
-        conv_relu_pool<1, 8, 27>(P + O_W1, P + O_B1, s_in, s_a);
-        __syncthreads();
-        conv_relu_pool<8, 16, 13>(P + O_W2, P + O_B2, s_a, s_b);
-        __syncthreads();
-        conv_relu_pool<16, 32, 6>(P + O_W3, P + O_B3, s_b, s_c);
-        __syncthreads();
-        conv4_avgpool(P, s_c, s_d);
-        __syncthreads();
+        cnn_features(P, sm);
         if (threadIdx.x < 32) {
-            float acc = cnn_head(P, s_d, s_ext[0], s_ext[1], s_ext[2]);
+            float acc = cnn_head(P, sm.d, s_ext[0], s_ext[1], s_ext[2]);
             if (threadIdx.x == 0) {
                 if (net == 0) est[row] = acc;
                 else prob[row] = 1.0f / (1.0f + expf(-acc));
