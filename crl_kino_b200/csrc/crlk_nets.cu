@@ -263,6 +263,22 @@ extern "C" int crlk_estimator_create(const float *const *est_params_host,
             off += sizes[i];
         }
     }
+    // conv weights [co][ci][3x3] -> [ci][3x3][co]: the threads of a warp work on neighbouring output
+    // channels, so each weight load becomes one cache line instead of one line per lane
+    {
+        static const int w_off[4] = {O_W1, O_W2, O_W3, O_W4}, w_ci[4] = {1, 8, 16, 32}, w_co[4] = {8, 16, 32, 64};
+        float *tmp = (float *)malloc(sizeof(float) * 64 * 32 * 9);
+        for (int net = 0; net < 2; net++)
+            for (int l = 0; l < 4; l++) {
+                float *W = h + (size_t)net * CNN_PARAMS + w_off[l];
+                const int CI = w_ci[l], CO = w_co[l];
+                memcpy(tmp, W, sizeof(float) * CO * CI * 9);
+                for (int co = 0; co < CO; co++)
+                    for (int ci = 0; ci < CI; ci++)
+                        for (int k = 0; k < 9; k++) W[(ci * 9 + k) * CO + co] = tmp[(co * CI + ci) * 9 + k];
+            }
+        free(tmp);
+    }
     CrlkEstimator *e = new CrlkEstimator();
     CRLK_CUDA(cudaGetDevice(&e->device));
     CRLK_CUDA(cudaMalloc(&e->d_params, sizeof(float) * 2 * CNN_PARAMS));
@@ -320,10 +336,10 @@ __device__ __forceinline__ void conv_pool_rows(const float *__restrict__ w, cons
 #pragma unroll
             for (int x = 0; x < XT; x++) acc[r][x] = b0;
         for (int ci = 0; ci < CI; ci++) {
-            const float *wp = w + (co * CI + ci) * 9;
+            const float *wp = w + (size_t)ci * 9 * CO + co;          // weights stored [ci][3x3][co]
             float wv[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) wv[k] = __ldg(&wp[k]);
+            for (int k = 0; k < 9; k++) wv[k] = __ldg(&wp[k * CO]);
             const float *ip = in + ci * HP * HP + (2 * pr) * HP;     // bordered rows 2pr .. 2pr + 3
 #pragma unroll
             for (int r = 0; r < 2; r++) {
@@ -358,10 +374,10 @@ __device__ __forceinline__ void conv4_avgpool(const float *__restrict__ P, const
 #pragma unroll
         for (int k = 0; k < 9; k++) acc[k] = b0;
         for (int ci = 0; ci < 32; ci++) {
-            const float *wp = P + O_W4 + (co * 32 + ci) * 9;
+            const float *wp = P + O_W4 + (size_t)ci * 9 * 64 + co;   // weights stored [ci][3x3][co]
             float wv[9], iv[CNN_C_W * CNN_C_W];
 #pragma unroll
-            for (int k = 0; k < 9; k++) wv[k] = __ldg(&wp[k]);
+            for (int k = 0; k < 9; k++) wv[k] = __ldg(&wp[k * 64]);
 #pragma unroll
             for (int k = 0; k < CNN_C_W * CNN_C_W; k++) iv[k] = s_c[ci * CNN_C_W * CNN_C_W + k];
 #pragma unroll
