@@ -101,7 +101,7 @@ __device__ __forceinline__ double crlk_rcp_pos(double a)
 // atan2 for the rollout scoring loop (dwa.py:58), about 30 float64 instructions instead of
 // the library's ~65: q = min/max of |y|, |x| by a Newton division with residual correction,
 // then the degree-10 Taylor polynomial of atan about the nearest multiple of 1/16 (`tab`:
-// CRLK_ATAN_NK x (CRLK_ATAN_DEG + 1) coefficients, shared memory), then the octant fix-ups.
+// (CRLK_ATAN_DEG + 1) x CRLK_ATAN_NK coefficients, shared memory), then the octant fix-ups.
 // Worst error 1.5 ulp against a 200-bit reference (tools/gen_atan_table.py; measured on the
 // device by tests/test_gpu_dwa.py) -- the library's bound is 2 ulp, numpy's own SIMD arctan2
 // differs from libm in the last bit for 8 % of inputs.  Zero, tiny, huge and NaN arguments take
@@ -118,10 +118,10 @@ __device__ __forceinline__ double crlk_atan2(double y, double x, const double *t
     q = fma(fma(-mx, q, mn), r, q);
     const int k = __double2int_rn(q * 16.0);
     const double t = fma(-(double)k, 0.0625, q);
-    const double *a = tab + k * (CRLK_ATAN_DEG + 1);
-    double p = a[CRLK_ATAN_DEG];
+    const double *a = tab + k;                         // tab[coefficient][interval]
+    double p = a[CRLK_ATAN_DEG * CRLK_ATAN_NK];
 #pragma unroll
-    for (int n = CRLK_ATAN_DEG - 1; n >= 0; n--) p = fma(p, t, a[n]);
+    for (int n = CRLK_ATAN_DEG - 1; n >= 0; n--) p = fma(p, t, a[n * CRLK_ATAN_NK]);
     if (ay > ax) p = 1.5707963267948966 - p;
     if (x < 0.0) p = 3.141592653589793 - p;
     return copysign(p, y);

@@ -630,8 +630,11 @@ __device__ __constant__ unsigned long long c_atan_bits[CRLK_ATAN_NK * (CRLK_ATAN
 // copy the atan coefficient table into shared memory (call before the first barrier of the kernel)
 __device__ __forceinline__ void load_atan_table(double *dst)
 {
-    for (int i = threadIdx.x; i < CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1); i += blockDim.x)
-        dst[i] = __longlong_as_double((long long)c_atan_bits[i]);
+    // stored [coefficient][interval]: lanes that fall into different intervals read different banks
+    for (int i = threadIdx.x; i < CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1); i += blockDim.x) {
+        const int k = i / (CRLK_ATAN_DEG + 1), n = i - k * (CRLK_ATAN_DEG + 1);
+        dst[n * CRLK_ATAN_NK + k] = __longlong_as_double((long long)c_atan_bits[i]);
+    }
 }
 
 __global__ void k_debug_atan2(const double *__restrict__ y, const double *__restrict__ x, int n, double *out)
@@ -855,8 +858,8 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         }
         double sn, cs;
         sincos(th, &sn, &cs);
-        sm.wcos[task] = cs;
-        sm.wsin[task] = sn;
+        sm.wcos[ks * d.nw_max + j] = cs;          // [sub-step][w command]: neighbouring rollouts, neighbouring banks
+        sm.wsin[ks * d.nw_max + j] = sn;
         if ((ks + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (ks + 1) / d.n_sub - 1] = th;
         if (ks + 1 == d.n_sub) sm.wom[j] = cur;      // omega after the first dt step
     }
@@ -872,11 +875,12 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     int ri = tid / nw, rj = tid - ri * nw;
     auto heading_cost = [&](int i, int j, double &x, double &y) {
         const double *vt = sm.vtab + i * spos;
-        const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
+        const double *wc = sm.wcos + j, *ws = sm.wsin + j;
+        const int nwm = d.nw_max;
         x = st[0]; y = st[1];
         for (int k = 0; k < d.n_sub; k++) {
-            x = x + vt[k] * wc[k] * dt;
-            y = y + vt[k] * ws[k] * dt;
+            x = x + vt[k] * wc[k * nwm] * dt;
+            y = y + vt[k] * ws[k * nwm] * dt;
         }
         double ang = crlk_atan2(gy - y, gx - x, sm.atab);
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
@@ -917,13 +921,14 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             sm.c0[r] = ca;
             acc0 += ca;
             const double *vt = sm.vtab + i * spos;
-            const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
+            const double *wc = sm.wcos + j, *ws = sm.wsin + j;
+            const int nwm = d.nw_max;
             double min_dis = pymin(clr0, 100.0);
             for (int row = 1; row <= d.n_outer; row++) {
                 if (row > 1)
                     for (int k = (row - 1) * d.n_sub; k < row * d.n_sub; k++) {
-                        x = x + vt[k] * wc[k] * dt;
-                        y = y + vt[k] * ws[k] * dt;
+                        x = x + vt[k] * wc[k * nwm] * dt;
+                        y = y + vt[k] * ws[k * nwm] * dt;
                     }
                 if (row % d.skip == 0) {
                     double dis = pymax(clearance_thread(e, os, x, y, sm.wth[j * d.n_outer + row - 1]),
@@ -1034,18 +1039,19 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         double row1[5];
         {
             const double *vt = sm.vtab + i * spos;
-            const double *wc = sm.wcos + j * spos, *ws = sm.wsin + j * spos;
+            const double *wc = sm.wcos + j, *ws = sm.wsin + j;
             double x = st[0], y = st[1];
             for (int k = 0; k < d.n_sub; k++) {
-                x = x + vt[k] * wc[k] * dt;
-                y = y + vt[k] * ws[k] * dt;
+                x = x + vt[k] * wc[k * d.nw_max] * dt;
+                y = y + vt[k] * ws[k * d.nw_max] * dt;
             }
             row1[0] = x; row1[1] = y; row1[2] = sm.wth[j * d.n_outer];
             row1[3] = vt[d.n_sub - 1]; row1[4] = sm.wom[j];
         }
         PHASE_MARK(6);
         // thread 0 only, before the closing barrier; also gets cos / sin of row 1's heading
-        epilogue(sm.scal[4], sm.scal[5], ix, row1, sm.wcos[j * spos + d.n_sub - 1], sm.wsin[j * spos + d.n_sub - 1]);
+        epilogue(sm.scal[4], sm.scal[5], ix, row1, sm.wcos[(d.n_sub - 1) * d.nw_max + j],
+                 sm.wsin[(d.n_sub - 1) * d.nw_max + j]);
     }
     PHASE_MARK(9);
     __syncthreads();
