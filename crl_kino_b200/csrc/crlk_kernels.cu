@@ -623,7 +623,6 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
 #ifndef PLAN_MIN_BLOCKS
 #define PLAN_MIN_BLOCKS 4
 #endif
-#define PW_BLOCK 128
 
 __device__ __constant__ unsigned long long c_atan_bits[CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1)] = CRLK_ATAN_TAB_INIT;
 
@@ -660,33 +659,30 @@ struct DwaSmem {
     double *c0, *c1;
     double *vtab, *vlast, *c2n;
     double *wcos, *wsin, *wth, *wom;
-    double *red_v, *red_s;            // [32] screened minimum / runner-up per warp
-    int *red_i;                       // [32]
+    double *red_v, *red_s;            // [32] column-sum partials per warp (heading, speed); nearest_block scratch
+    int *red_i;                       // [32] index of the per-warp minimum
     double *red2_v;                   // [32] third column-sum partial per warp
     double *red3_v, *red3_s;          // [32] minimum / runner-up per warp
     double *hdr;                      // [8]  v_hi v_lo w_hi w_lo of the current window
     int *ihdr;                        // [4]  nv nw
     RobotPose *pose;                  // footprint of the state the next validity test looks at
     double *atab;                     // atan coefficient table (crlk_atan2)
-    double *scal;                     // [16]
-    int *iscal;                       // [8]: 0 n_leaves, 1 opt idx, 2 near tie, 3 cached R, 4 n_levels, 5 n_nodes
-    int *queue;                       // [1024] scratch for the collision survivor list
-    int spos, rmax, nmax;
+    double *scal;                     // [16]: 4 winning v command, 5 winning w command
+    int *iscal;                       // [8]: 1 winning rollout index, 2 near-tie flag
+    int spos, rmax;
 };
 
-#define PW_MAX_LEVELS 24
 
 __host__ __device__ inline int dwa_spos(const DwaP &d)
 {
     return d.use_clearance ? d.n_sub * d.n_outer : d.n_sub;
 }
 __host__ __device__ inline int dwa_rmax(const DwaP &d) { return d.nv_max * d.nw_max; }
-__host__ __device__ inline int dwa_nmax(const DwaP &d) { return dwa_rmax(d) / 32 + 16; }
 
 __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, DwaSmem *s)
 {
     size_t off = 0;
-    int spos = dwa_spos(d), rmax = dwa_rmax(d), nmax = dwa_nmax(d);
+    int spos = dwa_spos(d), rmax = dwa_rmax(d);
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
     size_t o_c0 = take(sizeof(double) * rmax);
     size_t o_c1 = take(d.use_clearance ? sizeof(double) * rmax : 0);
@@ -708,7 +704,6 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_at = take(sizeof(double) * CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1));
     size_t o_sc = take(sizeof(double) * 16);
     size_t o_is = take(sizeof(int) * 8);
-    size_t o_q = take(sizeof(int) * 1024);
     if (s) {
         s->c0 = (double *)(base + o_c0); s->c1 = (double *)(base + o_c1);
         s->vtab = (double *)(base + o_vtab); s->vlast = (double *)(base + o_vlast);
@@ -723,8 +718,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->ihdr = (int *)(base + o_ih); s->pose = (RobotPose *)(base + o_po);
         s->atab = (double *)(base + o_at);
         s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
-        s->queue = (int *)(base + o_q);
-        s->spos = spos; s->rmax = rmax; s->nmax = nmax;
+        s->spos = spos; s->rmax = rmax;
     }
     return off;
 }
