@@ -354,6 +354,14 @@ __device__ __forceinline__ void body_to_world(double cs, double sn, double x, do
 template <bool WANT_NEAR = true>
 __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, double py, bool &near)
 {
+    if (!WANT_NEAR) {
+        // raster first: most sample points fall into cells that no obstacle touches or that one covers
+        const float rx = ((float)px - os.gx0) * os.rinv, ry = ((float)py - os.gy0) * os.rinv;
+        if (rx >= 0.f && ry >= 0.f && rx < (float)os.rnx && ry < (float)os.rny) {
+            const unsigned c = __ldg(&os.raster[(int)ry * os.rnx + (int)rx]);
+            if (c < 2u) return c != 0u;
+        }
+    }
     const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
     float fx0 = floorf(((float)px - 1e-6f - os.gx0) * os.ginv), fx1 = floorf(((float)px + 1e-6f - os.gx0) * os.ginv);
     float fy0 = floorf(((float)py - 1e-6f - os.gy0) * os.ginv), fy1 = floorf(((float)py + 1e-6f - os.gy0) * os.ginv);

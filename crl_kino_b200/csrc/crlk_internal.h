@@ -23,6 +23,11 @@ struct ObsSet {
     const int *cell_items;    // obstacle ids, cell by cell
     int M, ncx, ncy;
     float gx0, gy0, ginv;     // grid origin and 1 / cell size
+    // occupancy raster for point queries (same origin, CRLK_RASTER_SUB cells per grid cell and axis):
+    // 0 = no obstacle touches the cell, 1 = the obstacles together cover the whole cell, 2 = mixed (test exactly)
+    const uint8_t *raster;
+    int rnx, rny;
+    float rinv;
 };
 
 struct DwaP {
@@ -46,6 +51,7 @@ struct CrlkEnv {
     EnvP p;
     float4 *d_rects;  // M obstacles [l, b, r, t]
     int *d_cell_start, *d_cell_items;
+    uint8_t *d_raster;
     ObsSet os;
     int M;
 };

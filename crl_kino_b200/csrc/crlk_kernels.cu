@@ -4,6 +4,7 @@
 #include <math_constants.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #include "crlk_device.cuh"
 
@@ -60,6 +61,9 @@ int crlk_count_loop_le(double limit, double step)
 #ifndef CRLK_GRID_CELL
 #define CRLK_GRID_CELL 0.5f   // obstacle grid pitch in metres (tuned on the cfg4 map, see profiles/)
 #endif
+#ifndef CRLK_RASTER_SUB
+#define CRLK_RASTER_SUB 4     // occupancy raster cells per grid cell and axis
+#endif
 
 static void fill_envp(const CrlkEnvParams *in, EnvP *p)
 {
@@ -107,6 +111,78 @@ static int build_grid(CrlkEnv *env, const float *r, int M)
                 int c = yy * ncx + xx;
                 items[start[c] + fill[c]++] = i;
             }
+    // Occupancy raster for the point queries of the local observation (729 per observation): a
+    // cell is 0 when no obstacle comes within `margin` of it, 1 when the obstacles together cover
+    // it and `margin` around it, else 2.  The margin (>= 1e-4 m) is far larger than the float32 error of
+    // the device's cell index, so a 0 / 1 answer is exactly what the scan over all obstacles gives
+    // (closed intervals, rigid.py:158-166); only cells marked 2 still run that scan.
+    const int RS = CRLK_RASTER_SUB;
+    const int rnx = ncx * RS, rny = ncy * RS;
+    const double h = (double)cell / RS;
+    const double margin = fmax(1e-4, 1e-5 * (double)ext);
+    uint8_t *raster = (uint8_t *)malloc((size_t)rnx * rny);
+    enum { RASTER_CAND = 64 };
+    int cand[RASTER_CAND];
+    double xs[2 * RASTER_CAND + 2], ys[2 * RASTER_CAND + 2];
+    for (int ry = 0; ry < rny; ry++)
+        for (int rx = 0; rx < rnx; rx++) {
+            const double cl = (double)x0 + rx * h - margin, cr = (double)x0 + (rx + 1) * h + margin;
+            const double cb = (double)y0 + ry * h - margin, ct = (double)y0 + (ry + 1) * h + margin;
+            // obstacles that reach into the (expanded) cell, clipped to it
+            int nc = 0;
+            for (int gy = cy((float)cb); gy <= cy((float)ct); gy++)
+                for (int gx = cx((float)cl); gx <= cx((float)cr); gx++)
+                    for (int k = start[gy * ncx + gx]; k < start[gy * ncx + gx + 1] && nc < RASTER_CAND; k++) {
+                        const float *o = r + 4 * items[k];
+                        const double l = o[0], b = o[1], rr = o[2], t = o[3];
+                        if (rr < cl || l > cr || t < cb || b > ct) continue;
+                        bool dup = false;
+                        for (int q = 0; q < nc; q++) dup |= (cand[q] == items[k]);
+                        if (!dup) cand[nc++] = items[k];
+                    }
+            uint8_t v = 0;
+            if (nc >= RASTER_CAND) v = 2;
+            else if (nc > 0) {
+                // covered by the UNION of the (closed) rectangles?  Cut the cell at every rectangle
+                // edge inside it; the cell is covered iff the centre of every elementary piece is.
+                // (Abutting tiles cover a cell together; a one-ulp gap between two tiles leaves an
+                // uncovered sliver, and the cell stays "mixed".)
+                int nx = 0, ny = 0;
+                xs[nx++] = cl; xs[nx++] = cr; ys[ny++] = cb; ys[ny++] = ct;
+                for (int q = 0; q < nc; q++) {
+                    const float *o = r + 4 * cand[q];
+                    if (o[0] > cl && o[0] < cr) xs[nx++] = o[0];
+                    if (o[2] > cl && o[2] < cr) xs[nx++] = o[2];
+                    if (o[1] > cb && o[1] < ct) ys[ny++] = o[1];
+                    if (o[3] > cb && o[3] < ct) ys[ny++] = o[3];
+                }
+                std::sort(xs, xs + nx); std::sort(ys, ys + ny);
+                bool all = true;
+                for (int a = 0; a + 1 < nx && all; a++)
+                    for (int c2 = 0; c2 + 1 < ny && all; c2++) {
+                        if (xs[a + 1] == xs[a] || ys[c2 + 1] == ys[c2]) continue;
+                        const double mx = 0.5 * (xs[a] + xs[a + 1]), my = 0.5 * (ys[c2] + ys[c2 + 1]);
+                        bool in = false;
+                        for (int q = 0; q < nc && !in; q++) {
+                            const float *o = r + 4 * cand[q];
+                            in = (mx >= o[0] && mx <= o[2] && my >= o[1] && my <= o[3]);
+                        }
+                        all = in;
+                    }
+                v = all ? 1 : 2;
+            }
+            raster[(size_t)ry * rnx + rx] = v;
+        }
+    if (env->d_raster) cudaFree(env->d_raster);
+    env->d_raster = nullptr;
+    cudaError_t e3 = cudaMalloc(&env->d_raster, (size_t)rnx * rny);
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(env->d_raster, raster, (size_t)rnx * rny, cudaMemcpyHostToDevice);
+    free(raster);
+    if (e3 != cudaSuccess) {
+        free(start); free(items); free(fill);
+        crlk_set_error("occupancy raster upload failed: %s", cudaGetErrorString(e3));
+        return CRLK_E_CUDA;
+    }
     if (env->d_cell_start) cudaFree(env->d_cell_start);
     if (env->d_cell_items) cudaFree(env->d_cell_items);
     env->d_cell_start = env->d_cell_items = nullptr;
@@ -125,6 +201,8 @@ static int build_grid(CrlkEnv *env, const float *r, int M)
     env->os.cell_items = env->d_cell_items;
     env->os.M = M; env->os.ncx = ncx; env->os.ncy = ncy;
     env->os.gx0 = x0; env->os.gy0 = y0; env->os.ginv = ginv;
+    env->os.raster = env->d_raster; env->os.rnx = rnx; env->os.rny = rny;
+    env->os.rinv = (float)(1.0 / h);
     return CRLK_OK;
 }
 
@@ -167,6 +245,7 @@ extern "C" int crlk_env_destroy(CrlkEnv *env)
     if (env->d_rects) cudaFree(env->d_rects);
     if (env->d_cell_start) cudaFree(env->d_cell_start);
     if (env->d_cell_items) cudaFree(env->d_cell_items);
+    if (env->d_raster) cudaFree(env->d_raster);
     delete env;
     return CRLK_OK;
 }

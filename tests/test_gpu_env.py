@@ -169,3 +169,31 @@ def test_circle_robot_golden(mname):
             assert (c == -1.0) == (ref == -1.0)
             if ref != -1.0:
                 assert abs(c - min(ref, 100.0)) <= 1e-9 * max(1.0, abs(ref))
+
+
+@pytest.mark.parametrize("seed,cells", ((0, 10000), (5, 2500)))
+def test_local_obs_raster_path_equals_exact_path(seed, cells):
+    """Observations built through the occupancy raster (no near-boundary output requested) are
+    bit-identical to the exact per-obstacle path (near-boundary output requested) and to the
+    oracle's scan over all obstacles, also for poses hugging obstacle faces and raster lines."""
+    from crl_kino_b200 import ops
+    from crl_kino_b200.workloads import dense_map, random_states
+    rects = dense_map(n_cells=cells, seed=seed)
+    env, o = make_envs(rects)
+    rng = np.random.default_rng(seed + 1)
+    B = 3000
+    states = random_states(rng, B, moving=True)
+    goals = random_states(rng, B)
+    # a third of the poses exactly on raster / obstacle lines, axis aligned: sample points land on cell edges
+    k = B // 3
+    states[:k, 0] = np.round(states[:k, 0] / 0.125) * 0.125
+    states[:k, 1] = np.round(states[:k, 1] / 0.125) * 0.125
+    states[:k, 2] = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi], k)
+    fast, f32, _ = ops.local_obs(env.handle, states, goals, want64=True, want32=True, want_near=False)
+    exact, _, near = ops.local_obs(env.handle, states, goals, want64=True, want32=False, want_near=True)
+    assert np.array_equal(np_(fast), np_(exact))
+    assert np.array_equal(np_(f32)[:, :733], np_(fast).astype(np.float32))
+    ref = o.local_obs_batch(states[:400], goals[:400])
+    ok = np_(near)[:400] == 0
+    assert np.array_equal(np_(fast)[:400][ok][:, 4:], ref[ok][:, 4:])
+    assert 0.02 < np_(fast)[:, 4:].mean() < 0.98          # both free and occupied cells occur
