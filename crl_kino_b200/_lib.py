@@ -81,7 +81,7 @@ PROTOTYPES = {
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
     "crlk_debug_atan2": (C.c_int, [P, P, I32, P, P]),
     "crlk_gym_step": (C.c_int, [P, P, P, I32, P, F64, P, I32, P, P, P, P, I32, P, P]),
-    "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P]),
+    "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),
     "crlk_policy_destroy": (C.c_int, [P]),
     "crlk_policy_forward": (C.c_int, [P, P, I32, P, F32, I32, P, P, P]),

@@ -1514,7 +1514,7 @@ __global__ void __launch_bounds__(T, MINB)
 k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
            const double *__restrict__ goals, const double *__restrict__ streams, int Q, int *iters_out,
            int *cursor_out, uint8_t *reached_out, uint8_t *flags_out, int *overflow, int *work_counter,
-           unsigned long long *stats)
+           unsigned long long *stats, const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DwaSmem sm;
@@ -1527,8 +1527,8 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
         __syncthreads();
         if (tid == 0) s_q = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int q = s_q;
-        if (q >= Q) break;
+        if (s_q >= Q) break;
+        const int q = order ? order[s_q] : s_q;       // work item -> query (longest-expected first)
         const size_t tb = (size_t)f.stride * q;
         double *tx64 = f.x64 + tb, *ty64 = f.y64 + tb;
         int n = f.n_nodes[q];
@@ -1628,7 +1628,7 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
                              const CrlkPlanParams *plan, const CrlkForestView *forest, const double *goals,
                              const double *streams, int32_t S, int32_t Q, int32_t *iters, int32_t *cursor,
                              uint8_t *reached, uint8_t *flags, int32_t *overflow, uint64_t *stats,
-                             void *stream)
+                             const int32_t *order, void *stream)
 {
     CRLK_REQUIRE(env != nullptr && plan != nullptr && forest != nullptr, "env/plan/forest is NULL");
     DwaP d;
@@ -1667,7 +1667,7 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
     if (rc) return rc;
     kern<<<grid, threads, smem, (cudaStream_t)stream>>>(
         env->p, d, x, env->os, *forest, pp, goals, streams, Q, iters, cursor, reached, flags, overflow,
-        counter, (unsigned long long *)stats);
+        counter, (unsigned long long *)stats, order);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

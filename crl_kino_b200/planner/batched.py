@@ -310,6 +310,10 @@ class FusedRRT(BatchedRRT):
                          node_capacity=node_capacity, with_f32=with_f32)
         d = self.starts.device
         self.flags = torch.zeros(self.Q, dtype=torch.uint8, device=d)
+        # scheduling hint: queries whose goal is far from the start tend to need the most iterations;
+        # handing those out first shortens the tail of the launch (results do not depend on the order)
+        gap = (self.starts[:, :2] - self.goals[:, :2]).norm(dim=1)
+        self.order = torch.argsort(gap, descending=True).to(torch.int32).contiguous()
 
     def plan_async(self, streams):
         """Launch the planning kernel on the current stream; streams: CUDA float64 [Q, S, 5]."""
@@ -323,7 +327,8 @@ class FusedRRT(BatchedRRT):
         check(lib().crlk_plan_dwa(self.env.handle.h, C.byref(self.dwa.params()), C.byref(self.xp), C.byref(pp),
                                   C.byref(self._fv), p(self.goals), p(streams), streams.shape[1], self.Q,
                                   p(self.iters), p(self.cursor), p(self.reached), p(self.flags),
-                                  p(self.overflow), p(self.stats), ops._stream()))
+                                  p(self.overflow), p(self.stats), p(self.order) if self.order is not None else None,
+                                  ops._stream()))
 
     def plan(self, streams, **_):
         streams = ops.as_dev(streams).contiguous()

@@ -329,11 +329,14 @@ typedef struct {
  *   flags    dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin
  *            somewhere in the run, bit2 out of node / pool capacity
  *   overflow dev i32[1] += number of queries that ran out of capacity
- *   stats    dev u64[3] (nullable) += extensions, control steps, rollouts */
+ *   stats    dev u64[3] (nullable) += extensions, control steps, rollouts
+ *   order    dev i32[Q] (nullable) a permutation of 0..Q-1: the order in which thread blocks pick
+ *            queries up (scheduling only -- e.g. longest expected first; results do not depend on it) */
 int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
                   const CrlkPlanParams *plan, const CrlkForestView *forest, const double *goals,
                   const double *streams, int32_t S, int32_t Q, int32_t *iters, int32_t *cursor,
-                  uint8_t *reached, uint8_t *flags, int32_t *overflow, uint64_t *stats, void *stream);
+                  uint8_t *reached, uint8_t *flags, int32_t *overflow, uint64_t *stats,
+                  const int32_t *order, void *stream);
 
 #ifdef __cplusplus
 }
