@@ -75,7 +75,8 @@ PROTOTYPES = {
     "crlk_nearest_scratch_bytes": (I64, [I32, I32]),
     "crlk_extend_dwa": (C.c_int, [P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P]),
     "crlk_gather_rows": (C.c_int, [P, I64, I32, P, I32, P, P]),
-    "crlk_estimator_choose_parent": (C.c_int, [P, P, P, I64, P, I32, P, I32, P, P, P, P]),
+    "crlk_estimator_choose_parent": (C.c_int, [P, P, P, I64, P, P, I32, P, I32, P, P, P, P]),
+    "crlk_rrt_retry_choice": (C.c_int, [P, P, P, P, P, I32, F64, I32, P, P, P, P, P, P]),
     "crlk_estimator_cp_workspace_bytes": (I64, [I32, I32]),
     "crlk_rrt_select": (C.c_int, [P, P, I32, I32, F64, F64, P, P, P, P]),
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),

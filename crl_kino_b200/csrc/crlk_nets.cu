@@ -475,12 +475,13 @@ extern "C" int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, 
 
 // per node: Euclidean distance to the query's target and the [1, 20) filter (:29-31)
 __global__ void k_cp_dist(const double *__restrict__ states, long long stride, const int *__restrict__ n_nodes,
-                          int max_nodes, const double *__restrict__ targets, int Q, double *dist, int *skip)
+                          const int *__restrict__ first_node, int max_nodes, const double *__restrict__ targets,
+                          int Q, double *dist, int *skip)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)Q * max_nodes) return;
     int q = (int)(i / max_nodes), n = (int)(i - (long long)q * max_nodes);
-    if (n >= n_nodes[q]) { skip[i] = 1; dist[i] = CUDART_INF; return; }
+    if (n >= n_nodes[q] || (first_node && n < first_node[q])) { skip[i] = 1; dist[i] = CUDART_INF; return; }
     const double *s = states + ((size_t)stride * q + n) * 5;
     double dx = s[0] - targets[5 * (size_t)q], dy = s[1] - targets[5 * (size_t)q + 1];
     double dd = sqrt(fma(dy, dy, __dmul_rn(dx, dx)));            // np.linalg.norm
@@ -542,8 +543,8 @@ k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const
 // node passed the filter (:33-34).
 __global__ void __launch_bounds__(256)
 k_cp_final(const double *__restrict__ dist, const int *__restrict__ skip, const float *__restrict__ est,
-           const float *__restrict__ prob, const int *__restrict__ n_nodes, int max_nodes, int Q, int *idx,
-           double *cost)
+           const float *__restrict__ prob, const int *__restrict__ n_nodes, const int *__restrict__ first_node,
+           int max_nodes, int Q, int *idx, double *cost)
 {
     __shared__ double sv[8];
     __shared__ int si[8], sany[8];
@@ -573,7 +574,9 @@ k_cp_final(const double *__restrict__ dist, const int *__restrict__ skip, const 
             if (sv[w] < best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
             any |= sany[w];
         }
-        if (!any) { idx[q] = 0; cost[q] = 100.0; }
+        // no candidate in the band: element 0 of the candidate list, cost 100 (:33-34)
+        const int f0 = first_node ? first_node[q] : 0;
+        if (!any) { idx[q] = (f0 < n) ? f0 : 0; cost[q] = 100.0; }
         else { idx[q] = bi; cost[q] = best; }
     }
 }
@@ -586,9 +589,9 @@ extern "C" int64_t crlk_estimator_cp_workspace_bytes(int32_t Q, int32_t max_node
 }
 
 extern "C" int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstimator *e, const double *states,
-                                            int64_t stride, const int32_t *n_nodes, int32_t max_nodes,
-                                            const double *targets, int32_t Q, int32_t *idx, double *cost,
-                                            void *workspace, void *stream)
+                                            int64_t stride, const int32_t *n_nodes, const int32_t *first_node,
+                                            int32_t max_nodes, const double *targets, int32_t Q, int32_t *idx,
+                                            double *cost, void *workspace, void *stream)
 {
     CRLK_REQUIRE(env && e, "env/estimator is NULL");
     CRLK_REQUIRE(Q >= 0 && max_nodes >= 1 && stride >= max_nodes, "shape");
@@ -602,14 +605,14 @@ extern "C" int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstima
     int *skip = (int *)(ws + rows * 8);
     float *est = (float *)(ws + rows * 12);
     float *prob = (float *)(ws + rows * 16);
-    k_cp_dist<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(states, (long long)stride, n_nodes, max_nodes,
-                                                            targets, Q, dist, skip);
+    k_cp_dist<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(states, (long long)stride, n_nodes, first_node,
+                                                            max_nodes, targets, Q, dist, skip);
     CRLK_LAUNCH_CHECK();
     k_estimator_nodes<<<(unsigned)rows, CNN_THREADS, 0, st>>>(make_obs_grid(), env->os, e->d_params, states,
                                                              (long long)stride, max_nodes, targets, skip, rows,
                                                              est, prob);
     CRLK_LAUNCH_CHECK();
-    k_cp_final<<<Q, 256, 0, st>>>(dist, skip, est, prob, n_nodes, max_nodes, Q, idx, cost);
+    k_cp_final<<<Q, 256, 0, st>>>(dist, skip, est, prob, n_nodes, first_node, max_nodes, Q, idx, cost);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

@@ -106,7 +106,7 @@ k_rrt_append(CrlkForestView f, CrlkExtendView x, const int *__restrict__ parent_
         }
         if (sqrt(fma(dy, dy, dx * dx)) <= goal_radius) { reached[q] = 1; done[q] = 1; fin = true; }
     }
-    if (primary && !fin && nn > 0) {
+    if (primary == 1 && !fin && nn > 0) {
         // choose_parent(new_node_list, goal): first minimum
         int best = 0;
         double bd = CUDART_INF;
@@ -125,8 +125,46 @@ k_rrt_append(CrlkForestView f, CrlkExtendView x, const int *__restrict__ parent_
             retry_active[q] = 1;
         }
     }
-    // out of iterations: finished after this round's last pass
-    if (!fin && iters[q] >= max_iter && (!primary || !retry_active[q])) done[q] = 1;
+    // out of iterations: finished after this round's last pass (primary == 2: crlk_rrt_retry_choice decides)
+    if (primary != 2 && !fin && iters[q] >= max_iter && (!primary || !retry_active[q])) done[q] = 1;
+}
+
+// Retry decision of a primary pass run with primary == 2: (idx, cost) come from the caller's own
+// choose_parent over the nodes the pass appended (rrt.py:78-79 with RRT_RL_Estimator.choose_parent).
+__global__ void k_rrt_retry_choice(CrlkForestView f, const int *__restrict__ n_before, const int *__restrict__ idx,
+                                   const double *__restrict__ cost, const uint8_t *__restrict__ active, int Q,
+                                   double retry_radius, int max_iter, const int *__restrict__ iters, uint8_t *done,
+                                   uint8_t *retry_active, double *retry_from, int *retry_parent)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    if (!active[q] || done[q]) return;
+    bool retry = f.n_nodes[q] > n_before[q] && cost[q] < retry_radius;
+    if (retry) {
+        const double *src = f.states + ((size_t)f.stride * q + idx[q]) * 5;
+        for (int c = 0; c < 5; c++) retry_from[5 * (size_t)q + c] = src[c];
+        retry_parent[q] = idx[q];
+        retry_active[q] = 1;
+    } else if (iters[q] >= max_iter) {
+        done[q] = 1;
+    }
+}
+
+extern "C" int crlk_rrt_retry_choice(const CrlkForestView *forest, const int32_t *n_before, const int32_t *idx,
+                                     const double *cost, const uint8_t *active, int32_t Q, double retry_radius,
+                                     int32_t max_iter, const int32_t *iters, uint8_t *done, uint8_t *retry_active,
+                                     double *retry_from, int32_t *retry_parent, void *stream)
+{
+    CRLK_REQUIRE(forest && forest->states && forest->n_nodes, "forest");
+    CRLK_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return CRLK_OK;
+    CRLK_REQUIRE(n_before && idx && cost && active && iters && done && retry_active && retry_from && retry_parent,
+                 "NULL array");
+    k_rrt_retry_choice<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*forest, n_before, idx, cost, active, Q,
+                                                                         retry_radius, max_iter, iters, done,
+                                                                         retry_active, retry_from, retry_parent);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
 }
 
 extern "C" int crlk_rrt_append(const CrlkForestView *forest, const CrlkExtendView *ext,

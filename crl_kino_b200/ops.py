@@ -308,8 +308,9 @@ def estimator_forward(est, obs32):
     return e, p
 
 
-def estimator_choose_parent(env, est, states, n_nodes, targets, max_nodes=None):
-    """states: float64 CUDA [Q, stride, 5]; n_nodes int32 [Q]; targets [Q, 5] -> (idx i32[Q], cost f64[Q])."""
+def estimator_choose_parent(env, est, states, n_nodes, targets, max_nodes=None, first_node=None):
+    """states: float64 CUDA [Q, stride, 5]; n_nodes int32 [Q]; targets [Q, 5] -> (idx i32[Q], cost f64[Q]).
+    first_node (int32 [Q], optional): candidates are the nodes [first_node[q], n_nodes[q])."""
     Q, stride, _ = states.shape
     targets = as_dev(targets).reshape(Q, 5)
     n_nodes = n_nodes.to(device=states.device, dtype=torch.int32).contiguous()
@@ -318,8 +319,9 @@ def estimator_choose_parent(env, est, states, n_nodes, targets, max_nodes=None):
     cost = torch.empty(Q, dtype=torch.float64, device=states.device)
     nbytes = lib().crlk_estimator_cp_workspace_bytes(Q, max_nodes)
     ws = torch.empty(int(nbytes), dtype=torch.uint8, device=states.device)
-    check(lib().crlk_estimator_choose_parent(env.h, est.h, _ptr(states), stride, _ptr(n_nodes), max_nodes,
-                                             _ptr(targets), Q, _ptr(idx), _ptr(cost), _ptr(ws), _stream()))
+    check(lib().crlk_estimator_choose_parent(env.h, est.h, _ptr(states), stride, _ptr(n_nodes), _ptr(first_node),
+                                             max_nodes, _ptr(targets), Q, _ptr(idx), _ptr(cost), _ptr(ws),
+                                             _stream()))
     return idx, cost
 
 

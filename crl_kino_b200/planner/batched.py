@@ -129,10 +129,12 @@ class BatchedRRT:
     is the one the sequential planner would build from the same stream.
 
     steering: 'dwa' (RRT) or 'rl' (RRT_RL with `policy`, optional noise stream).
+    parent selection: nearest node, or -- with `estimator` (the pair returned by load_estimator) --
+    RRT_RL_Estimator.choose_parent (rrt_rl_estimator.py:26-79) for both the sample and the retry.
     """
 
     def __init__(self, env, starts, goals, max_iter=500, dwa=None, policy=None, eps=0.0,
-                 keep_paths=True, node_capacity=None, with_f32=True):
+                 keep_paths=True, node_capacity=None, with_f32=True, estimator=None):
         import ctypes as C
         from .._lib import ExtendView, ForestView
         self.env = env
@@ -140,6 +142,8 @@ class BatchedRRT:
         self.max_iter = max_iter
         self.policy = policy
         self.eps = eps
+        self.estimator = estimator[0].pair if isinstance(estimator, (tuple, list)) else \
+            (estimator.pair if estimator is not None and hasattr(estimator, "pair") else estimator)
         if dwa is None and policy is None:
             from ..policy.dwa import DWA
             dwa = DWA(env)
@@ -226,7 +230,7 @@ class BatchedRRT:
         p = lambda t: C.c_void_p(t.data_ptr())
         check(lib().crlk_rrt_append(C.byref(self._fv), C.byref(ev), p(parent_idx), p(active), p(self.goals),
                                     self.Q, self.xp.n_max_extend, self.xp.n_tree, self.first_has_start,
-                                    1 if primary else 0, self.max_iter, 1.0, 5.0, p(self.iters), p(self.done),
+                                    int(primary), self.max_iter, 1.0, 5.0, p(self.iters), p(self.done),
                                     p(self.reached), p(self.retry_active), p(self.retry_from),
                                     p(self.retry_parent), p(self.overflow), ops._stream()))
 
@@ -237,13 +241,31 @@ class BatchedRRT:
         f = self.forest
         p = lambda t: C.c_void_p(t.data_ptr())
         valid, _, _ = ops.valid_state(self.env.handle, samples)                       # rrt.py:66
-        idx, dist, _ = ops.nearest(f.x, f.y, f.n_nodes, samples, x32=f.x32, y32=f.y32,
-                                   coord_bound=self.coord_bound)                       # rrt.py:68
+        est = self.estimator
+        # every round appends at most 2 * (per - 1) nodes per tree: a host-side bound of the tree sizes
+        bound = min(f.cap, 1 + 2 * (self.per - 1) * (self.rounds + 1))
+        if est is None:
+            idx, dist, _ = ops.nearest(f.x, f.y, f.n_nodes, samples, x32=f.x32, y32=f.y32,
+                                       coord_bound=self.coord_bound)                   # rrt.py:68
+        else:
+            idx, dist = ops.estimator_choose_parent(self.env.handle, est.handle, f.states, f.n_nodes, samples,
+                                                    max_nodes=bound)                   # rrt_rl_estimator.py:26
         check(lib().crlk_rrt_select(p(valid), p(dist), self.Q, self.max_iter, 1.0, 20.0, p(self.done),
                                     p(self.iters), p(self.active), ops._stream()))      # rrt.py:69
         ops.gather_rows(f.states, idx, out=self.from_states)                          # rrt.py:70
         out = self._extend(0, self.from_states, samples, self.active)                 # rrt.py:72
-        self._append(out, idx, self.active, True)                                     # rrt.py:74-79
+        if est is None:
+            self._append(out, idx, self.active, True)                                 # rrt.py:74-79
+        else:
+            n_before = f.n_nodes.clone()
+            self._append(out, idx, self.active, 2)                                    # rrt.py:74-77
+            ridx, rcost = ops.estimator_choose_parent(self.env.handle, est.handle, f.states, f.n_nodes,
+                                                      self.goals, max_nodes=min(f.cap, bound + 2 * (self.per - 1)),
+                                                      first_node=n_before)             # rrt.py:78
+            check(lib().crlk_rrt_retry_choice(C.byref(self._fv), p(n_before), p(ridx), p(rcost), p(self.active),
+                                              self.Q, 5.0, self.max_iter, p(self.iters), p(self.done),
+                                              p(self.retry_active), p(self.retry_from), p(self.retry_parent),
+                                              ops._stream()))                          # rrt.py:79
         out2 = self._extend(1, self.retry_from, self.goals, self.retry_active)        # rrt.py:80
         self._append(out2, self.retry_parent, self.retry_active, False)               # rrt.py:81-83
         self.rounds += 1

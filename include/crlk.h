@@ -231,11 +231,13 @@ int crlk_estimator_forward(const CrlkEstimator *e, const float *obs, int32_t ld_
  * observation built and scored by both CNNs: cost = (est + 1) * 15 + 100 * (1 - round(prob));
  * other nodes keep the distance as cost; first minimum.  (0, 100) when no node passes the filter.
  *   states dev f64[Q x stride x 5] node tables, n_nodes dev i32[Q], targets dev f64[Q x 5]
+ *   first_node dev i32[Q] (nullable): the candidate list of query q is nodes [first_node[q], n_nodes[q])
+ *              (the `new_node_list` of rrt.py:78); idx stays an index into the whole tree
  *   idx dev i32[Q], cost dev f64[Q]; workspace: crlk_estimator_cp_workspace_bytes(Q, max_nodes). */
 int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstimator *e, const double *states,
-                                 int64_t stride, const int32_t *n_nodes, int32_t max_nodes,
-                                 const double *targets, int32_t Q, int32_t *idx, double *cost,
-                                 void *workspace, void *stream);
+                                 int64_t stride, const int32_t *n_nodes, const int32_t *first_node,
+                                 int32_t max_nodes, const double *targets, int32_t Q, int32_t *idx,
+                                 double *cost, void *workspace, void *stream);
 int64_t crlk_estimator_cp_workspace_bytes(int32_t Q, int32_t max_nodes);
 
 /* ---- planner bookkeeping on the device: RRT.planning (planner/rrt.py:51-89) ---- */
@@ -274,14 +276,25 @@ int crlk_rrt_select(const uint8_t *valid, const double *dist, int32_t Q, int32_t
  * when primary != 0 -- choose the new node nearest to the goal for the retry
  * extension (rrt.py:78-80: cost < retry_radius).  first_has_start: 0 for the DWA
  * steer (the first segment's Node.path lacks the start state, rrt.py:102-104),
- * 1 for the RL steer (rrt_rl.py:27).  overflow (dev i32[1]) counts trees that
- * ran out of node or pool capacity (those queries are stopped and reported). */
+ * 1 for the RL steer (rrt_rl.py:27).  primary == 2: a primary pass whose retry choice is made by
+ * the caller with its own choose_parent (RRT_RL_Estimator) and handed in through
+ * crlk_rrt_retry_choice.  overflow (dev i32[1]) counts trees that ran out of node or pool capacity
+ * (those queries are stopped and reported). */
 int crlk_rrt_append(const CrlkForestView *forest, const CrlkExtendView *ext, const int32_t *parent_idx,
                     const uint8_t *active, const double *goals, int32_t Q, int32_t n_max_extend,
                     int32_t n_tree, int32_t first_has_start, int32_t primary, int32_t max_iter,
                     double goal_radius, double retry_radius, const int32_t *iters, uint8_t *done,
                     uint8_t *reached, uint8_t *retry_active, double *retry_from, int32_t *retry_parent,
                     int32_t *overflow, void *stream);
+
+/* Retry decision after a crlk_rrt_append(primary = 2): n_before dev i32[Q] = n_nodes before that
+ * append; (idx, cost) dev = choose_parent(new nodes, goal) (rrt.py:78); a query retries from node
+ * idx iff it appended nodes, is not done and cost < retry_radius (rrt.py:79); otherwise it is
+ * finished when its iterations are used up. */
+int crlk_rrt_retry_choice(const CrlkForestView *forest, const int32_t *n_before, const int32_t *idx,
+                          const double *cost, const uint8_t *active, int32_t Q, double retry_radius,
+                          int32_t max_iter, const int32_t *iters, uint8_t *done, uint8_t *retry_active,
+                          double *retry_from, int32_t *retry_parent, void *stream);
 
 /* ---- gym side of the env: DifferentialDriveGym.step (env/differential_gym.py:136-178) ---- */
 

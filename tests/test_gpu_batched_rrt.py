@@ -200,3 +200,29 @@ def test_rrt_rl_estimator_class_reproduces_reference_run():
     _check_rl_tree(states, parents, path, g, "rl_est")
     assert p.n_control_steps == len(g["rl_est_noise"])
     assert next(it, None) is None                                      # every recorded sample was consumed
+
+
+@pytest.mark.parametrize("copies", (1, 3))
+def test_batched_rrt_estimator_reproduces_reference_run(copies):
+    """RRT_RL_Estimator.planning (learned parent selection for the sample AND for the retry, policy
+    steering, eps = 0.05) for several queries in lock step: every copy of the recorded query rebuilds
+    the reference's tree from the recorded sample and noise streams."""
+    from crl_kino_b200.estimator import load_estimator
+    from crl_kino_b200.planner.batched import BatchedRRT
+    g = golden("plan_rl")
+    w = golden("estimator_weights")
+    est = load_estimator({k[4:]: w[k] for k in w.files if k.startswith("est.")},
+                         {k[4:]: w[k] for k in w.files if k.startswith("cls.")})
+    env, _ = make_envs(fixture_map("test_env1"))
+    start = np.tile(np.array([[-5, -15, 0, 0, 0.0]]), (copies, 1))
+    goal = np.tile(np.array([[10, 10, 0, 0, 0.0]]), (copies, 1))
+    p = BatchedRRT(env, start, goal, max_iter=int(g["rl_est_max_iter"]), policy=_policy(int(g["seed"])), eps=0.05,
+                   estimator=est)
+    noise = np.concatenate([g["rl_est_noise"], np.zeros((128, 2), dtype=np.float32)])[None]
+    samples = np.concatenate([g["rl_est_samples"], np.tile(goal[:1], (8, 1))])[None]
+    reached = p.plan(np.tile(samples, (copies, 1, 1)), check_every=4, noise=np.tile(noise, (copies, 1, 1)))
+    for q in range(copies):
+        states, parents = p.tree(q)
+        _check_rl_tree(states, parents, p.final_course(q), g, "rl_est")
+        assert int(p.noise_cursor[q].item()) == len(g["rl_est_noise"])
+        assert bool(reached[q]) == bool(g["rl_est_reach"])
