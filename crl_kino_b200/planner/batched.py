@@ -111,6 +111,54 @@ class BatchedExtender:
         torch.cuda.current_stream().synchronize()
         return {k: h.numpy() for k, h in self._h_out.items()}
 
+    # ---- pipelined host-buffer entry points ------------------------------------------
+    def _pipe_init(self):
+        d = self.forest.x.device
+        self._pipe = []
+        for _ in range(2):
+            self._pipe.append(dict(
+                h_in=torch.empty_like(self._h_samples).pin_memory(), d_in=torch.empty_like(self._d_samples),
+                h_out={k: torch.empty_like(v).pin_memory() for k, v in self._h_out.items()},
+                out=None, from_states=torch.empty_like(self.from_states),
+                done=torch.cuda.Event(), copied=torch.cuda.Event(), busy=False))
+        self._copy_stream = torch.cuda.Stream(device=d)
+        self._slot = 0
+
+    def submit_host(self, samples_np):
+        """Asynchronous form of step_host: stages the samples (pinned) and enqueues H2D, the step and the
+        D2H of its results; returns a ticket for collect().  Two steps may be in flight, so the D2H of one
+        step overlaps the kernels of the next.  Every step still moves its own inputs and results."""
+        if not hasattr(self, "_pipe"):
+            self._pipe_init()
+        i = self._slot
+        self._slot ^= 1
+        s = self._pipe[i]
+        if s["busy"]:
+            s["copied"].synchronize()              # the slot's previous results must have been collected / copied
+        s["h_in"].numpy()[...] = samples_np
+        s["d_in"].copy_(s["h_in"], non_blocking=True)
+        keep_out, keep_from = self.out, self.from_states
+        self.out, self.from_states = s["out"], s["from_states"]
+        out = self.step(s["d_in"])
+        s["out"] = out
+        self.out, self.from_states = keep_out, keep_from
+        s["done"].record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(s["done"])
+            for k, h in s["h_out"].items():
+                h.copy_(out[k], non_blocking=True)
+            s["copied"].record()
+        s["busy"] = True
+        return i
+
+    def collect(self, ticket):
+        """Results of a submit_host() call as numpy views of pinned memory (valid until the slot is reused
+        two submissions later)."""
+        s = self._pipe[ticket]
+        s["copied"].synchronize()
+        s["busy"] = False
+        return {k: h.numpy() for k, h in s["h_out"].items()}
+
     def h2d_bytes(self):
         return self._h_samples.numel() * 8
 

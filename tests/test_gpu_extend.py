@@ -136,3 +136,37 @@ def test_rrt_api_errors():
         p.planning()
     with pytest.raises(AssertionError):
         p.set_start_and_goal(np.array([0, -21.0, 0, 0, 0]), np.array([10, 10, 0, 0, 0.0]))
+
+
+def test_pipelined_host_api_equals_synchronous():
+    """BatchedExtender.submit_host / collect (two steps in flight) returns, step for step, the same
+    arrays as step_host."""
+    from crl_kino_b200 import ops
+    from crl_kino_b200.planner.batched import BatchedExtender, Forest
+    from crl_kino_b200.policy.dwa import DWA
+    from crl_kino_b200.workloads import dense_map, free_states, random_states
+    env, o = make_envs(dense_map(n_cells=2000, seed=3))
+    rng = np.random.default_rng(8)
+    Q, N = 96, 64
+    nodes = free_states(lambda c: o.valid_state_batch(c)[1], rng, Q * N, 0.5)
+    nodes[:, 3:] = 0
+    forest = Forest(Q, N)
+    forest.fill(nodes.reshape(Q, N, 5))
+    d = DWA(env)
+    d.set_dwa(dt=0.2, v_res=0.05, w_res=0.2)
+    ext = BatchedExtender(env, forest, dwa=d)
+    batches = [random_states(rng, Q, moving=True) for _ in range(5)]
+    sync = [{k: v.copy() for k, v in ext.step_host(b).items()} for b in batches]
+    got, pending = [], None
+    for b in batches:
+        t = ext.submit_host(b)
+        if pending is not None:
+            got.append({k: v.copy() for k, v in ext.collect(pending).items()})
+        pending = t
+    got.append({k: v.copy() for k, v in ext.collect(pending).items()})
+    for a, b in zip(sync, got):
+        ns = a["n_steps"]
+        for k in ("n_steps", "status", "n_nodes", "nearest_idx", "flags"):
+            assert np.array_equal(a[k], b[k]), k
+        for q in range(Q):
+            assert np.array_equal(a["path"][q, :ns[q]], b["path"][q, :ns[q]])
