@@ -1258,13 +1258,15 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose 
     float px = (float)x, py = (float)y;
     float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
     float thr2 = thr * thr;
+    const float cf = (float)g.c, sf = (float)g.s;
+    const float cthr = (float)(CRLK_COLLISION_DIS + 2.0 * CRLK_NEAR_EPS);   // farther than this: not even marginal
     bool coll = false, definite = false, marginal = false;
     // each thread screens its share of the cell lists and tests its survivors at once
     // (a pose touches a few hundred listed obstacles at most: <= 1-2 per thread)
     grid_visit(os, px, py, thr, tid, T, [&](int o, bool in) {
         if (!in) return;
         float4 r = __ldg(&rects[o]);
-        if (aabb_center_d2(r, px, py) <= thr2) {
+        if (aabb_center_d2(r, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, r) <= cthr) {
             bool d, m;
             coll |= dis2obs_exact(e, g, r, d, m) < 0.0;
             definite |= d; marginal |= m;
