@@ -727,8 +727,11 @@ k_rl_step(EnvP e, ExtP x, ObsSet os, const double *__restrict__ targets,
     const float4 *__restrict__ rects = os.rects;
     bool coll = false, definite = false, marginal = false;
     int count = 0;
+    const float cf = (float)g.c, sf = (float)g.s;
+    const float lbthr = (float)(CRLK_COLLISION_DIS + 2.0 * CRLK_NEAR_EPS);
     grid_visit(os, px, py, thr, lane, 32, [&](int o, bool in) {
-        bool keep = in && aabb_center_d2(__ldg(&rects[in ? o : 0]), px, py) <= thr2;
+        const float4 rr = __ldg(&rects[in ? o : 0]);
+        bool keep = in && aabb_center_d2(rr, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, rr) <= lbthr;
         unsigned mask = __ballot_sync(0xffffffffu, keep);
         if (mask) {
             int pos = count + __popc(mask & ((1u << lane) - 1u));
