@@ -289,12 +289,14 @@ __device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py,
     }
 }
 
-// get_clearance (differential_env.py:126-132) for one pose by ONE thread: a
-// growing box of grid cells around the pose is screened in FP32 against the
-// best exact distance found so far; the search stops as soon as the box covers
-// every obstacle that could still beat it (centre distance < best + rc).
-// Returns min(100, min distance), or -1 on collision -- the same value as the
-// scan over all obstacles.
+// get_clearance (differential_env.py:126-132) for one pose by ONE thread.  The grid cells are
+// visited ring by ring around the pose's own cell (Chebyshev rings 0, 1, 2, ...): everything listed
+// only in ring k or beyond lies at least (k - 1) cells away, so the search stops as soon as that
+// distance exceeds best + rc.  An obstacle listed in several cells is handled exactly once, in the
+// cell that holds its point closest to the pose (which is also the first ring that reaches it).
+// Each obstacle passes two FP32 screens (body origin to the solid rectangle, footprint to the
+// obstacle's bounding circle) before the exact FP64 test.  Returns min(100, min distance), or -1 on
+// collision -- the same value as the scan over all obstacles.
 static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const ObsSet &os, double x, double y,
                                                      double th, bool *definite_out, bool *marginal_out)
 {
@@ -303,37 +305,45 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
     const float px = (float)x, py = (float)y;
     const float cf = (float)g.c, sf = (float)g.s;
     const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
+    const float cell = 1.0f / os.ginv;
+    auto cellx = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gx0) * os.ginv), 0.f), hx); };
+    auto celly = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gy0) * os.ginv), 0.f), hy); };
+    const int cx0 = cellx(px), cy0 = celly(py);
     double best = CRLK_CLEARANCE_CAP;
     bool definite = false, marginal = false;
-    float r = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
-    for (;;) {
-        float rr = r + 2e-3f;
-        int cx0 = (int)fminf(fmaxf(floorf((px - rr - os.gx0) * os.ginv), 0.f), hx);
-        int cx1 = (int)fminf(fmaxf(floorf((px + rr - os.gx0) * os.ginv), 0.f), hx);
-        int cy0 = (int)fminf(fmaxf(floorf((py - rr - os.gy0) * os.ginv), 0.f), hy);
-        int cy1 = (int)fminf(fmaxf(floorf((py + rr - os.gy0) * os.ginv), 0.f), hy);
-        for (int cy = cy0; cy <= cy1; cy++) {
-            int s = __ldg(&os.cell_start[cy * os.ncx + cx0]);
-            int en = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
-            for (int k = s; k < en; k++) {
-                float4 o = __ldg(&os.rects[__ldg(&os.cell_items[k])]);
-                const float bf = (float)fmax(best, 0.0) * 1.0001f;
-                const float lim = bf + e.rc + CRLK_CULL_MARGIN;
-                // two FP32 screens: body origin to the solid obstacle, then the footprint itself to the
-                // obstacle's bounding circle; only obstacles that can still beat `best` are tested exactly
-                if (aabb_center_d2(o, px, py) <= lim * lim && footprint_lb(e, cf, sf, px, py, o) <= bf) {
-                    bool dd, mm;
-                    double dis = dis2obs_exact(e, g, o, dd, mm);
-                    definite |= dd; marginal |= mm;
-                    best = fmin(best, dis);
-                }
+    float bf = (float)best * 1.0001f;                       // float upper bound of the best distance so far
+    float lim = bf + e.rc + CRLK_CULL_MARGIN;               // body origin farther than this: cannot beat it
+    const int kmax = max(max(cx0, os.ncx - 1 - cx0), max(cy0, os.ncy - 1 - cy0));
+    auto visit = [&](int cx, int cy) {
+        const int c = cy * os.ncx + cx;
+        const int s = __ldg(&os.cell_start[c]), en = __ldg(&os.cell_start[c + 1]);
+        for (int k = s; k < en; k++) {
+            const float4 o = __ldg(&os.rects[__ldg(&os.cell_items[k])]);
+            const float qx = fminf(fmaxf(px, o.x), o.z), qy = fminf(fmaxf(py, o.y), o.w);   // closest point of the AABB
+            const float dx = px - qx, dy = py - qy;
+            if (dx * dx + dy * dy > lim * lim) continue;
+            if (cellx(qx) != cx || celly(qy) != cy) continue;            // handled from another cell
+            if (footprint_lb(e, cf, sf, px, py, o) > bf) continue;
+            bool dd, mm;
+            const double dis = dis2obs_exact(e, g, o, dd, mm);
+            definite |= dd; marginal |= mm;
+            if (dis < best) {
+                best = dis;
+                bf = (float)fmax(best, 0.0) * 1.0001f;
+                lim = bf + e.rc + CRLK_CULL_MARGIN;
             }
         }
-        if (best < 0.0) break;
-        float need = (float)best * 1.0001f + e.rc + CRLK_CULL_MARGIN;
-        bool whole = (cx0 == 0 && cy0 == 0 && cx1 == os.ncx - 1 && cy1 == os.ncy - 1);
-        if (need <= r || whole) break;
-        r = fminf(need, 2.0f * r);
+    };
+    for (int k = 0; k <= kmax && best >= 0.0; k++) {
+        if (k >= 1 && (float)(k - 1) * cell > lim + 2e-3f) break;
+        if (k == 0) { visit(cx0, cy0); continue; }
+        const int xl = cx0 - k, xr = cx0 + k, yb = cy0 - k, yt = cy0 + k;
+        const int xa = max(xl, 0), xb = min(xr, os.ncx - 1);
+        if (yb >= 0) for (int cx = xa; cx <= xb && best >= 0.0; cx++) visit(cx, yb);
+        if (yt < os.ncy) for (int cx = xa; cx <= xb && best >= 0.0; cx++) visit(cx, yt);
+        const int ya = max(yb + 1, 0), yc = min(yt - 1, os.ncy - 1);
+        if (xl >= 0) for (int cy = ya; cy <= yc && best >= 0.0; cy++) visit(xl, cy);
+        if (xr < os.ncx) for (int cy = ya; cy <= yc && best >= 0.0; cy++) visit(xr, cy);
     }
     if (definite_out) *definite_out = definite;
     if (marginal_out) *marginal_out = marginal;
