@@ -297,8 +297,11 @@ __device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py,
 // Each obstacle passes two FP32 screens (body origin to the solid rectangle, footprint to the
 // obstacle's bounding circle) before the exact FP64 test.  Returns min(100, min distance), or -1 on
 // collision -- the same value as the scan over all obstacles.
+// `bound`: only distances below it matter to the caller (a running minimum); the result is then
+// min(bound, clearance), found without looking at obstacles that cannot get under the bound.
 static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const ObsSet &os, double x, double y,
-                                                     double th, bool *definite_out, bool *marginal_out)
+                                                     double th, bool *definite_out, bool *marginal_out,
+                                                     double bound = CRLK_CLEARANCE_CAP)
 {
     RobotPose g;
     robot_pose_setup(e, x, y, th, g);
@@ -309,7 +312,7 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
     auto cellx = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gx0) * os.ginv), 0.f), hx); };
     auto celly = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gy0) * os.ginv), 0.f), hy); };
     const int cx0 = cellx(px), cy0 = celly(py);
-    double best = CRLK_CLEARANCE_CAP;
+    double best = fmin(bound, CRLK_CLEARANCE_CAP);
     bool definite = false, marginal = false;
     float bf = (float)best * 1.0001f;                       // float upper bound of the best distance so far
     float lim = bf + e.rc + CRLK_CULL_MARGIN;               // body origin farther than this: cannot beat it

@@ -858,9 +858,9 @@ struct DwaResult {
 
 // get_clearance for one pose by one thread (used only when use_clearance = 1).
 __device__ __forceinline__ double clearance_thread(const EnvP &e, const ObsSet &os, double x, double y,
-                                                   double th)
+                                                   double th, double bound = CRLK_CLEARANCE_CAP)
 {
-    return clearance_grid_thread(e, os, x, y, th, nullptr, nullptr);
+    return clearance_grid_thread(e, os, x, y, th, nullptr, nullptr, bound);
 }
 
 // DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
@@ -1004,7 +1004,9 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                         y = y + vt[k] * ws[k * nwm] * dt;
                     }
                 if (row % d.skip == 0) {
-                    double dis = pymax(clearance_thread(e, os, x, y, sm.wth[j * d.n_outer + row - 1]),
+                    // only a clearance below the running minimum changes it (dwa.py:67-68), so the
+                    // search is told to ignore everything farther than that
+                    double dis = pymax(clearance_thread(e, os, x, y, sm.wth[j * d.n_outer + row - 1], min_dis),
                                        0.001);
                     min_dis = pymin(dis, min_dis);
                 }
