@@ -299,7 +299,9 @@ __device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py,
 // collision -- the same value as the scan over all obstacles.
 // `bound`: only distances below it matter to the caller (a running minimum); the result is then
 // min(bound, clearance), found without looking at obstacles that cannot get under the bound.
-static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const ObsSet &os, double x, double y,
+// This version runs the exact FP64 test on every obstacle that passes the screens (the slow but
+// unconditional path; clearance_grid_thread below falls back to it).
+static __device__ __noinline__ double clearance_grid_exact(const EnvP &e, const ObsSet &os, double x, double y,
                                                      double th, bool *definite_out, bool *marginal_out,
                                                      double bound = CRLK_CLEARANCE_CAP)
 {
@@ -348,6 +350,159 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
         if (xl >= 0) for (int cy = ya; cy <= yc && best >= 0.0; cy++) visit(xl, cy);
         if (xr < os.ncx) for (int cy = ya; cy <= yc && best >= 0.0; cy++) visit(xr, cy);
     }
+    if (definite_out) *definite_out = definite;
+    if (marginal_out) *marginal_out = marginal;
+    return (best < 0.0) ? -1.0 : best;
+}
+
+
+// ---- float32 mirror of dis2obs_exact: the same tests and formulas in single precision.  Used only
+// to rank obstacles; every value that is reported comes from the float64 routine.
+struct RobotPoseF {
+    float x, y, c, s;
+    float wx[4], wy[4];
+};
+
+__device__ __forceinline__ bool seg_hits_aabb_f(float sx, float sy, float gx, float gy, float l, float b, float r,
+                                                float t)
+{
+    float dx = gx - sx, dy = gy - sy;
+    float fx = (dx == 0.0f) ? 1e30f : __frcp_rn(dx);
+    float fy = (dy == 0.0f) ? 1e30f : __frcp_rn(dy);
+    float t1 = (l - sx) * fx, t2 = (r - sx) * fx;
+    float t3 = (b - sy) * fy, t4 = (t - sy) * fy;
+    float tmin = fmaxf(fminf(t1, t2), fminf(t3, t4));
+    float tmax = fminf(fmaxf(t1, t2), fmaxf(t3, t4));
+    return (tmax >= 0.0f) && (tmin <= tmax) && (tmin <= 1.0f);
+}
+
+__device__ __forceinline__ float point_rect_boundary_d2_f(float px, float py, float l, float b, float r, float t)
+{
+    float ex = fmaxf(fmaxf(l - px, px - r), 0.0f);
+    float ey = fmaxf(fmaxf(b - py, py - t), 0.0f);
+    float in = fminf(fminf(px - l, r - px), fminf(py - b, t - py));
+    return (in > 0.0f) ? in * in : ex * ex + ey * ey;
+}
+
+__device__ __forceinline__ float dis2obs_f32(const EnvP &e, const RobotPoseF &g, float4 o)
+{
+    if (e.radius > 0.0) {
+        if (g.x >= o.x && g.x <= o.z && g.y >= o.y && g.y <= o.w) return -1.0f;
+        float dc = sqrtf(point_rect_boundary_d2_f(g.x, g.y, o.x, o.y, o.z, o.w)) - (float)e.radius;
+        return (dc > (float)CRLK_COLLISION_DIS) ? dc : -1.0f;
+    }
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        hit |= seg_hits_aabb_f(g.wx[i], g.wy[i], g.wx[j], g.wy[j], o.x, o.y, o.z, o.w);
+    }
+    if (hit) return -1.0f;
+    float d2 = 1e30f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d2 = fminf(d2, point_rect_boundary_d2_f(g.wx[i], g.wy[i], o.x, o.y, o.z, o.w));
+    const float ox[4] = {o.x, o.x, o.z, o.z}, oy[4] = {o.y, o.w, o.w, o.y};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float qx = ox[i] - g.x, qy = oy[i] - g.y;
+        float px = g.c * qx + g.s * qy, py = g.c * qy - g.s * qx;
+        d2 = fminf(d2, point_rect_boundary_d2_f(px, py, e.rl, e.rb, e.rr, e.rt));
+    }
+    float dis = sqrtf(d2);
+    return (dis > (float)CRLK_COLLISION_DIS) ? dis : -1.0f;
+}
+
+#define CLR_EPS 2e-4f      // bound of |float32 distance - float64 distance| used below (coordinates are O(50))
+#define CLR_CAND 12
+
+// get_clearance for one pose by ONE thread, float32 ranking + float64 verdict.  The ring search of
+// clearance_grid_exact, but an obstacle that passes the two screens is first measured in float32;
+// the thread only remembers the obstacles whose float32 distance is within 2 eps of the smallest
+// one seen (the exact minimum is necessarily among them) and runs the float64 test on those few at
+// the very end -- where all threads of a warp are at the same instruction again, instead of each
+// lane dragging the whole warp through a float64 test at a different moment of its scan.
+// Falls back to clearance_grid_exact when the candidate list overflows (many obstacles at the same
+// distance) or when float32 saw a collision that float64 does not confirm.
+static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const ObsSet &os, double x, double y,
+                                                     double th, bool *definite_out, bool *marginal_out,
+                                                     double bound = CRLK_CLEARANCE_CAP)
+{
+    RobotPose g;
+    robot_pose_setup(e, x, y, th, g);
+    RobotPoseF gf;
+    gf.x = (float)g.x; gf.y = (float)g.y; gf.c = (float)g.c; gf.s = (float)g.s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { gf.wx[i] = (float)g.wx[i]; gf.wy[i] = (float)g.wy[i]; }
+    const float px = gf.x, py = gf.y, cf = gf.c, sf = gf.s;
+    const float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
+    const float cell = 1.0f / os.ginv;
+    auto cellx = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gx0) * os.ginv), 0.f), hx); };
+    auto celly = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gy0) * os.ginv), 0.f), hy); };
+    const int cx0 = cellx(px), cy0 = celly(py);
+    const double b0 = fmin(bound, CRLK_CLEARANCE_CAP);
+    float min32 = (float)b0 * 1.000001f + CLR_EPS;          // float32 view of the bound, rounded up
+    int cid[CLR_CAND];
+    float cd[CLR_CAND];
+    int nc = 0;
+    bool overflow = false, stop = false;
+    float bf = fmaxf(min32, 0.0f) + 2.0f * CLR_EPS;         // candidates have a float32 distance <= bf
+    float lim = bf + e.rc + CRLK_CULL_MARGIN;
+    const int kmax = max(max(cx0, os.ncx - 1 - cx0), max(cy0, os.ncy - 1 - cy0));
+    auto visit = [&](int cx, int cy) {
+        const int c = cy * os.ncx + cx;
+        const int s = __ldg(&os.cell_start[c]), en = __ldg(&os.cell_start[c + 1]);
+        for (int k = s; k < en; k++) {
+            const int id = __ldg(&os.cell_items[k]);
+            const float4 o = __ldg(&os.rects[id]);
+            const float qx = fminf(fmaxf(px, o.x), o.z), qy = fminf(fmaxf(py, o.y), o.w);   // closest point of the AABB
+            const float dx = px - qx, dy = py - qy;
+            if (dx * dx + dy * dy > lim * lim) continue;
+            if (cellx(qx) != cx || celly(qy) != cy) continue;            // handled from another cell
+            if (footprint_lb(e, cf, sf, px, py, o) > bf) continue;
+            const float d = dis2obs_f32(e, gf, o);
+            if (d > min32 + 2.0f * CLR_EPS) continue;
+            if (d < 0.0f) {
+                // float32 sees a collision: nothing can rank below it; let float64 confirm this one
+                cid[0] = id; cd[0] = d; nc = 1; min32 = d; stop = true;
+                return;
+            }
+            if (d < min32) {
+                // new smallest float32 distance: drop the remembered obstacles that are now out of range
+                min32 = d;
+                int m = 0;
+                for (int q = 0; q < nc; q++)
+                    if (cd[q] <= d + 2.0f * CLR_EPS) { cid[m] = cid[q]; cd[m] = cd[q]; m++; }
+                nc = m;
+                bf = fmaxf(min32, 0.0f) + 2.0f * CLR_EPS;
+                lim = bf + e.rc + CRLK_CULL_MARGIN;
+            }
+            if (nc < CLR_CAND) { cid[nc] = id; cd[nc] = d; nc++; }
+            else overflow = true;
+        }
+    };
+    for (int k = 0; k <= kmax && !overflow && !stop; k++) {
+        if (k >= 1 && (float)(k - 1) * cell > lim + 2e-3f) break;
+        if (k == 0) { visit(cx0, cy0); continue; }
+        const int xl = cx0 - k, xr = cx0 + k, yb = cy0 - k, yt = cy0 + k;
+        const int xa = max(xl, 0), xb = min(xr, os.ncx - 1);
+        if (yb >= 0) for (int cx = xa; cx <= xb && !stop; cx++) visit(cx, yb);
+        if (yt < os.ncy) for (int cx = xa; cx <= xb && !stop; cx++) visit(cx, yt);
+        const int ya = max(yb + 1, 0), yc = min(yt - 1, os.ncy - 1);
+        if (xl >= 0) for (int cy = ya; cy <= yc && !stop; cy++) visit(xl, cy);
+        if (xr < os.ncx) for (int cy = ya; cy <= yc && !stop; cy++) visit(xr, cy);
+    }
+    // float64 verdict on the remembered obstacles (all lanes of the warp arrive here together)
+    double best = b0;
+    bool definite = false, marginal = false, confirmed = false;
+    for (int q = 0; q < nc; q++) {
+        bool dd, mm;
+        const double dis = dis2obs_exact(e, g, __ldg(&os.rects[cid[q]]), dd, mm);
+        definite |= dd; marginal |= mm;
+        confirmed |= (dis < 0.0);
+        best = fmin(best, dis);
+    }
+    if (overflow || (min32 < 0.0f && !confirmed))
+        return clearance_grid_exact(e, os, x, y, th, definite_out, marginal_out, bound);
     if (definite_out) *definite_out = definite;
     if (marginal_out) *marginal_out = marginal;
     return (best < 0.0) ? -1.0 : best;
