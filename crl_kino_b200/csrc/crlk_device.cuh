@@ -480,16 +480,20 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
             else overflow = true;
         }
     };
+    // one loop over the cells of ring 0, 1, 2, ... in spiral order with a single visit site, so that
+    // the lanes of a warp (each on its own pose) meet again at every cell instead of drifting apart
+    // through four separate edge loops
     for (int k = 0; k <= kmax && !overflow && !stop; k++) {
         if (k >= 1 && (float)(k - 1) * cell > lim + 2e-3f) break;
-        if (k == 0) { visit(cx0, cy0); continue; }
-        const int xl = cx0 - k, xr = cx0 + k, yb = cy0 - k, yt = cy0 + k;
-        const int xa = max(xl, 0), xb = min(xr, os.ncx - 1);
-        if (yb >= 0) for (int cx = xa; cx <= xb && !stop; cx++) visit(cx, yb);
-        if (yt < os.ncy) for (int cx = xa; cx <= xb && !stop; cx++) visit(cx, yt);
-        const int ya = max(yb + 1, 0), yc = min(yt - 1, os.ncy - 1);
-        if (xl >= 0) for (int cy = ya; cy <= yc && !stop; cy++) visit(xl, cy);
-        if (xr < os.ncx) for (int cy = ya; cy <= yc && !stop; cy++) visit(xr, cy);
+        const int ncell = (k == 0) ? 1 : 8 * k;
+        int dx = -k, dy = -k, sx = 1, sy = 0, run = 0;
+        for (int t = 0; t < ncell && !stop; t++) {
+            const int cx = cx0 + dx, cy = cy0 + dy;
+            if (cx >= 0 && cx < os.ncx && cy >= 0 && cy < os.ncy) visit(cx, cy);
+            // walk the ring: bottom edge left to right, right edge upwards, top edge right to left, left edge down
+            dx += sx; dy += sy;
+            if (++run == 2 * k) { run = 0; const int tx = sx; sx = -sy; sy = tx; }
+        }
     }
     // float64 verdict on the remembered obstacles (all lanes of the warp arrive here together)
     double best = b0;
