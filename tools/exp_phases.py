@@ -7,14 +7,16 @@ from crl_kino_b200.env import DifferentialDriveEnv
 from crl_kino_b200.policy.dwa import DWA
 from crl_kino_b200.workloads import DENSE_DWA, dense_map, free_states
 rects = dense_map(); env = DifferentialDriveEnv(1.0,-0.1,np.pi,1.0,np.pi); env.set_obs(rects)
-dwa = DWA(env); dwa.set_dwa(**DENSE_DWA); dp = dwa.params(); xp = ops.extend_params()
+dwa = DWA(env); dwa.set_dwa(**DENSE_DWA)
+if os.environ.get('USE_CLEARANCE'): dwa.set_dwa(use_clearance=True)
+dp = dwa.params(); xp = ops.extend_params()
 rng = np.random.default_rng(0)
 clr = lambda c: env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
 cand = free_states(clr, rng, 4000, 2.5); cand[:, 3:] = 0
 tg = cand.copy(); ang = rng.uniform(-np.pi, np.pi, len(cand)); tg[:, 0] += 15*np.cos(ang); tg[:, 1] += 15*np.sin(ang)
 names = ["wait-prev", "tables", "rollouts+sums", "f:warp0-reduce", "f:cost", "costs+argmin", "f:row1", "f:closing-barrier", "collision", "f:epilogue"]
 raw = ctypes.CDLL(lib()._name)
-for Q in (1, 444, 1776):
+for Q in ((1, 296) if os.environ.get('USE_CLEARANCE') else (1, 444, 1776)):
     f, g = ops.as_dev(cand[:Q]), ops.as_dev(tg[:Q])
     buf = (ctypes.c_ulonglong * 16)()
     ops.extend_dwa(env.handle, dp, xp, f, g); torch.cuda.synchronize()
