@@ -512,6 +512,64 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
     return (best < 0.0) ? -1.0 : best;
 }
 
+// get_clearance against a short list of obstacles in shared memory (the per-rollout clearance term:
+// every pose of a control step lies within the prediction horizon of the current state, so the block
+// gathers the obstacles that can matter once and each thread then loops over that list -- the same
+// trip count in every lane, no grid walk, no global loads).  `list` must hold every obstacle whose
+// rectangle is closer than bound + rc to the pose's body origin.  Same float32 ranking / float64
+// verdict as clearance_grid_thread; returns a negative NaN-free sentinel (-2) when the caller has to
+// fall back to the grid search (candidate overflow, unconfirmed float32 collision).
+static __device__ __noinline__ double clearance_from_list(const EnvP &e, const float4 *list, int n, double x,
+                                                          double y, double cs, double sn, double bound)
+{
+    RobotPose g;
+    robot_pose_from_cs(e, x, y, cs, sn, g);
+    RobotPoseF gf;
+    gf.x = (float)g.x; gf.y = (float)g.y; gf.c = (float)g.c; gf.s = (float)g.s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { gf.wx[i] = (float)g.wx[i]; gf.wy[i] = (float)g.wy[i]; }
+    const float px = gf.x, py = gf.y;
+    const double b0 = fmin(bound, CRLK_CLEARANCE_CAP);
+    float min32 = (float)b0 * 1.000001f + CLR_EPS;
+    int cid[CLR_CAND];
+    float cd[CLR_CAND];
+    int nc = 0;
+    bool overflow = false;
+    float bf = fmaxf(min32, 0.0f) + 2.0f * CLR_EPS;
+    float lim = bf + e.rc + CRLK_CULL_MARGIN;
+    for (int k = 0; k < n; k++) {
+        const float4 o = list[k];
+        const float qx = fminf(fmaxf(px, o.x), o.z), qy = fminf(fmaxf(py, o.y), o.w);
+        const float dx = px - qx, dy = py - qy;
+        if (dx * dx + dy * dy > lim * lim) continue;
+        if (footprint_lb(e, gf.c, gf.s, px, py, o) > bf) continue;
+        const float d = dis2obs_f32(e, gf, o);
+        if (d > min32 + 2.0f * CLR_EPS) continue;
+        if (d < 0.0f) { cid[0] = k; cd[0] = d; nc = 1; min32 = d; break; }
+        if (d < min32) {
+            min32 = d;
+            int m = 0;
+            for (int q = 0; q < nc; q++)
+                if (cd[q] <= d + 2.0f * CLR_EPS) { cid[m] = cid[q]; cd[m] = cd[q]; m++; }
+            nc = m;
+            bf = fmaxf(min32, 0.0f) + 2.0f * CLR_EPS;
+            lim = bf + e.rc + CRLK_CULL_MARGIN;
+        }
+        if (nc < CLR_CAND) { cid[nc] = k; cd[nc] = d; nc++; }
+        else { overflow = true; break; }
+    }
+    double best = b0;
+    bool confirmed = false;
+    for (int q = 0; q < nc; q++) {
+        bool dd, mm;
+        const double dis = dis2obs_exact(e, g, list[cid[q]], dd, mm);
+        confirmed |= (dis < 0.0);
+        best = fmin(best, dis);
+    }
+    if (overflow || (min32 < 0.0f && !confirmed)) return -2.0;
+    return (best < 0.0) ? -1.0 : best;
+}
+
 // ------------------------------------------------ local occupancy map (R9)
 
 #define OBS_NPTS 729

@@ -734,6 +734,8 @@ extern "C" int crlk_debug_atan2(const double *y, const double *x, int32_t n, dou
     return CRLK_OK;
 }
 
+#define CL_CAP 1024      // capacity of the per-control-step obstacle list of the clearance term
+
 struct DwaSmem {
     double *c0, *c1;
     double *vtab, *vlast, *c2n;
@@ -746,6 +748,8 @@ struct DwaSmem {
     int *ihdr;                        // [4]  nv nw
     RobotPose *pose;                  // footprint of the state the next validity test looks at
     double *atab;                     // atan coefficient table (crlk_atan2)
+    float4 *clist;                    // [CL_CAP] obstacles that can matter to this control step's clearance term
+    int *cl_n;                        // [2] list length (> CL_CAP: overflow, use the grid search), spare
     double *scal;                     // [16]: 4 winning v command, 5 winning w command
     int *iscal;                       // [8]: 1 winning rollout index, 2 near-tie flag
     int spos, rmax;
@@ -781,6 +785,8 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_ih = take(sizeof(int) * 4);
     size_t o_po = take(sizeof(RobotPose));
     size_t o_at = take(sizeof(double) * CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1));
+    size_t o_cl = take(d.use_clearance ? sizeof(float4) * CL_CAP : 0);
+    size_t o_cn = take(sizeof(int) * 4);
     size_t o_sc = take(sizeof(double) * 16);
     size_t o_is = take(sizeof(int) * 8);
     if (s) {
@@ -796,6 +802,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
         s->red3_v = (double *)(base + o_r3); s->red3_s = s->red3_v + 32;
         s->ihdr = (int *)(base + o_ih); s->pose = (RobotPose *)(base + o_po);
         s->atab = (double *)(base + o_at);
+        s->clist = (float4 *)(base + o_cl); s->cl_n = (int *)(base + o_cn);
         s->scal = (double *)(base + o_sc); s->iscal = (int *)(base + o_is);
         s->spos = spos; s->rmax = rmax;
     }
@@ -893,7 +900,10 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         sm.hdr[0] = vh; sm.hdr[1] = vl; sm.hdr[2] = wh; sm.hdr[3] = wl;
         sm.ihdr[0] = min(arange_len(vl, vh + d.v_res, d.v_res), d.nv_max);
         sm.ihdr[1] = min(arange_len(wl, wh + d.w_res, d.w_res), d.nw_max);
+        sm.cl_n[0] = 0;
     }
+    // clearance of the shared first row (dwa.py:65-67, i = 0): one thread, next to the header thread
+    if (CLR && tid == T - 1) sm.hdr[4] = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
     const int S = d.n_sub * d.n_outer, spos = sm.spos;
 
     PHASE_START();
@@ -936,11 +946,43 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         if ((ks + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (ks + 1) / d.n_sub - 1] = th;
         if (ks + 1 == d.n_sub) sm.wom[j] = cur;      // omega after the first dt step
     }
-    // clearance of the shared first row (dwa.py:65-67, i = 0)
     double clr0 = CRLK_CLEARANCE_CAP;
-    if (CLR) clr0 = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
+    if (CLR) {
+        clr0 = sm.hdr[4];
+        // Obstacle list of this control step: a rollout pose lies within `reach` of the current
+        // position and only clearances below min(clr0, 100) change a rollout's minimum, so an
+        // obstacle can matter only if its rectangle is closer than that + rc + reach to the current
+        // position.  Each obstacle is taken from the one cell that holds its closest point.
+        const float reach = (float)(fmax(fabs(e.max_v), fabs(e.min_v)) * e.base_dt * S) * 1.001f + 1e-3f;
+        const float rl = (float)fmin(clr0, CRLK_CLEARANCE_CAP) * 1.0001f + e.rc + reach + 2.0f * CRLK_CULL_MARGIN;
+        const float p0x = (float)st[0], p0y = (float)st[1];
+        const float hxm = (float)(os.ncx - 1), hym = (float)(os.ncy - 1);
+        auto cellx = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gx0) * os.ginv), 0.f), hxm); };
+        auto celly = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gy0) * os.ginv), 0.f), hym); };
+        const int bx0 = cellx(p0x - rl - 2e-3f), bx1 = cellx(p0x + rl + 2e-3f);
+        const int by0 = celly(p0y - rl - 2e-3f), by1 = celly(p0y + rl + 2e-3f);
+        const int bw = bx1 - bx0 + 1, ncell_box = bw * (by1 - by0 + 1);
+        if ((long long)ncell_box <= 64LL * T) {
+            for (int c = tid; c < ncell_box; c += T) {
+                const int cy = by0 + c / bw, cx = bx0 + (c - (c / bw) * bw);
+                const int s0 = __ldg(&os.cell_start[cy * os.ncx + cx]), s1 = __ldg(&os.cell_start[cy * os.ncx + cx + 1]);
+                for (int k = s0; k < s1; k++) {
+                    const float4 o = __ldg(&os.rects[__ldg(&os.cell_items[k])]);
+                    const float qx = fminf(fmaxf(p0x, o.x), o.z), qy = fminf(fmaxf(p0y, o.y), o.w);
+                    const float dx = p0x - qx, dy = p0y - qy;
+                    if (dx * dx + dy * dy > rl * rl) continue;
+                    if (cellx(qx) != cx || celly(qy) != cy) continue;
+                    const int pos = atomicAdd(&sm.cl_n[0], 1);
+                    if (pos < CL_CAP) sm.clist[pos] = o;
+                }
+            }
+        } else if (tid == 0) {
+            sm.cl_n[0] = CL_CAP + 1;              // box too large (open space): grid search per pose
+        }
+    }
     __syncthreads();
     PHASE_MARK(1);
+    const int cl_n = CLR ? sm.cl_n[0] : 0;
 
     // rollouts: heading cost from trajectory row 1 (dwa.py:58-62); every thread also keeps the
     // running sums of its cost columns (dwa.py:76-78 divides each column by its sum)
@@ -1006,8 +1048,12 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                 if (row % d.skip == 0) {
                     // only a clearance below the running minimum changes it (dwa.py:67-68), so the
                     // search is told to ignore everything farther than that
-                    double dis = pymax(clearance_thread(e, os, x, y, sm.wth[j * d.n_outer + row - 1], min_dis),
-                                       0.001);
+                    const int ks = row * d.n_sub - 1;
+                    double cl = -2.0;
+                    if (cl_n <= CL_CAP)
+                        cl = clearance_from_list(e, sm.clist, cl_n, x, y, wc[ks * nwm], ws[ks * nwm], min_dis);
+                    if (cl == -2.0) cl = clearance_thread(e, os, x, y, sm.wth[j * d.n_outer + row - 1], min_dis);
+                    double dis = pymax(cl, 0.001);
                     min_dis = pymin(dis, min_dis);
                 }
             }
