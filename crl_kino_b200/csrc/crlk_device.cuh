@@ -412,6 +412,23 @@ __device__ __forceinline__ float dis2obs_f32(const EnvP &e, const RobotPoseF &g,
     return (dis > (float)CRLK_COLLISION_DIS) ? dis : -1.0f;
 }
 
+// Separating-axis lower bound of the rectangle-to-rectangle distance in float32: the gap between the
+// two boxes along the world axes (robot's world AABB vs the obstacle) and along the robot's axes
+// (robot rectangle vs the obstacle's bounding box in the body frame); the distance of two convex
+// sets is at least their gap along any axis.  ~40 instructions, exact whenever a face of one
+// rectangle looks at the other.
+__device__ __forceinline__ float rect_sat_lb(const EnvP &e, const RobotPoseF &g, float wl, float wr, float wb,
+                                             float wt, float4 o)
+{
+    const float gw = fmaxf(fmaxf(o.x - wr, wl - o.z), fmaxf(o.y - wt, wb - o.w));        // world axes
+    const float cx = 0.5f * (o.x + o.z) - g.x, cy = 0.5f * (o.y + o.w) - g.y;
+    const float hx = 0.5f * (o.z - o.x), hy = 0.5f * (o.w - o.y);
+    const float qx = g.c * cx + g.s * cy, qy = g.c * cy - g.s * cx;                       // obstacle centre, body frame
+    const float rx = fabsf(g.c) * hx + fabsf(g.s) * hy, ry = fabsf(g.s) * hx + fabsf(g.c) * hy;   // its half extents there
+    const float gb = fmaxf(fmaxf((qx - rx) - e.rr, e.rl - (qx + rx)), fmaxf((qy - ry) - e.rt, e.rb - (qy + ry)));
+    return fmaxf(gw, gb) - 1e-4f;
+}
+
 #define CLR_EPS 2e-4f      // bound of |float32 distance - float64 distance| used below (coordinates are O(50))
 #define CLR_CAND 12
 
@@ -529,6 +546,10 @@ static __device__ __noinline__ double clearance_from_list(const EnvP &e, const f
 #pragma unroll
     for (int i = 0; i < 4; i++) { gf.wx[i] = (float)g.wx[i]; gf.wy[i] = (float)g.wy[i]; }
     const float px = gf.x, py = gf.y;
+    const float wl = fminf(fminf(gf.wx[0], gf.wx[1]), fminf(gf.wx[2], gf.wx[3]));
+    const float wr = fmaxf(fmaxf(gf.wx[0], gf.wx[1]), fmaxf(gf.wx[2], gf.wx[3]));
+    const float wb = fminf(fminf(gf.wy[0], gf.wy[1]), fminf(gf.wy[2], gf.wy[3]));
+    const float wt = fmaxf(fmaxf(gf.wy[0], gf.wy[1]), fmaxf(gf.wy[2], gf.wy[3]));
     const double b0 = fmin(bound, CRLK_CLEARANCE_CAP);
     float min32 = (float)b0 * 1.000001f + CLR_EPS;
     int cid[CLR_CAND];
@@ -542,7 +563,8 @@ static __device__ __noinline__ double clearance_from_list(const EnvP &e, const f
         const float qx = fminf(fmaxf(px, o.x), o.z), qy = fminf(fmaxf(py, o.y), o.w);
         const float dx = px - qx, dy = py - qy;
         if (dx * dx + dy * dy > lim * lim) continue;
-        if (footprint_lb(e, gf.c, gf.s, px, py, o) > bf) continue;
+        if (e.radius > 0.0 ? footprint_lb(e, gf.c, gf.s, px, py, o) > bf
+                           : rect_sat_lb(e, gf, wl, wr, wb, wt, o) > bf) continue;
         const float d = dis2obs_f32(e, gf, o);
         if (d > min32 + 2.0f * CLR_EPS) continue;
         if (d < 0.0f) { cid[0] = k; cd[0] = d; nc = 1; min32 = d; break; }

@@ -983,6 +983,12 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     __syncthreads();
     PHASE_MARK(1);
     const int cl_n = CLR ? sm.cl_n[0] : 0;
+#ifdef CRLK_PHASE_TIMING
+    if (CLR && tid == 0) {
+        atomicAdd(&g_phase_cycles[10], (unsigned long long)min(cl_n, CL_CAP));
+        atomicAdd(&g_phase_cycles[11], (unsigned long long)(cl_n > CL_CAP ? 1 : 0));
+    }
+#endif
 
     // rollouts: heading cost from trajectory row 1 (dwa.py:58-62); every thread also keeps the
     // running sums of its cost columns (dwa.py:76-78 divides each column by its sum)

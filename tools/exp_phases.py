@@ -27,3 +27,5 @@ for Q in ((1, 296) if os.environ.get('USE_CLEARANCE') else (1, 444, 1776)):
     tot = sum(buf[:10])
     print(f"Q={Q} control steps={steps} cycles/step={tot/steps:.0f} ({tot/steps/1.965e3:.1f} us)")
     print("   " + "  ".join(f"{n}={buf[i]/steps:.0f}" for i, n in enumerate(names)))
+    if os.environ.get('USE_CLEARANCE'):
+        print(f"   obstacle list: mean length {buf[10]/steps:.0f}, overflow in {100*buf[11]/steps:.1f}% of the control steps")
