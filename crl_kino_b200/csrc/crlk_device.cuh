@@ -111,8 +111,13 @@ static __device__ __noinline__ double crlk_atan2_special(double y, double x) { r
 __device__ __forceinline__ double crlk_atan2(double y, double x, const double *tab)
 {
     const double ay = fabs(y), ax = fabs(x);
-    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
-    if (!(mx > 1e-280 && mx < 1e280)) return crlk_atan2_special(y, x);
+    // max / min of two non-negative numbers with one comparison (fmax / fmin carry NaN handling)
+    const bool steep = ay > ax;
+    const double mx = steep ? ay : ax, mn = steep ? ax : ay;
+    // the fast path wants 1e-280 < mx < 1e280: one integer range test on the exponent field
+    // (biased exponents 93 .. 1953); NaN, infinities, zero and subnormals fail it
+    const unsigned ex = ((unsigned)__double2hiint(mx) >> 20) & 0x7ffu;
+    if (ex - 93u > 1860u) return crlk_atan2_special(y, x);
     const double r = crlk_rcp_pos(mx);
     double q = mn * r;
     q = fma(fma(-mx, q, mn), r, q);
@@ -122,8 +127,8 @@ __device__ __forceinline__ double crlk_atan2(double y, double x, const double *t
     double p = a[CRLK_ATAN_DEG * CRLK_ATAN_NK];
 #pragma unroll
     for (int n = CRLK_ATAN_DEG - 1; n >= 0; n--) p = fma(p, t, a[n * CRLK_ATAN_NK]);
-    if (ay > ax) p = 1.5707963267948966 - p;
-    if (x < 0.0) p = 3.141592653589793 - p;
+    if (steep) p = 1.5707963267948966 - p;
+    if (__double2hiint(x) < 0) p = 3.141592653589793 - p;            // x < 0 or x == -0.0 (atan2(+-0, -0) = +-pi)
     return copysign(p, y);
 }
 
