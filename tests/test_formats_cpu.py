@@ -65,3 +65,22 @@ def test_planning_results_dict(tmp_path):
     back = pickle.load(open(tmp_path / "planning_results_env1.pkl", "rb"))
     assert np.array_equal(back["runtime"], data["runtime"]) and np.array_equal(back["path_len"], data["path_len"])
     assert cio.benchmark_pairs(np.zeros((4, 5)))[:4] == [(0, 1), (0, 2), (0, 3), (1, 0)]
+
+
+def test_gym_action_space_maps_match_reference():
+    """DifferentialDriveGym.a2v / v2a (differential_gym.py:110-128) are host arithmetic: against the
+    values the unmodified reference produced (tests/golden/gym.npz)."""
+    from crl_kino_b200.env import DifferentialDriveEnv, DifferentialDriveGym
+    g = golden("gym")
+    gym_env = DifferentialDriveGym(DifferentialDriveEnv(1.0, -0.1, np.pi, 1.0, np.pi))
+    for ep in range(int(g["n_episodes"])):
+        a = g[f"ep{ep}_actions"][0]
+        assert np.array_equal(gym_env.a2v(a), g[f"ep{ep}_a2v"])
+        assert np.array_equal(gym_env.v2a(a), g[f"ep{ep}_v2a"])
+    assert gym_env.observation_space.shape == (733,) and gym_env.action_space.low.dtype == np.float32
+    assert gym_env.curriculum == {"obs_num": 7, "ori": False}
+    gym_env.set_curriculum(ori=True)
+    assert gym_env.curriculum["ori"] is True
+    info = dict(zip(("goal", "goal_dis", "heading", "collision", "clearance", "v", "w", "step"),
+                    (True, 0.5, 0.1, False, 1.0, 0.7, 0.2, 1.0)))
+    assert abs(gym_env._reward(info) - (50.0 - 0.75 - 0.05 + 1.0 + 0.7 - 0.1 - 2.5)) < 1e-12
