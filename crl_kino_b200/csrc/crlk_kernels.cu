@@ -274,19 +274,17 @@ __device__ __forceinline__ void warp_drain(const EnvP &e, const RobotPose &g, co
     }
 }
 
-// One warp per pose.  Flag only: screen the grid cells around the pose at the
-// collision radius.  With clearance: a full FP32 pass finds an upper bound of
-// the answer, then only cells within that bound are screened.
+// valid_state_check, flag only: one warp per pose screens the grid cells around the pose at the
+// collision radius (FP32), queues the survivors and tests them exactly (FP64), one per lane.
 __global__ void __launch_bounds__(256)
 k_valid_state(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8_t *valid,
-              double *clearance, uint8_t *near_boundary)
+              uint8_t *near_boundary)
 {
     __shared__ int s_queue[8][WQ_CAP];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int pose = blockIdx.x * 8 + warp;
     if (pose >= B) return;
     const float4 *__restrict__ rects = os.rects;
-    const int M = os.M;
     const double *st = states + 5 * (size_t)pose;
     RobotPose g;
     robot_pose_setup(e, st[0], st[1], st[2], g);
@@ -294,30 +292,8 @@ k_valid_state(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8
     int *queue = s_queue[warp];
     double best = CRLK_CLEARANCE_CAP;
     bool definite = false, marginal = false;
-    const bool want_clear = clearance != nullptr;
-
-    float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
-    if (want_clear) {
-        // pass 1: every lane finds its obstacle of smallest lower bound and
-        // evaluates it exactly; the warp minimum is an upper bound of the answer.
-        float lmin = CUDART_INF_F;
-        int limin = -1;
-        for (int o = lane; o < M; o += 32) {
-            float d2 = aabb_center_d2(__ldg(&rects[o]), px, py);
-            if (d2 < lmin) { lmin = d2; limin = o; }
-        }
-        if (limin >= 0) {
-            bool d, m;
-            double dis = dis2obs_exact(e, g, __ldg(&rects[limin]), d, m);
-            definite |= d; marginal |= m;
-            best = fmin(best, dis);
-        }
-        best = warp_min_d(best);
-        // pass 2 screens against that bound (never below the collision screen)
-        float b = (float)fmax(best, 0.0) * 1.0001f + e.rc + CRLK_CULL_MARGIN;
-        thr = fmaxf(thr, b);
-    }
-    float thr2 = thr * thr;
+    const float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
+    const float thr2 = thr * thr;
     int count = 0;   // warp-uniform
     grid_visit(os, px, py, thr, lane, 32, [&](int o, bool in) {
         bool keep = in && aabb_center_d2(__ldg(&rects[in ? o : 0]), px, py) <= thr2;
@@ -341,12 +317,12 @@ k_valid_state(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8
     bool any_mar = __any_sync(0xffffffffu, marginal);
     if (lane == 0) {
         if (valid) valid[pose] = (best < 0.0) ? 0 : 1;
-        if (clearance) clearance[pose] = (best < 0.0) ? -1.0 : best;
         if (near_boundary) near_boundary[pose] = (any_mar && !any_def) ? 1 : 0;
     }
 }
 
-// Clearance mode: one thread per pose, grid ring search.
+// get_clearance (and the validity flag with it): one thread per pose, ring search over the grid
+// (clearance_grid_thread).
 __global__ void __launch_bounds__(128)
 k_clearance(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8_t *valid, double *clearance,
             uint8_t *near_boundary)
@@ -372,7 +348,7 @@ extern "C" int crlk_valid_state(const CrlkEnv *env, const double *states, int32_
                                                                       clearance, near_boundary);
     else
         k_valid_state<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(env->p, env->os, states, B, valid,
-                                                                    clearance, near_boundary);
+                                                                    near_boundary);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }

@@ -131,7 +131,12 @@ int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals
  *   opt_cost  dev f64[B]   (nullable)
  *   opt_traj  dev f64[B x traj_rows x 5] (nullable); traj_rows from crlk_dwa_traj_rows
  *   n_rollouts dev i32[B]  (nullable) realised grid size nv * nw
- *   near_tie  dev u8[B]    (nullable) second-best cost within 1e-9 relative. */
+ *   near_tie  dev u8[B]    (nullable) second-best cost within 1e-9 relative.
+ * The three cost columns are normalised by their sums (dwa.py:76-78); the kernel adds each column in
+ * a different association than numpy's pairwise sum and multiplies by the reciprocal, so a
+ * normalised cost can differ from the reference's by ~1e-15 relative: opt_idx can differ from
+ * np.argmin only between rollouts whose costs agree to that level -- all of which near_tie reports.
+ * opt_cost is evaluated for the winner with the reference's divisions. */
 int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, const double *states,
                      const double *goals, int32_t goal_stride, int32_t B, double *opt_v,
                      int32_t *opt_idx, double *opt_cost, double *opt_traj, int32_t *n_rollouts,
