@@ -84,3 +84,32 @@ def test_gym_action_space_maps_match_reference():
     info = dict(zip(("goal", "goal_dis", "heading", "collision", "clearance", "v", "w", "step"),
                     (True, 0.5, 0.1, False, 1.0, 0.7, 0.2, 1.0)))
     assert abs(gym_env._reward(info) - (50.0 - 0.75 - 0.05 + 1.0 + 0.7 - 0.1 - 2.5)) < 1e-12
+
+
+def test_policy_state_dict_in_the_reference_layout():
+    """load_policy's load_state_dict takes the reference's DDPGPolicy state dict (actor / actor_old /
+    critic / critic_old entries; the actor is nn.Sequential `model` with Linear layers at even
+    indices, policy/net.py:126-133) and keeps only the actor."""
+    import torch
+    from crl_kino_b200.env import DifferentialDriveEnv, DifferentialDriveGym
+    from crl_kino_b200.policy.rl_policy import DDPGPolicy
+    from crl_kino_b200.policy.net import Actor
+    gym_env = DifferentialDriveGym(DifferentialDriveEnv(1.0, -0.1, np.pi, 1.0, np.pi))
+    layer = [1024, 512, 512, 512]
+    dims = [733] + layer + [2]
+    rng = np.random.default_rng(0)
+    sd = {}
+    for prefix in ("actor", "actor_old"):
+        for i in range(5):
+            sd[f"{prefix}.model.{2 * i}.weight"] = torch.as_tensor(rng.standard_normal((dims[i + 1], dims[i])).astype(np.float32))
+            sd[f"{prefix}.model.{2 * i}.bias"] = torch.as_tensor(rng.standard_normal(dims[i + 1]).astype(np.float32))
+    sd["critic.model.0.weight"] = torch.zeros(4, 735)
+    sd["critic_old.model.0.weight"] = torch.zeros(4, 735)
+    actor = Actor(layer, gym_env.observation_space.shape, gym_env.action_space.shape,
+                  [gym_env.action_space.low, gym_env.action_space.high], seed=1)
+    policy = DDPGPolicy(actor, None, None, None, action_range=[gym_env.action_space.low, gym_env.action_space.high])
+    policy.load_state_dict(sd)
+    for i in range(5):
+        assert np.array_equal(actor.weights[i], sd[f"actor.model.{2 * i}.weight"].numpy())
+        assert np.array_equal(actor.biases[i], sd[f"actor.model.{2 * i}.bias"].numpy())
+    assert actor.low.dtype == np.float32 and np.allclose(actor.low, [-0.1, -np.pi]) and np.allclose(actor.high, [1.0, np.pi])
