@@ -39,7 +39,8 @@ class ExtendView(C.Structure):
 
 class PlanParams(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("d_min", C.c_double), ("d_max", C.c_double),
-                ("goal_radius", C.c_double), ("retry_radius", C.c_double)]
+                ("goal_radius", C.c_double), ("retry_radius", C.c_double), ("seed", C.c_uint64),
+                ("state_lo", C.c_double * 5), ("state_hi", C.c_double * 5), ("goal_sample_rate", C.c_int32)]
 
 
 class ExtendParams(C.Structure):
@@ -83,6 +84,7 @@ PROTOTYPES = {
     "crlk_debug_atan2": (C.c_int, [P, P, I32, P, P]),
     "crlk_gym_step": (C.c_int, [P, P, P, I32, P, F64, P, I32, P, P, P, P, I32, P, P]),
     "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P, P]),
+    "crlk_sample_stream": (C.c_int, [P, P, I32, I32, P, P]),
     "crlk_policy_create": (C.c_int, [I32, P, P, P, P, P, P]),
     "crlk_policy_destroy": (C.c_int, [P]),
     "crlk_policy_forward": (C.c_int, [P, P, I32, P, F32, I32, P, P, P]),

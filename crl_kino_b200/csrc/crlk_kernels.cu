@@ -1504,7 +1504,63 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
 struct PlanP {
     int max_iter, S;
     double d_min, d_max, goal_radius, retry_radius;
+    unsigned long long seed;
+    double lo[5], hi[5];
+    int goal_rate;
 };
+
+// Counter-based uniform in [0, 1): splitmix64 finaliser over (seed, query, draw, component).
+__host__ __device__ inline double crlk_sample_u01(unsigned long long seed, unsigned long long q, unsigned long long i,
+                                                  unsigned long long c)
+{
+    unsigned long long z = seed ^ (q * 0x100000001B3ull) ^ (i * 0x9E3779B97F4A7C15ull) ^ ((c + 1ull) * 0xD6E8FEB86659FD93ull);
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * 1.1102230246251565e-16;      // 2^-53
+}
+
+// RRT.sample (rrt.py:146-154): draw i of query q -> component c of the sampled state.
+__device__ __forceinline__ double plan_sample(const PlanP &pp, const double *goal, int q, int i, int c)
+{
+    const double ub = crlk_sample_u01(pp.seed, (unsigned long long)q, (unsigned long long)i, 5ull);
+    if ((int)floor(ub * 101.0) <= pp.goal_rate) return goal[c];
+    const double u = crlk_sample_u01(pp.seed, (unsigned long long)q, (unsigned long long)i, (unsigned long long)c);
+    return pp.lo[c] + u * (pp.hi[c] - pp.lo[c]);
+}
+
+__global__ void k_sample_stream(PlanP pp, const double *__restrict__ goals, int Q, int S, double *out)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Q * S * 5) return;
+    const int c = (int)(t % 5);
+    const long long r = t / 5;
+    const int i = (int)(r % S), q = (int)(r / S);
+    out[t] = plan_sample(pp, goals + 5 * (size_t)q, q, i, c);
+}
+
+static void fill_planp(const CrlkPlanParams *plan, int S, PlanP *pp)
+{
+    pp->max_iter = plan->max_iter; pp->S = S;
+    pp->d_min = plan->d_min; pp->d_max = plan->d_max;
+    pp->goal_radius = plan->goal_radius; pp->retry_radius = plan->retry_radius;
+    pp->seed = plan->seed; pp->goal_rate = plan->goal_sample_rate;
+    for (int c = 0; c < 5; c++) { pp->lo[c] = plan->state_lo[c]; pp->hi[c] = plan->state_hi[c]; }
+}
+
+extern "C" int crlk_sample_stream(const CrlkPlanParams *plan, const double *goals, int32_t Q, int32_t S,
+                                  double *out, void *stream)
+{
+    CRLK_REQUIRE(plan != nullptr && Q >= 0 && S >= 0, "plan / shape");
+    if (Q == 0 || S == 0) return CRLK_OK;
+    CRLK_REQUIRE(goals && out, "NULL array");
+    PlanP pp;
+    fill_planp(plan, S, &pp);
+    const long long n = (long long)Q * S * 5;
+    k_sample_stream<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pp, goals, Q, S, out);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
 
 // RRT.choose_parent (rrt.py:156-161) over one tree by the whole CTA: exact
 // float64 distances, first minimum.  Every thread returns the same (idx, dist).
@@ -1608,9 +1664,16 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
         };
 
         while (iters < pp.max_iter && cur < pp.S && !over) {
-            const double *sp = streams + ((size_t)q * pp.S + cur) * 5;
+            double sx, sy, sth;
+            if (streams) {
+                const double *sp = streams + ((size_t)q * pp.S + cur) * 5;
+                sx = sp[0]; sy = sp[1]; sth = sp[2];
+            } else {                            // drawn here (rrt.py:146-154): only x, y, theta are ever used
+                const double *gl = goals + 5 * (size_t)q;
+                sx = plan_sample(pp, gl, q, cur, 0); sy = plan_sample(pp, gl, q, cur, 1);
+                sth = plan_sample(pp, gl, q, cur, 2);
+            }
             cur++;
-            const double sx = sp[0], sy = sp[1], sth = sp[2];
             if (tid == 0) robot_pose_setup(e, sx, sy, sth, *sm.pose);
             __syncthreads();
             int col = collision_block(e, os, sm.pose);                                // rrt.py:66
@@ -1671,16 +1734,14 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
     if (rc) return rc;
     CRLK_REQUIRE(Q >= 0 && S >= 0 && plan->max_iter >= 0, "shape");
     if (Q == 0) return CRLK_OK;
-    CRLK_REQUIRE(goals && (S == 0 || streams) && iters && cursor && reached && overflow, "NULL array");
+    CRLK_REQUIRE(goals && iters && cursor && reached && overflow, "NULL array");
     CRLK_REQUIRE(forest->x64 && forest->y64 && forest->states && forest->parent && forest->n_nodes &&
                  forest->stride >= 1, "forest");
     CRLK_REQUIRE(!forest->pool || (forest->seg_off && forest->seg_len && forest->seg_flag && forest->pool_used),
                  "forest path pool");
     CRLK_REQUIRE((forest->x32 == nullptr) == (forest->y32 == nullptr), "x32/y32 must both be given or both NULL");
     PlanP pp;
-    pp.max_iter = plan->max_iter; pp.S = S;
-    pp.d_min = plan->d_min; pp.d_max = plan->d_max;
-    pp.goal_radius = plan->goal_radius; pp.retry_radius = plan->retry_radius;
+    fill_planp(plan, S, &pp);
     size_t smem = crlk_dwa_smem_bytes(d);
     const bool wide = dwa_use_wide(Q);
     auto kern = d.use_clearance ? (wide ? k_plan_dwa<DWA_WIDE_THREADS, 1, true> : k_plan_dwa<PLAN_THREADS, PLAN_MIN_BLOCKS, true>)

@@ -385,24 +385,50 @@ class FusedRRT(BatchedRRT):
         gap = (self.starts[:, :2] - self.goals[:, :2]).norm(dim=1)
         self.order = torch.argsort(gap, descending=True).to(torch.int32).contiguous()
 
-    def plan_async(self, streams):
-        """Launch the planning kernel on the current stream; streams: CUDA float64 [Q, S, 5]."""
-        from .._lib import PlanParams, check, lib
+    def plan_params(self, seed=0, goal_sample_rate=5):
+        from .._lib import PlanParams
         C = self._C
-        assert streams.is_cuda and streams.dtype == torch.float64 and streams.is_contiguous()
-        assert streams.shape[0] == self.Q and streams.shape[2] == 5
+        sb = self.env.get_bounds()["state_bounds"]
+        return PlanParams(self.max_iter, 1.0, 20.0, 1.0, 5.0, int(seed) & 0xFFFFFFFFFFFFFFFF,    # rrt.py:69, :75, :79
+                          (C.c_double * 5)(*sb[:, 0]), (C.c_double * 5)(*sb[:, 1]), int(goal_sample_rate))
+
+    def sample_streams(self, n, seed=0, goal_sample_rate=5):
+        """The draws plan_async(None, ...) consumes, materialised on the device: float64 [Q, n, 5]."""
+        from .._lib import check, lib
+        C = self._C
+        out = torch.empty(self.Q, n, 5, dtype=torch.float64, device=self.goals.device)
+        pp = self.plan_params(seed, goal_sample_rate)
+        check(lib().crlk_sample_stream(C.byref(pp), C.c_void_p(self.goals.data_ptr()), self.Q, n,
+                                       C.c_void_p(out.data_ptr()), ops._stream()))
+        return out
+
+    def plan_async(self, streams, seed=0, max_samples=None, goal_sample_rate=5):
+        """Launch the planning kernel on the current stream.  streams: CUDA float64 [Q, S, 5], or None:
+        the kernel then draws its own samples (RRT.sample with a counter-based generator keyed by
+        `seed`, at most max_samples per query; workloads.device_sample_stream is the host mirror)."""
+        from .._lib import check, lib
+        C = self._C
         p = lambda t: C.c_void_p(t.data_ptr())
-        pp = PlanParams(self.max_iter, 1.0, 20.0, 1.0, 5.0)            # rrt.py:69, :75, :79
+        pp = self.plan_params(seed, goal_sample_rate)
+        if streams is None:
+            S = int(max_samples or 8 * self.max_iter + 64)
+            sptr = None
+        else:
+            assert streams.is_cuda and streams.dtype == torch.float64 and streams.is_contiguous()
+            assert streams.shape[0] == self.Q and streams.shape[2] == 5
+            S = streams.shape[1]
+            sptr = p(streams)
         self._streams = streams
         check(lib().crlk_plan_dwa(self.env.handle.h, C.byref(self.dwa.params()), C.byref(self.xp), C.byref(pp),
-                                  C.byref(self._fv), p(self.goals), p(streams), streams.shape[1], self.Q,
+                                  C.byref(self._fv), p(self.goals), sptr, S, self.Q,
                                   p(self.iters), p(self.cursor), p(self.reached), p(self.flags),
                                   p(self.overflow), p(self.stats), p(self.order) if self.order is not None else None,
                                   ops._stream()))
 
-    def plan(self, streams, **_):
-        streams = ops.as_dev(streams).contiguous()
-        self.plan_async(streams)
+    def plan(self, streams=None, seed=0, max_samples=None, **_):
+        if streams is not None:
+            streams = ops.as_dev(streams).contiguous()
+        self.plan_async(streams, seed=seed, max_samples=max_samples)
         torch.cuda.synchronize()
         if int(self.overflow.item()):
             raise RuntimeError(f"{int(self.overflow.item())} trees ran out of node/path capacity")

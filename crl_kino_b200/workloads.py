@@ -109,3 +109,31 @@ def sample_stream(state_bounds, goal, n, seed, goal_sample_rate=5):
 
 
 DENSE_DWA = dict(dt=0.2, predict_time=1.0, v_res=0.4 / 63, w_res=0.4 * np.pi / 63)   # 64 x 64 nominal grid
+
+
+def device_sample_stream(state_bounds, goals, n, seed, goal_sample_rate=5):
+    """Host mirror of the planner kernel's own sample generator (crlk_sample_stream, include/crlk.h):
+    [Q, n, 5] float64, bit-identical to what crlk_plan_dwa draws when it is given no streams.
+    Counter based: u01(seed, q, i, c) = (splitmix64_finalise(seed ^ q*K1 ^ i*K2 ^ (c+1)*K3) >> 11) * 2^-53;
+    component c of draw i is lo + u * (hi - lo); draw i is the goal iff floor(101 * u01(.., 5)) <= rate
+    (RRT.sample, rrt.py:146-154: random.randint(0, 100) > goal_sample_rate picks the uniform branch)."""
+    goals = np.asarray(goals, dtype=np.float64).reshape(-1, 5)
+    Q = len(goals)
+    sb = np.asarray(state_bounds, dtype=np.float64)
+    u64 = np.uint64
+    q = np.arange(Q, dtype=u64)[:, None, None]
+    i = np.arange(n, dtype=u64)[None, :, None]
+    c = np.arange(1, 7, dtype=u64)[None, None, :]
+    with np.errstate(over="ignore"):
+        z = u64(int(seed) & 0xFFFFFFFFFFFFFFFF) ^ (q * u64(0x100000001B3)) ^ (i * u64(0x9E3779B97F4A7C15)) \
+            ^ (c * u64(0xD6E8FEB86659FD93))
+        z ^= z >> u64(30)
+        z *= u64(0xBF58476D1CE4E5B9)
+        z ^= z >> u64(27)
+        z *= u64(0x94D049BB133111EB)
+        z ^= z >> u64(31)
+    u = (z >> u64(11)).astype(np.float64) * 1.1102230246251565e-16
+    out = sb[:, 0] + u[:, :, :5] * (sb[:, 1] - sb[:, 0])
+    pick_goal = np.floor(u[:, :, 5] * 101.0).astype(np.int64) <= goal_sample_rate
+    out[pick_goal] = np.repeat(goals[:, None, :], n, 1)[pick_goal]
+    return out

@@ -327,7 +327,23 @@ typedef struct {
     double d_min, d_max;         /* sample acceptance band 1.0 <= d < 20 (rrt.py:69) */
     double goal_radius;          /* 1.0 (rrt.py:75, :81) */
     double retry_radius;         /* 5.0 (rrt.py:79) */
+    /* RRT.sample (rrt.py:146-154) on the device, used when no sample streams are passed:
+     * draw i of query q is the goal with probability (goal_sample_rate + 1) / 101, else
+     * state_lo + u * (state_hi - state_lo) per component, u from the counter-based generator
+     * crlk_sample_u01(seed, q, i, component) below. */
+    uint64_t seed;
+    double state_lo[5], state_hi[5];   /* get_bounds()['state_bounds'] (differential_env.py:153-161) */
+    int32_t goal_sample_rate;    /* 5 (rrt.py:36) */
 } CrlkPlanParams;
+
+/* The sample generator of crlk_plan_dwa, materialised: out dev f64[Q x S x 5] receives exactly the
+ * draws the planner consumes when called with streams == NULL (same plan->seed / bounds / rate).
+ * Counter based: u01(seed, q, i, c) = (mix(seed ^ q * 0x100000001B3 ^ i * 0x9E3779B97F4A7C15 ^
+ * (c + 1) * 0xD6E8FEB86659FD93) >> 11) * 2^-53 with mix = the splitmix64 finaliser; c = 0..4 the state
+ * components, c = 5 the goal-bias draw (goal iff floor(101 u) <= goal_sample_rate).
+ * crl_kino_b200/workloads.py::device_sample_stream is the host mirror (bit-identical). */
+int crlk_sample_stream(const CrlkPlanParams *plan, const double *goals, int32_t Q, int32_t S, double *out,
+                       void *stream);
 
 /* Q complete RRT.planning runs in ONE launch, one thread block per query from its
  * first sample to its last node: per consumed sample the validity check
@@ -340,7 +356,8 @@ typedef struct {
  *            trees on return; with a path pool, pool_cap >= 2 * max_iter * n_max_extend
  *   goals    dev f64[Q x 5]
  *   streams  dev f64[Q x S x 5] pre-drawn samples per query (RRT.sample, rrt.py:146-154,
- *            draws from host RNG state; the stream is that sequence), consumed in order
+ *            draws from host RNG state; the stream is that sequence), consumed in order;
+ *            NULL: up to S samples per query are drawn on the device (plan->seed, see CrlkPlanParams)
  *   iters    dev i32[Q] accepted samples (loop index of rrt.py:60 at exit)
  *   cursor   dev i32[Q] samples consumed (== S with iters < max_iter: stream exhausted)
  *   reached  dev u8[Q]  reach_exactly (rrt.py:76, :82)

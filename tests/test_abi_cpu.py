@@ -32,7 +32,7 @@ def test_header_symbols_exported_and_bound():
 def test_struct_layouts_match_header():
     from crl_kino_b200._lib import DwaParams, EnvParams, ExtendParams, PlanParams
     assert ctypes.sizeof(EnvParams) == 6 * 8 + 4 * 8 + 4 * 4 + 8
-    assert ctypes.sizeof(PlanParams) == 8 + 4 * 8
+    assert ctypes.sizeof(PlanParams) == 8 + 4 * 8 + 8 + 10 * 8 + 8
     assert ctypes.sizeof(DwaParams) == 7 * 8 + 2 * 4
     assert ctypes.sizeof(ExtendParams) == 4 + 4 + 8 + 8
 

@@ -113,3 +113,21 @@ def test_policy_state_dict_in_the_reference_layout():
         assert np.array_equal(actor.weights[i], sd[f"actor.model.{2 * i}.weight"].numpy())
         assert np.array_equal(actor.biases[i], sd[f"actor.model.{2 * i}.bias"].numpy())
     assert actor.low.dtype == np.float32 and np.allclose(actor.low, [-0.1, -np.pi]) and np.allclose(actor.high, [1.0, np.pi])
+
+
+def test_device_sample_stream_host_mirror_properties():
+    """The host mirror of the planner kernel's sample generator (workloads.device_sample_stream):
+    deterministic in (seed, query, draw), independent of the batch it is asked in, inside the state
+    bounds, goal bias (5 + 1) / 101 (rrt.py:147)."""
+    from crl_kino_b200.workloads import device_sample_stream
+    sb = golden("fixtures")["state_bounds"]
+    goals = np.tile(np.array([[10, 10, 0, 0, 0.0]]), (6, 1)) + np.arange(6)[:, None] * 0.1
+    a = device_sample_stream(sb, goals, 3000, seed=7)
+    b = device_sample_stream(sb, goals[:3], 1000, seed=7)
+    assert a.shape == (6, 3000, 5) and np.array_equal(a[:3, :1000], b)
+    assert not np.array_equal(a, device_sample_stream(sb, goals, 3000, seed=8))
+    is_goal = np.all(a == goals[:, None, :], axis=2)
+    assert 0.045 < is_goal.mean() < 0.075
+    u = a[~is_goal]
+    assert np.all(u >= sb[:, 0]) and np.all(u < sb[:, 1])
+    assert abs(u[:, 0].mean()) < 0.5 and 10.5 < u[:, 0].std() < 12.5          # uniform on [-20, 20)

@@ -226,3 +226,32 @@ def test_batched_rrt_estimator_reproduces_reference_run(copies):
         _check_rl_tree(states, parents, p.final_course(q), g, "rl_est")
         assert int(p.noise_cursor[q].item()) == len(g["rl_est_noise"])
         assert bool(reached[q]) == bool(g["rl_est_reach"])
+
+
+def test_fused_rrt_device_sampling():
+    """crlk_plan_dwa without sample streams draws RRT.sample's candidates itself (counter-based
+    generator): the draws equal the host mirror bit for bit, and planning from the seed alone builds
+    exactly the trees that planning from those materialised streams builds."""
+    import torch
+    from crl_kino_b200.planner.batched import FusedRRT
+    from crl_kino_b200.workloads import device_sample_stream, query_pairs
+    env, o = make_envs(fixture_map("test_env2"))
+    Q, iters, S = 24, 12, 200
+    s, gl = query_pairs(lambda c: o.valid_state_batch(c)[1], Q, seed=21)
+    a = FusedRRT(env, s, gl, max_iter=iters)
+    dev = a.sample_streams(S, seed=1234)
+    host = device_sample_stream(env.get_bounds()["state_bounds"], gl, S, seed=1234)
+    assert np.array_equal(np_(dev), host)
+    frac_goal = np.mean(np.all(host == gl[:, None, :], axis=2))
+    assert 0.03 < frac_goal < 0.09                                    # (5 + 1) / 101, rrt.py:147
+    assert host[..., 0].min() >= -20 and host[..., 0].max() < 20 and abs(host[..., 2]).max() < np.pi
+    ra = a.plan(None, seed=1234, max_samples=S)
+    b = FusedRRT(env, s, gl, max_iter=iters)
+    rb = b.plan(host)
+    assert np.array_equal(ra, rb) and np.array_equal(np_(a.cursor), np_(b.cursor))
+    assert torch.equal(a.forest.n_nodes, b.forest.n_nodes)
+    for q in range(Q):
+        sa, pa = a.tree(q)
+        sb_, pb = b.tree(q)
+        assert np.array_equal(sa, sb_) and np.array_equal(pa, pb)
+    assert int(np_(a.forest.n_nodes).sum()) > 3 * Q
