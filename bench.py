@@ -210,6 +210,17 @@ def planning_leg(args, env, dwa, rank):
     out["h2d_bytes"] = h_streams.numel() * 8
     out["d2h_bytes"] = sum(h.numel() * h.element_size() for h in h_res)
     assert np.array_equal(h_res[0].numpy().astype(bool), reached)
+    nodes_from_streams = fp.forest.n_nodes.clone()
+    # the same planner drawing its own samples on the device (no sample streams at all)
+    fp.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fp.plan_async(None, seed=300 + rank, max_samples=S)
+    for h, t in zip(h_res, (fp.reached, fp.iters, fp.forest.n_nodes)):
+        h.copy_(t, non_blocking=True)
+    torch.cuda.synchronize()
+    out["device_sampling_seconds"] = time.perf_counter() - t0
+    out["device_sampling_reached_frac"] = float(h_res[0].numpy().astype(bool).mean())
 
     if args.plan_lockstep:
         p = BatchedRRT(env, starts, goals, max_iter=args.plan_iters, dwa=dwa, keep_paths=False)
@@ -219,7 +230,7 @@ def planning_leg(args, env, dwa, rank):
         out["lockstep_seconds"] = time.perf_counter() - t0
         out["lockstep_rounds"] = p.samples_used
         out["lockstep_identical"] = bool(np.array_equal(r2, reached) and
-                                         torch.equal(p.forest.n_nodes, fp.forest.n_nodes))
+                                         torch.equal(p.forest.n_nodes, nodes_from_streams))
     return out
 
 
@@ -498,6 +509,10 @@ def run_ours(args):
                                 "mean_samples_consumed_rank0": plan["mean_samples"],
                                 "streams_exhausted_rank0": plan["streams_exhausted"],
                                 "extensions_per_sec": tot_pext / t_plan, "gpu_launches": 1,
+                                "device_sampling_rank0": {"queries_per_sec": plan["queries"] / plan["device_sampling_seconds"],
+                                                          "reached_frac": plan["device_sampling_reached_frac"],
+                                                          "note": "no sample streams: the kernel draws RRT.sample itself "
+                                                                  "(counter-based generator), wall clock incl. the D2H of the results"},
                                 "note": "Q full RRT.planning runs in one launch of k_plan_dwa (FusedRRT: one CTA per "
                                         "query from first sample to last node, persistent CTAs pull queries); trees "
                                         "and sample streams resident in HBM, CUDA-event time, best of 2 after warm-up; "
