@@ -294,9 +294,16 @@ def mlp_roofline(peaks):
     algo = 3600384.0 * B
     peak = float(peaks.get("bf16_tflops", 1590.0))
     ach = algo / (ms * 1e-3) / 1e12
+    big = torch.zeros(65536, ops.OBS_LD, dtype=torch.float32, device="cuda")
+    big[:, :733] = torch.rand(65536, 733, device="cuda")
+    ms_big = timed(lambda: ops.policy_forward(h, big), 5)
+    ach_big = 3600384.0 * 65536 / (ms_big * 1e-3) / 1e12
     return {"kernel": "k_gemm_bf16x3 (+ split, head)", "bound": "tensor", "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms": ms,
-            "ncu": "profiles/r1d_gemm_ncu_summary.txt: tensor pipe 46.5 % active in the layer-0 GEMM",
+            "ncu": "profiles/r1j_gemm_ncu_summary.txt: tensor pipe 58.6 % active in the layer-0 GEMM",
+            "at_65536_rows": {"achieved": ach_big, "frac": ach_big / peak, "ms": ms_big,
+                              "kernel": "k_gemm_bf16x3_pair<256> (tcgen05.mma.cta_group::2, 256 x 256 tiles)",
+                              "bf16_mma_tflops": 6.0 * ach_big * (1.835 - 0.786 * 0.4583) / 1.835},
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "note": "algorithmic float32 FLOP (3,600,384 per sample); the kernel issues 6 bf16 MMAs per "
                     "float32 product pair (bf16 x 3 operand split) to keep float32-level accuracy, so the "

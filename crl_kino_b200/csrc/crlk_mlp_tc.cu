@@ -467,6 +467,193 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------- CTA-pair variant
+// Two CTAs of a cluster (two SMs of a TPC) work on one 256 x 128 output tile with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the W tile
+// (64 of the 128 feature rows); the tensor core reads both halves.  Per k block a CTA then
+// fetches 48 KB of A + 24 KB of W from L2 instead of 48 + 48 -- the single-CTA kernel is bound by
+// exactly that operand traffic -- and the smaller stage allows a 3-deep ring.
+// Protocol: both producers load into their own shared memory but signal the LEADER's (rank 0)
+// full barrier (cp.async.bulk.tensor ... cta_group::2 with the peer bit of the barrier address
+// cleared); the leader's MMA thread issues all MMAs and releases a stage / publishes an
+// accumulator with tcgen05.commit ... multicast::cluster to both CTAs; each CTA's epilogue warps
+// drain their own 128 TMEM lanes and hand the accumulator back to the leader (remote arrive).
+// PBN = feature columns of the pair tile (128 or 256): a CTA stages PBN / 2 rows of W per plane.
+#define TCP_A_BYTES (3 * TC_STAGE_BYTES)                 // three A planes, 128 rows each
+template <int PBN> struct PairCfg {
+    static constexpr int b_plane = PBN / 2 * TC_BK * 2;           // bytes of one half W plane tile
+    static constexpr int b_bytes = 3 * b_plane;
+    static constexpr int stage = TCP_A_BYTES + b_bytes;           // 72 KB (PBN 128) / 96 KB (PBN 256)
+    static constexpr int stages = (PBN == 128) ? 3 : 2;
+    static constexpr int smem = stages * stage + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// TMA load of one box into this CTA's shared memory, completion bytes reported to the pair leader's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// arrive on a barrier of the pair leader (rank 0) from either CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .b32 r;\n\t"
+        "mapa.shared::cluster.u32 r, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}"
+        ::"r"(bar) : "memory");
+}
+
+template <int PBN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16x3_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+                   int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
+                   __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc,
+                   const int *__restrict__ n_rows_dev, int a_lo_kb)
+{
+    if (n_rows_dev) B = min(B, *n_rows_dev);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + PairCfg<PBN>::stages * PairCfg<PBN>::stage;
+    const uint32_t full0 = bars, empty0 = bars + 8 * PairCfg<PBN>::stages;
+    const uint32_t tfull0 = bars + 16 * PairCfg<PBN>::stages, tempty0 = tfull0 + 16;
+    const uint32_t tslot = tempty0 + 16;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + PairCfg<PBN>::stages * PairCfg<PBN>::stage + 16 * PairCfg<PBN>::stages + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles_n = N / PBN, tiles = tiles_n * ((B + 2 * TC_BM - 1) / (2 * TC_BM));   // 256-row pair tiles
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < PairCfg<PBN>::stages; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(2 * PBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                        // barriers of both CTAs are initialised before anyone signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ---- producer (both CTAs): own A rows, own half of the W rows
+        int git = 0;
+        for (int t = pair; t < tiles; t += npairs) {
+            const int m0 = (t / tiles_n) * 2 * TC_BM + (int)rank * TC_BM;
+            const int n0 = (t % tiles_n) * PBN + (int)rank * (PBN / 2);
+            for (int kb = 0; kb < kblocks; kb++, git++) {
+                const int s = git % PairCfg<PBN>::stages, ph = (git / PairCfg<PBN>::stages) & 1;
+                const uint32_t st = base + s * PairCfg<PBN>::stage;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const bool lo = kb < a_lo_kb;
+                if (rank == 0)                  // the leader's barrier counts the bytes of both CTAs
+                    mbar_expect_tx(full0 + 8 * s, 2 * ((lo ? TCP_A_BYTES : TC_STAGE_BYTES) + PairCfg<PBN>::b_bytes));
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    if (pl == 0 || lo)
+                        tma_load_2d_pair(st + pl * TC_STAGE_BYTES, &tmA, kb * TC_BK, pl * Mpad + m0, full0 + 8 * s);
+                    tma_load_2d_pair(st + TCP_A_BYTES + pl * PairCfg<PBN>::b_plane, &tmWh, kb * TC_BK, pl * N + n0,
+                                     full0 + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ---- MMA issuer: one thread of the leader CTA, M = 256 across the pair
+        const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, PBN);
+        int git = 0, ti = 0;
+        for (int t = pair; t < tiles; t += npairs, ti++) {
+            const int as = ti & 1, aph = (ti >> 1) & 1;
+            mbar_wait(tempty0 + 8 * as, aph ^ 1);            // both CTAs' epilogues drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + (uint32_t)(as * PBN);
+            for (int kb = 0; kb < kblocks; kb++, git++) {
+                const int s = git % PairCfg<PBN>::stages, ph = (git / PairCfg<PBN>::stages) & 1;
+                const uint32_t st = base + s * PairCfg<PBN>::stage;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool lo = kb < a_lo_kb;
+#pragma unroll
+                for (int pr = 0; pr < TC_NPAIR; pr++) {
+                    if (!lo && c_pair_a[pr] != 0) continue;
+                    uint64_t da = umma_desc_sw128(st + c_pair_a[pr] * TC_STAGE_BYTES);
+                    uint64_t db = umma_desc_sw128(st + TCP_A_BYTES + c_pair_w[pr] * PairCfg<PBN>::b_plane);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        umma_bf16_pair(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | pr | k) != 0);
+                }
+                umma_commit_pair(empty0 + 8 * s);            // frees the stage in both CTAs
+            }
+            umma_commit_pair(tfull0 + 8 * as);               // accumulator complete, both CTAs
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue (both CTAs): this CTA's 128 rows of the pair tile
+        const int q = warp & 3;
+        int ti = 0;
+        for (int t = pair; t < tiles; t += npairs, ti++) {
+            const int as = ti & 1, aph = (ti >> 1) & 1;
+            const int m0 = (t / tiles_n) * 2 * TC_BM + (int)rank * TC_BM, n0 = (t % tiles_n) * PBN;
+            const int m = m0 + 32 * q + lane;
+            mbar_wait(tfull0 + 8 * as, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < PBN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * PBN + 32 * c), r);
+                if (c == PBN / 32 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty0 + 8 * as);
+                }
+                if (m < B) epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                        // the peer may still be reading this CTA's operands / signalling its barriers
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * PBN));
+    }
+}
+
 // float32 [B, ld_in] -> three bf16 planes [3][Mpad][ld_out] (columns >= K zero filled)
 __global__ void k_split_planes(const float *__restrict__ in, int ld_in, int K, int B, int Mpad,
                                __nv_bfloat16 *__restrict__ out, int ld_out)
@@ -504,13 +691,14 @@ static EncodeTiledFn get_encode()
 }
 
 // 2-D bf16 tensor [rows][cols] (row pitch ld elements), box = 64 columns x 128 rows, 128 B swizzle.
-static int make_map(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, uint64_t ld)
+static int make_map(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows = TC_BM)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) { crlk_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CRLK_E_CUDA; }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {ld * 2};
-    cuuint32_t box[2] = {TC_BK, TC_BM};
+    cuuint32_t box[2] = {TC_BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -524,6 +712,7 @@ static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 struct TcLayer {
     __nv_bfloat16 *d_w;   // [3][N][Kp]
     CUtensorMap map_w;
+    CUtensorMap map_wh;   // the same tensor with 64-row boxes (half W tiles of the CTA-pair kernel)
     int N, K, Kp;
 };
 
@@ -584,10 +773,14 @@ int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_ho
         free(h);
         int rc = make_map(&L.map_w, L.d_w, 3ull * L.N, L.Kp, L.Kp);
         if (rc) return rc;
+        rc = make_map(&L.map_wh, L.d_w, 3ull * L.N, L.Kp, L.Kp, TC_BN / 2);
+        if (rc) return rc;
     }
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::smem));
+    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::smem));
     *out = t;
     return CRLK_OK;
 }
@@ -641,7 +834,26 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
         bool is_last = (i == t->n_hidden - 1);
         dim3 grid(L.N / TC_BN, Mpad / TC_BM);
         const int kblocks = L.Kp / TC_BK;
-        if (unfused && !need_persist)
+        // CTA-pair (cta_group::2) kernel with 256 x 256 tiles: 15 % faster than the single-CTA kernel once
+        // every pair has several tiles to work through (measured: 203 vs 177 algorithmic TFLOP/s at 65,536
+        // rows), slower below that (fewer, larger tiles per wave).  CRLK_MLP_PAIR=0 / 128 / 256 forces.
+        static const int pair_env = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
+        const int pair = pair_env >= 0 ? pair_env : (B >= 24576 ? 256 : 0);
+        if (pair == 256 && Mpad % (2 * TC_BM) == 0 && L.N % 256 == 0) {
+            int tiles = (L.N / 256) * (Mpad / (2 * TC_BM));
+            int pairs = tiles < n_sms / 2 ? tiles : n_sms / 2;
+            k_gemm_bf16x3_pair<256><<<2 * pairs, TC_THREADS, PairCfg<256>::smem, st>>>(
+                mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
+                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N, n_rows_dev,
+                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks);
+        } else if (pair && Mpad % (2 * TC_BM) == 0) {
+            int tiles = (L.N / TC_BN) * (Mpad / (2 * TC_BM));
+            int pairs = tiles < n_sms / 2 ? tiles : n_sms / 2;
+            k_gemm_bf16x3_pair<128><<<2 * pairs, TC_THREADS, PairCfg<128>::smem, st>>>(
+                mapA, L.map_wh, Mpad, L.N, kblocks, d_bias[i], B,
+                is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N, n_rows_dev,
+                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks);
+        } else if (unfused && !need_persist)
             k_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
                 mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
                 is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N);

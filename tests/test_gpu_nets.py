@@ -167,3 +167,24 @@ def test_extend_rl_large_batch_split_is_invisible():
             assert np.array_equal(whole["node_step"][lo + q, :part["n_nodes"][q]], part["node_step"][q, :part["n_nodes"][q]])
         lo = hi
     assert (whole["n_steps"][np_(active) == 0] == 0).all() and whole["n_steps"].max() > 10
+
+
+def test_policy_forward_large_batch_pair_kernel():
+    """Batches >= 24,576 rows run the hidden layers on the CTA-pair GEMM (tcgen05.mma.cta_group::2,
+    256 x 256 tiles, W halves shared between two SMs); smaller ones on the single-CTA kernel.  Both
+    accumulate every output in the same order, so a large batch must equal, bit for bit, the same rows
+    evaluated in small chunks -- and agree with the oracle's float64-checked forward pass."""
+    import torch
+    from crl_kino_b200 import ops
+    pol = _policy(5)
+    rng = np.random.default_rng(6)
+    B = 24576 + 256
+    obs = np.concatenate([rng.normal(0, 4, (B, 4)), (rng.uniform(0, 1, (B, 729)) > 0.4).astype(np.float64)], 1)
+    o32 = ops.pad_obs(obs)
+    noise = torch.as_tensor(rng.standard_normal((B, 2)).astype(np.float32)).cuda()
+    big = np_(ops.policy_forward(pol.actor.handle, o32, noise, 0.05))
+    for lo in (0, 4096, B - 1024):
+        part = np_(ops.policy_forward(pol.actor.handle, o32[lo:lo + 1024].contiguous(), noise[lo:lo + 1024].contiguous(), 0.05))
+        assert np.array_equal(big[lo:lo + 1024], part)
+    ref = orc.actor_forward(pol.actor.weights, pol.actor.biases, obs[:256], np_(noise)[:256], 0.05)
+    np.testing.assert_allclose(big[:256], ref, rtol=1e-4, atol=1e-5)
