@@ -878,8 +878,6 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         sm.ihdr[1] = min(arange_len(wl, wh + d.w_res, d.w_res), d.nw_max);
         sm.cl_n[0] = 0;
     }
-    // clearance of the shared first row (dwa.py:65-67, i = 0): one thread, next to the header thread
-    if (CLR && tid == T - 1) sm.hdr[4] = pymax(clearance_thread(e, os, st[0], st[1], st[2]), 0.001);
     const int S = d.n_sub * d.n_outer, spos = sm.spos;
 
     PHASE_START();
@@ -924,21 +922,28 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     }
     double clr0 = CRLK_CLEARANCE_CAP;
     if (CLR) {
-        clr0 = sm.hdr[4];
-        // Obstacle list of this control step: a rollout pose lies within `reach` of the current
-        // position and only clearances below min(clr0, 100) change a rollout's minimum, so an
-        // obstacle can matter only if its rectangle is closer than that + rc + reach to the current
-        // position.  Each obstacle is taken from the one cell that holds its closest point.
+        // Clearance term, block-cooperative part.  (1) The clearance of the current state (the shared
+        // first row, dwa.py:65-67): the block gathers the obstacles within a radius guessed from the
+        // previous control step's clearance and takes the minimum over them, one entry per thread --
+        // valid when it is small enough that nothing outside that radius could beat it; otherwise one
+        // thread runs the grid search.  (2) The obstacle list of the rollouts: a rollout pose lies
+        // within `reach` of the current position and only clearances below min(clr0, 100) change a
+        // rollout's minimum, so an obstacle matters only if its rectangle is closer than that + rc +
+        // reach to the current position.  Each obstacle is taken from the one cell that holds its
+        // closest point.
         const float reach = (float)(fmax(fabs(e.max_v), fabs(e.min_v)) * e.base_dt * S) * 1.001f + 1e-3f;
-        const float rl = (float)fmin(clr0, CRLK_CLEARANCE_CAP) * 1.0001f + e.rc + reach + 2.0f * CRLK_CULL_MARGIN;
         const float p0x = (float)st[0], p0y = (float)st[1];
         const float hxm = (float)(os.ncx - 1), hym = (float)(os.ncy - 1);
         auto cellx = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gx0) * os.ginv), 0.f), hxm); };
         auto celly = [&](float v) { return (int)fminf(fmaxf(floorf((v - os.gy0) * os.ginv), 0.f), hym); };
-        const int bx0 = cellx(p0x - rl - 2e-3f), bx1 = cellx(p0x + rl + 2e-3f);
-        const int by0 = celly(p0y - rl - 2e-3f), by1 = celly(p0y + rl + 2e-3f);
-        const int bw = bx1 - bx0 + 1, ncell_box = bw * (by1 - by0 + 1);
-        if ((long long)ncell_box <= 64LL * T) {
+        auto gather = [&](float rl) {
+            const int bx0 = cellx(p0x - rl - 2e-3f), bx1 = cellx(p0x + rl + 2e-3f);
+            const int by0 = celly(p0y - rl - 2e-3f), by1 = celly(p0y + rl + 2e-3f);
+            const int bw = bx1 - bx0 + 1, ncell_box = bw * (by1 - by0 + 1);
+            if ((long long)ncell_box > 64LL * T) {
+                if (tid == 0) sm.cl_n[0] = CL_CAP + 1;      // open space: grid search per pose
+                return;
+            }
             for (int c = tid; c < ncell_box; c += T) {
                 const int cy = by0 + c / bw, cx = bx0 + (c - (c / bw) * bw);
                 const int s0 = __ldg(&os.cell_start[cy * os.ncx + cx]), s1 = __ldg(&os.cell_start[cy * os.ncx + cx + 1]);
@@ -952,9 +957,43 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                     if (pos < CL_CAP) sm.clist[pos] = o;
                 }
             }
-        } else if (tid == 0) {
-            sm.cl_n[0] = CL_CAP + 1;              // box too large (open space): grid search per pose
+        };
+        const double prev = sm.hdr[5];                            // clearance of the previous control step's state
+        const float guess = (float)((prev > 0.0 && prev < 20.0) ? prev + 0.25 : 1.0);
+        const float ra = guess * 1.0001f + e.rc + 2.0f * CRLK_CULL_MARGIN;   // covers every obstacle closer than `guess` to the footprint
+        gather(ra);
+        __syncthreads();
+        const int n0 = sm.cl_n[0];
+        double mine = CRLK_CLEARANCE_CAP;
+        if (n0 <= CL_CAP) {
+            RobotPose g0;
+            robot_pose_setup(e, st[0], st[1], st[2], g0);
+            const float cf0 = (float)g0.c, sf0 = (float)g0.s;
+            for (int k = tid; k < n0; k += T) {
+                const float4 o = sm.clist[k];
+                if (footprint_lb(e, cf0, sf0, p0x, p0y, o) > (float)fmax(mine, 0.0) * 1.0001f) continue;
+                bool dd, mm;
+                mine = fmin(mine, dis2obs_exact(e, g0, o, dd, mm));
+            }
         }
+        mine = warp_min_d(mine);
+        if (lane == 0) sm.red_v[warp] = mine;
+        __syncthreads();
+        double c_l = (lane < T / 32) ? sm.red_v[lane] : CRLK_CLEARANCE_CAP;
+        c_l = warp_min_d(c_l);
+        // an obstacle outside the gathered radius is farther than ra - rc from the footprint
+        const bool settled = n0 <= CL_CAP && (c_l < 0.0 || c_l <= (double)(ra - e.rc) - 4.0 * CRLK_CULL_MARGIN);
+        if (!settled) {
+            if (tid == T - 1) sm.hdr[4] = clearance_thread(e, os, st[0], st[1], st[2]);
+            __syncthreads();
+            c_l = sm.hdr[4];
+        }
+        clr0 = pymax(c_l, 0.001);
+        const float rl = (float)fmin(clr0, CRLK_CLEARANCE_CAP) * 1.0001f + e.rc + reach + 2.0f * CRLK_CULL_MARGIN;
+        __syncthreads();                                          // everyone has read cl_n / the first list
+        if (tid == 0) { sm.cl_n[0] = 0; sm.hdr[5] = c_l; }
+        __syncthreads();
+        gather(rl);
     }
     __syncthreads();
     PHASE_MARK(1);
@@ -1178,6 +1217,7 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5];
     load_atan_table(sm.atab);
+    if (threadIdx.x == 0) sm.hdr[5] = -1.0;                       // no previous control step yet
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
@@ -1389,6 +1429,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
     load_atan_table(sm.atab);
+    if (threadIdx.x == 0) sm.hdr[5] = -1.0;                       // no previous control step yet
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
         __syncthreads();
@@ -1611,6 +1652,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
     __shared__ int s_q;
     const int tid = threadIdx.x;
     load_atan_table(sm.atab);
+    if (threadIdx.x == 0) sm.hdr[5] = -1.0;                       // no previous control step yet
     for (;;) {
         __syncthreads();
         if (tid == 0) s_q = atomicAdd(work_counter, 1);
