@@ -200,7 +200,10 @@ int crlk_policy_create(int32_t n_layers, const int32_t *dims, const float *const
 int crlk_policy_destroy(CrlkPolicy *p);
 /* obs dev f32[B x ld_obs]; noise dev f32[B x 2] (nullable: no exploration
  * noise); act dev f32[B x 2] = clamp(tanh(mlp) + noise*eps) * scale + bias).
- * workspace dev bytes from crlk_policy_workspace_bytes(p, B). */
+ * workspace dev bytes from crlk_policy_workspace_bytes(p, B).
+ * Hidden layers whose widths are multiples of 128 run on the tensor cores (tcgen05, float32 operands as
+ * three bf16 planes, float32 accumulation: float32-level accuracy); B >= 24,576 uses the CTA-pair
+ * kernel (cta_group::2).  Other widths use a float32 SIMT GEMM. */
 int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_t ld_obs, const float *noise,
                         float eps, int32_t B, float *act, void *workspace, void *stream);
 int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
@@ -212,7 +215,12 @@ int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
  * advanced by the number of executed steps, so consecutive extensions of a query
  * walk its stream (the caller keeps noise_rows large enough).  Without a cursor
  * row k-1 is used at step k (noise_rows >= n_max_extend).
- * workspace: crlk_extend_rl_workspace_bytes. */
+ * workspace: crlk_extend_rl_workspace_bytes, 256-byte aligned.
+ * Every policy step runs on the compacted batch of queries that are still extending (row lists and
+ * counts live on the device, no host synchronisation); batches of 2048 queries or more advance as two
+ * halves on `stream` and an internal second stream (joined before the call's last kernel), so the
+ * GEMMs of one half overlap the observation / motion / collision kernels of the other.  Results do
+ * not depend on either.  The call is not re-entrant per device (serialised internally). */
 int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
                    const double *from_states, const double *targets, int32_t Q, const float *noise,
                    int32_t noise_rows, int32_t *noise_cursor, float eps, double *path, int32_t *n_steps,
