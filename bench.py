@@ -343,6 +343,13 @@ def sub_rates(env, dwa, peaks):
         out["estimator_tflops_algorithmic"] = 2 * 1.158038e6 * Bo / (ms * 1e-3) / 1e12     # 2 nets x 579,019 MAC x 2
     except Exception as e:                                                     # weights file not present
         out["estimator"] = f"skipped: {e}"
+    # gym side: B environments per crlk_gym_step call (motion + _info + _reward + _obs)
+    Bg = 1 << 15
+    gs = states[:Bg].clone()
+    acts = ops.as_dev(np.stack([rng.uniform(-0.1, 1.0, Bg), rng.uniform(-np.pi, np.pi, Bg)], 1))
+    rp = np.array([50.0, -1.5, -0.5, -300.0, 1.0, 1.0, -.5, -2.5])
+    ms = timed(lambda: ops.gym_step(env.handle, gs, goals[:Bg], acts, rp, 0.2, want64=False, want32=True), 5)
+    out["gym_env_steps_per_sec"] = Bg / (ms * 1e-3)
     Bd = 4096
     free = states[:Bd].clone()
     free[:, 3] = 0.4
