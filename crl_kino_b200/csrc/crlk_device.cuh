@@ -294,6 +294,34 @@ __device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py,
     }
 }
 
+// The same visit for a whole CTA: the grid rows of the box are handled side by side (thread t takes
+// row t / per, entries t % per, t % per + per, ...), so a thread's loads are one dependent chain
+// cell_start -> cell_items -> rects instead of one such chain per row.  Not uniform across threads:
+// the visitor must not use collectives.
+template <class F>
+__device__ __forceinline__ void grid_visit_rows(const ObsSet &os, float px, float py, float thr, int t,
+                                                int nthreads, F f)
+{
+    float r = thr + 2e-3f;
+    float hx = (float)(os.ncx - 1), hy = (float)(os.ncy - 1);
+    int cx0 = (int)fminf(fmaxf(floorf((px - r - os.gx0) * os.ginv), 0.f), hx);
+    int cx1 = (int)fminf(fmaxf(floorf((px + r - os.gx0) * os.ginv), 0.f), hx);
+    int cy0 = (int)fminf(fmaxf(floorf((py - r - os.gy0) * os.ginv), 0.f), hy);
+    int cy1 = (int)fminf(fmaxf(floorf((py + r - os.gy0) * os.ginv), 0.f), hy);
+    const int nrows = cy1 - cy0 + 1;
+    if (nrows > nthreads) {       // never with the planners' footprints; keep the result complete anyway
+        grid_visit(os, px, py, thr, t, nthreads, [&](int o, bool in) { if (in) f(o); });
+        return;
+    }
+    const int per = nthreads / nrows;
+    const int row = t / per, idx = t - row * per;
+    if (row >= nrows) return;
+    const int cy = cy0 + row;
+    const int s = __ldg(&os.cell_start[cy * os.ncx + cx0]);
+    const int e = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
+    for (int k = s + idx; k < e; k += per) f(__ldg(&os.cell_items[k]));
+}
+
 // get_clearance (differential_env.py:126-132) for one pose by ONE thread.  The grid cells are
 // visited ring by ring around the pose's own cell (Chebyshev rings 0, 1, 2, ...): everything listed
 // only in ring k or beyond lies at least (k - 1) cells away, so the search stops as soon as that

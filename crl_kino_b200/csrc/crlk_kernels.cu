@@ -1333,8 +1333,7 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose 
     bool coll = false, definite = false, marginal = false;
     // each thread screens its share of the cell lists and tests its survivors at once
     // (a pose touches a few hundred listed obstacles at most: <= 1-2 per thread)
-    grid_visit(os, px, py, thr, tid, T, [&](int o, bool in) {
-        if (!in) return;
+    grid_visit_rows(os, px, py, thr, tid, T, [&](int o) {
         float4 r = __ldg(&rects[o]);
         if (aabb_center_d2(r, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, r) <= cthr) {
             bool d, m;
@@ -1342,7 +1341,9 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose 
             definite |= d; marginal |= m;
         }
     });
-    // barrier-fused reductions
+    // barrier-fused reductions; most poses are not within the threshold band of any obstacle's
+    // bounding circle, so no thread ran an exact test and one barrier settles it
+    if (!__syncthreads_or(coll | definite | marginal)) return 0;
     int any_coll = __syncthreads_or(coll);
     int any_def = __syncthreads_or(definite);
     int any_mar = __syncthreads_or(marginal);
