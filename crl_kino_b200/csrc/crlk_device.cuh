@@ -296,7 +296,7 @@ __device__ __forceinline__ void grid_visit(const ObsSet &os, float px, float py,
 
 // The same visit for a whole CTA: the grid rows of the box are handled side by side (thread t takes
 // row t / per, entries t % per, t % per + per, ...), so a thread's loads are one dependent chain
-// cell_start -> cell_items -> rects instead of one such chain per row.  Not uniform across threads:
+// cell_start -> cell_rects instead of a chain cell_start -> cell_items -> rects per row.  Not uniform across threads:
 // the visitor must not use collectives.
 template <class F>
 __device__ __forceinline__ void grid_visit_rows(const ObsSet &os, float px, float py, float thr, int t,
@@ -310,7 +310,7 @@ __device__ __forceinline__ void grid_visit_rows(const ObsSet &os, float px, floa
     int cy1 = (int)fminf(fmaxf(floorf((py + r - os.gy0) * os.ginv), 0.f), hy);
     const int nrows = cy1 - cy0 + 1;
     if (nrows > nthreads) {       // never with the planners' footprints; keep the result complete anyway
-        grid_visit(os, px, py, thr, t, nthreads, [&](int o, bool in) { if (in) f(o); });
+        grid_visit(os, px, py, thr, t, nthreads, [&](int o, bool in) { if (in) f(__ldg(&os.rects[o])); });
         return;
     }
     const int per = nthreads / nrows;
@@ -319,7 +319,7 @@ __device__ __forceinline__ void grid_visit_rows(const ObsSet &os, float px, floa
     const int cy = cy0 + row;
     const int s = __ldg(&os.cell_start[cy * os.ncx + cx0]);
     const int e = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
-    for (int k = s + idx; k < e; k += per) f(__ldg(&os.cell_items[k]));
+    for (int k = s + idx; k < e; k += per) f(__ldg(&os.cell_rects[k]));
 }
 
 // get_clearance (differential_env.py:126-132) for one pose by ONE thread.  The grid cells are
@@ -356,7 +356,7 @@ static __device__ __noinline__ double clearance_grid_exact(const EnvP &e, const 
         const int c = cy * os.ncx + cx;
         const int s = __ldg(&os.cell_start[c]), en = __ldg(&os.cell_start[c + 1]);
         for (int k = s; k < en; k++) {
-            const float4 o = __ldg(&os.rects[__ldg(&os.cell_items[k])]);
+            const float4 o = __ldg(&os.cell_rects[k]);
             const float qx = fminf(fmaxf(px, o.x), o.z), qy = fminf(fmaxf(py, o.y), o.w);   // closest point of the AABB
             const float dx = px - qx, dy = py - qy;
             if (dx * dx + dy * dy > lim * lim) continue;
@@ -503,7 +503,7 @@ static __device__ __noinline__ double clearance_grid_thread(const EnvP &e, const
         const int s = __ldg(&os.cell_start[c]), en = __ldg(&os.cell_start[c + 1]);
         for (int k = s; k < en; k++) {
             const int id = __ldg(&os.cell_items[k]);
-            const float4 o = __ldg(&os.rects[id]);
+            const float4 o = __ldg(&os.cell_rects[k]);
             const float qx = fminf(fmaxf(px, o.x), o.z), qy = fminf(fmaxf(py, o.y), o.w);   // closest point of the AABB
             const float dx = px - qx, dy = py - qy;
             if (dx * dx + dy * dy > lim * lim) continue;
@@ -684,7 +684,7 @@ __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, 
             int s0 = __ldg(&os.cell_start[cy * os.ncx + cx0]);
             int e0 = __ldg(&os.cell_start[cy * os.ncx + cx1 + 1]);
             for (int i = s0; i < e0; i++) {
-                float4 r = __ldg(&os.rects[__ldg(&os.cell_items[i])]);
+                float4 r = __ldg(&os.cell_rects[i]);
                 double l = r.x, bo = r.y, rr = r.z, t = r.w;
                 occ |= (px >= l && px <= rr && py >= bo && py <= t);
                 if (!WANT_NEAR) continue;

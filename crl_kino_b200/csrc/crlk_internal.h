@@ -21,6 +21,7 @@ struct ObsSet {
     const float4 *rects;      // [M] left, bottom, right, top
     const int *cell_start;    // [ncx * ncy + 1]
     const int *cell_items;    // obstacle ids, cell by cell
+    const float4 *cell_rects; // rects[cell_items[k]] stored again in cell order: one dependent load less
     int M, ncx, ncy;
     float gx0, gy0, ginv;     // grid origin and 1 / cell size
     // occupancy raster for point queries (same origin, CRLK_RASTER_SUB cells per grid cell and axis):
@@ -51,6 +52,7 @@ struct CrlkEnv {
     EnvP p;
     float4 *d_rects;  // M obstacles [l, b, r, t]
     int *d_cell_start, *d_cell_items;
+    float4 *d_cell_rects;
     uint8_t *d_raster;
     ObsSet os;
     int M;

@@ -185,20 +185,30 @@ static int build_grid(CrlkEnv *env, const float *r, int M)
     }
     if (env->d_cell_start) cudaFree(env->d_cell_start);
     if (env->d_cell_items) cudaFree(env->d_cell_items);
+    if (env->d_cell_rects) cudaFree(env->d_cell_rects);
     env->d_cell_start = env->d_cell_items = nullptr;
+    env->d_cell_rects = nullptr;
+    // the rectangles once more in cell order (16 B per list entry; ~1 MB for the 10,004-obstacle map)
+    float4 *crects = (float4 *)malloc(sizeof(float4) * (size_t)(total + 1));
+    for (int k = 0; k < total; k++)
+        crects[k] = make_float4(r[4 * items[k]], r[4 * items[k] + 1], r[4 * items[k] + 2], r[4 * items[k] + 3]);
     cudaError_t e1 = cudaMalloc(&env->d_cell_start, sizeof(int) * ((size_t)ncell + 1));
     cudaError_t e2 = cudaMalloc(&env->d_cell_items, sizeof(int) * (size_t)(total + 1));
+    if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMalloc(&env->d_cell_rects, sizeof(float4) * (size_t)(total + 1));
     if (e1 == cudaSuccess && e2 == cudaSuccess) {
         e1 = cudaMemcpy(env->d_cell_start, start, sizeof(int) * ((size_t)ncell + 1), cudaMemcpyHostToDevice);
         e2 = cudaMemcpy(env->d_cell_items, items, sizeof(int) * (size_t)(total + 1), cudaMemcpyHostToDevice);
+        if (e2 == cudaSuccess)
+            e2 = cudaMemcpy(env->d_cell_rects, crects, sizeof(float4) * (size_t)total, cudaMemcpyHostToDevice);
     }
-    free(start); free(items); free(fill);
+    free(start); free(items); free(fill); free(crects);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         crlk_set_error("obstacle grid upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         return CRLK_E_CUDA;
     }
     env->os.rects = env->d_rects; env->os.cell_start = env->d_cell_start;
     env->os.cell_items = env->d_cell_items;
+    env->os.cell_rects = env->d_cell_rects;
     env->os.M = M; env->os.ncx = ncx; env->os.ncy = ncy;
     env->os.gx0 = x0; env->os.gy0 = y0; env->os.ginv = ginv;
     env->os.raster = env->d_raster; env->os.rnx = rnx; env->os.rny = rny;
@@ -245,6 +255,7 @@ extern "C" int crlk_env_destroy(CrlkEnv *env)
     if (env->d_rects) cudaFree(env->d_rects);
     if (env->d_cell_start) cudaFree(env->d_cell_start);
     if (env->d_cell_items) cudaFree(env->d_cell_items);
+    if (env->d_cell_rects) cudaFree(env->d_cell_rects);
     if (env->d_raster) cudaFree(env->d_raster);
     delete env;
     return CRLK_OK;
@@ -948,7 +959,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                 const int cy = by0 + c / bw, cx = bx0 + (c - (c / bw) * bw);
                 const int s0 = __ldg(&os.cell_start[cy * os.ncx + cx]), s1 = __ldg(&os.cell_start[cy * os.ncx + cx + 1]);
                 for (int k = s0; k < s1; k++) {
-                    const float4 o = __ldg(&os.rects[__ldg(&os.cell_items[k])]);
+                    const float4 o = __ldg(&os.cell_rects[k]);
                     const float qx = fminf(fmaxf(p0x, o.x), o.z), qy = fminf(fmaxf(p0y, o.y), o.w);
                     const float dx = p0x - qx, dy = p0y - qy;
                     if (dx * dx + dy * dy > rl * rl) continue;
@@ -1322,7 +1333,6 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
 __device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose *gp)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    const float4 *__restrict__ rects = os.rects;
     const RobotPose g = *gp;
     const double x = g.x, y = g.y;
     float px = (float)x, py = (float)y;
@@ -1333,8 +1343,7 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose 
     bool coll = false, definite = false, marginal = false;
     // each thread screens its share of the cell lists and tests its survivors at once
     // (a pose touches a few hundred listed obstacles at most: <= 1-2 per thread)
-    grid_visit_rows(os, px, py, thr, tid, T, [&](int o) {
-        float4 r = __ldg(&rects[o]);
+    grid_visit_rows(os, px, py, thr, tid, T, [&](float4 r) {
         if (aabb_center_d2(r, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, r) <= cthr) {
             bool d, m;
             coll |= dis2obs_exact(e, g, r, d, m) < 0.0;
