@@ -903,6 +903,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     for (int i = tid; i < nv; i += T) {
         double cv = arange_at(v_lo, v1, vd, i);
         double cur = st[3];
+#pragma unroll 1
         for (int k = 0; k < S; k++) {
             double nxt = vel_substep(cur, cv, e.max_acc_v, e.min_v, e.max_v, dt);
             // f(cur) == cur is a fixed point of the (deterministic) sub-step: every later
@@ -920,6 +921,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         const int j = task / spos, ks = task - j * spos;
         double cw = arange_at(w_lo, w1, wd, j);
         double cur = st[4], th = st[2];
+#pragma unroll 1
         for (int k = 0; k <= ks; k++) {
             cur = vel_substep(cur, cw, e.max_acc_w, -e.max_w, e.max_w, dt);
             th = normalize_angle(th + cur * dt);
@@ -1025,9 +1027,20 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         const double *wc = sm.wcos + j, *ws = sm.wsin + j;
         const int nwm = d.nw_max;
         x = st[0]; y = st[1];
-        for (int k = 0; k < d.n_sub; k++) {
-            x = x + vt[k] * wc[k * nwm] * dt;
-            y = y + vt[k] * ws[k * nwm] * dt;
+        if (d.n_sub == 2) {
+            // the planners' 0.2 s control step: two 0.1 s sub-steps, straight-line code (left to
+            // itself the compiler unrolls the general loop 8/4/2/1-fold and spends more
+            // instructions on the remainder cascade than on the two sub-steps)
+            x = x + vt[0] * wc[0] * dt;
+            y = y + vt[0] * ws[0] * dt;
+            x = x + vt[1] * wc[nwm] * dt;
+            y = y + vt[1] * ws[nwm] * dt;
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < d.n_sub; k++) {
+                x = x + vt[k] * wc[k * nwm] * dt;
+                y = y + vt[k] * ws[k * nwm] * dt;
+            }
         }
         double ang = crlk_atan2(gy - y, gx - x, sm.atab);
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
@@ -1194,6 +1207,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             const double *vt = sm.vtab + i * spos;
             const double *wc = sm.wcos + j, *ws = sm.wsin + j;
             double x = st[0], y = st[1];
+#pragma unroll 1
             for (int k = 0; k < d.n_sub; k++) {
                 x = x + vt[k] * wc[k * d.nw_max] * dt;
                 y = y + vt[k] * ws[k * d.nw_max] * dt;
