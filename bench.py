@@ -29,7 +29,7 @@ M_FLOP_PAIR = 860.0         # FP ops per (pose, obstacle) pair, brute force
 FP64_LANES_PER_SM = 64      # B200: 64 FP64 FMA lanes per SM
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures
 # summarised in profiles/r1d_* / r1h_*_ncu_summary.txt (default workload sizes only)
-NCU_TRAFFIC_EXTEND_DWA = 261.632e3 + 512.0             # k_extend_dwa, 1024 queries, cfg4 map (profiles/r1j_extend_ncu_summary.txt)
+NCU_TRAFFIC_EXTEND_DWA = 244.224e3 + 0.0               # k_extend_dwa, 1024 queries, cfg4 map (profiles/r1t_extend_ncu_summary.txt)
 NCU_TRAFFIC_NEAREST = 820.148992e6 + 4.725248e6       # k_nearest, 1024 trees x 100,000 nodes
 
 
@@ -502,10 +502,10 @@ def run_ours(args):
             "roofline": {"kernel": "k_extend_dwa", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": NCU_TRAFFIC_EXTEND_DWA if (Q == 1024 and args.cells == 10000 and not args.use_clearance) else None,
-                         "ncu": "profiles/r1j_extend_ncu_summary.txt: fp64 pipe 27.0 % while active, issue slots 53.4 %, 128 regs, 2 CTAs/SM, launch time = longest chain of dependent control steps",
-                         "executed": {"fp64_pipe_pct_of_peak_while_active": 26.3, "issue_slots_pct": 51.4,
-                                      "sm_throughput_pct_of_elapsed": 34.8, "warp_instructions_per_launch": 172328128,
-                                      "source": "profiles/r1j_extend_ncu_summary.txt (ncu --set full, same command)"},
+                         "ncu": "profiles/r1t_extend_ncu_summary.txt: fp64 pipe 29.4 % while active, issue slots 51.7 %, 128 regs, 2 CTAs/SM; top stalls: fixed-latency dependencies of the float64 chains, then barriers",
+                         "executed": {"fp64_pipe_pct_of_peak_while_active": 29.4, "issue_slots_pct": 51.7,
+                                      "sm_throughput_pct_of_elapsed": 35.5, "warp_instructions_per_launch": 146798117,
+                                      "source": "profiles/r1t_extend_ncu_summary.txt (ncu --set full, same command)"},
                          "peak_source": f"derived: {sms} SM x {FP64_LANES_PER_SM} FP64 FMA lanes x 2 x "
                                         f"{sm_max:.0f} MHz (MEASURED_PEAKS.json holds only HBM and bf16 peaks)",
                          "algorithmic_flop_per_launch": flop / K,
