@@ -1047,6 +1047,44 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         return pymin(c0, CRLK_TWO_PI - c0);
     };
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+#ifdef CRLK_ROWMAJOR
+    // Experimental (off by default, A/B with CRLK_DEFS=CRLK_ROWMAJOR): one v command per thread.
+    // For a fixed v command the cost is a non-decreasing function of the heading cost alone (same
+    // speed term, constant obstacle term), so a thread that walks w commands of ONE row only has to
+    // remember the row's two smallest heading costs: no c0 array, no second pass over all rollouts,
+    // velocity-chain values loop-invariant, cos / sin loads warp-uniform.
+    const bool rowmajor = !CLR && nv <= T;
+    double tb0 = CUDART_INF, tb1 = CUDART_INF;
+    int tjb = 0, ti = 0;
+    if (rowmajor) {
+        const int G = T / nv;
+        const int jg = tid / nv;
+        ti = tid - jg * nv;
+        if (jg < G) {
+            auto track = [&](double c, int j) {
+                if (c < tb0) { tb1 = tb0; tb0 = c; tjb = j; }       // j ascends: the first minimum stays
+                else if (c < tb1) tb1 = c;
+            };
+            int j = jg;
+            for (; j + G < nw; j += 2 * G) {
+                double xa, ya, xb, yb;
+                double ca = heading_cost(ti, j, xa, ya);
+                double cb = heading_cost(ti, j + G, xb, yb);
+                acc0 += ca;
+                acc0 += cb;
+                track(ca, j);
+                track(cb, j + G);
+            }
+            if (j < nw) {
+                double xa, ya;
+                double ca = heading_cost(ti, j, xa, ya);
+                acc0 += ca;
+                track(ca, j);
+            }
+            if (tb0 < CUDART_INF) sm.c0[ti * nw + tjb] = tb0;      // kept for the reported cost of the winner
+        }
+    } else
+#endif
     if (!CLR) {
         // two independent rollouts per iteration: the FP64 dependency chains overlap
         int r = tid;
@@ -1145,6 +1183,23 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     };
     double best = CUDART_INF, second = CUDART_INF;
     int bi = 0x7fffffff;            // bits 0-15 rollout index, bits 16-30 its v index (saves an integer division)
+#ifdef CRLK_ROWMAJOR
+    if (rowmajor) {
+        if (tb0 < CUDART_INF) {
+            auto cost_val = [&](double c0v) {
+                return d.g_goal * (c0v * inv0) + d.g_ob * c1n_const + d.g_speed * ((v_hi - sm.vlast[ti]) * inv2);
+            };
+            best = cost_val(tb0);
+            bi = (ti * nw + tjb) | (ti << 16);
+            if (tb1 < CUDART_INF) {
+                second = cost_val(tb1);
+                // two different heading costs that round to the same cost: report it as a near tie
+                if (second == best && tb1 > tb0) second = best * (1.0 + 1e-12);
+            }
+        }
+    } else
+#endif
+    {
     ri = tid / nw; rj = tid - ri * nw;
     for (int r = tid; r < R; r += T) {
         const int i = ri;
@@ -1153,6 +1208,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         double c = cost_of(r, i);
         if (c < best) { second = best; best = c; bi = r | (i << 16); }       // r ascends: the first minimum stays
         else if (c < second) second = c;
+    }
     }
     // (minimum, its first index, runner-up) across the warp, then across the block by warp 0
 #pragma unroll
