@@ -72,7 +72,7 @@ PROTOTYPES = {
     "crlk_dwa_control": (C.c_int, [P, P, P, P, I32, I32, P, P, P, P, P, P, P]),
     "crlk_dwa_traj_rows": (C.c_int, [P, P]),
     "crlk_dwa_max_rollouts": (C.c_int, [P, P]),
-    "crlk_nearest": (C.c_int, [P, P, P, P, I64, P, I32, F64, P, I32, I32, P, P, P, P, P]),
+    "crlk_nearest": (C.c_int, [P, P, I32, P, P, I64, P, I32, F64, P, I32, I32, P, P, P, P, P]),
     "crlk_nearest_scratch_bytes": (I64, [I32, I32]),
     "crlk_extend_dwa": (C.c_int, [P, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P]),
     "crlk_gather_rows": (C.c_int, [P, I64, I32, P, I32, P, P]),
@@ -82,6 +82,7 @@ PROTOTYPES = {
     "crlk_rrt_select": (C.c_int, [P, P, I32, I32, F64, F64, P, P, P, P]),
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
     "crlk_debug_atan2": (C.c_int, [P, P, I32, P, P]),
+    "crlk_debug_div": (C.c_int, [P, P, I32, P, P, P]),
     "crlk_gym_step": (C.c_int, [P, P, P, I32, P, F64, P, I32, P, P, P, P, I32, P, P]),
     "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P, P]),
     "crlk_sample_stream": (C.c_int, [P, P, I32, I32, P, P]),

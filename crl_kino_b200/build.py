@@ -15,7 +15,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "--expt-extended-lambda", "--expt-re
 EXTRA_DEFS = ["-D" + d for d in os.environ.get("CRLK_DEFS", "").split() if d]
 UNITS = [("crlk_kernels.cu", ["--fmad=false"] + EXTRA_DEFS),
          ("crlk_planner.cu", ["--fmad=false"]),
-         ("crlk_nets.cu", []),
+         ("crlk_nets.cu", ["--fmad=false"] + EXTRA_DEFS),   # shares the float64 helpers of crlk_device.cuh; float32 FMAs are explicit
          ("crlk_mlp_tc.cu", EXTRA_DEFS)]
 
 

@@ -699,6 +699,31 @@ __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, 
     return occ;
 }
 
+// ------------------------------------------------- numpy's pairwise summation
+//
+// np.sum over a float64 column (dwa.py:76-78) runs DOUBLE_pairwise_sum: blocks of <= 128 elements
+// are added with eight strided accumulators, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a
+// sequential tail; longer inputs are split at n2 = n/2 - (n/2) % 8 and the two halves added.  The
+// tree only depends on n, the halves differ by < 16 elements, so all leaves sit at depth Dmin or
+// Dmin + 1 (checked on the host for every grid size a DwaP can produce, crlk_make_dwa) and the top
+// Dmin levels form a complete binary tree -- which a warp-shuffle butterfly reproduces exactly
+// (IEEE addition is commutative; the butterfly pairs exactly the tree's siblings).
+
+__host__ __device__ inline int pw_split(int n) { const int h = n >> 1; return h - (h & 7); }
+__host__ __device__ inline int pw_min_depth(int n) { int d = 0; while (n > 128) { n = pw_split(n); d++; } return d; }
+__host__ __device__ inline int pw_max_depth(int n) { int d = 0; while (n > 128) { n -= pw_split(n); d++; } return d; }
+
+// a / b rounded to nearest, given y = RN(1 / b): one multiply and two fused corrections instead
+// of the division sequence (Markstein: q' = RN(q + (a - b q) y) is the correctly rounded quotient
+// when y is the correctly rounded reciprocal and q is within an ulp).  crlk_debug_div compares it
+// with the division operator on the device (tests/test_gpu_dwa.py).
+__device__ __forceinline__ double div_rn_y(double a, double b, double y)
+{
+    const double q = a * y;
+    const double r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+
 // ---------------------------------------------------------------- reductions
 
 __device__ __forceinline__ double warp_min_d(double v)

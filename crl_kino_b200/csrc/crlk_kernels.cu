@@ -721,14 +721,36 @@ extern "C" int crlk_debug_atan2(const double *y, const double *x, int32_t n, dou
     return CRLK_OK;
 }
 
+__global__ void k_debug_div(const double *__restrict__ a, const double *__restrict__ b, int n, double *fast,
+                            double *exact)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double y = 1.0 / b[i];
+    fast[i] = div_rn_y(a[i], b[i], y);
+    exact[i] = a[i] / b[i];
+}
+
+// Test hook: the cost normalisation's quotient (div_rn_y with y = 1 / b) next to the division
+// operator, over n pairs (dev f64[n] each).
+extern "C" int crlk_debug_div(const double *a, const double *b, int32_t n, double *fast, double *exact, void *stream)
+{
+    CRLK_REQUIRE(n >= 0 && (n == 0 || (a && b && fast && exact)), "NULL array");
+    if (n == 0) return CRLK_OK;
+    k_debug_div<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, b, n, fast, exact);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
 #define CL_CAP 1024      // capacity of the per-control-step obstacle list of the clearance term
 
 struct DwaSmem {
     double *c0, *c1;
-    double *vtab, *vlast, *c2n;
+    double *vtab, *vlast, *c2;         // c2[i] = v_hi - v_last of v command i (speed column, dwa.py:72)
     double *wcos, *wsin, *wth, *wom;
     double *red_v, *red_s;            // [32] column-sum partials per warp (heading, speed); nearest_block scratch
-    int *red_i;                       // [32] index of the per-warp minimum
+    int *red_i;                       // [64] index of the per-warp minimum, then of the per-warp runner-up
+    double *node;                     // [3][128] level-Dmin node sums of the three cost columns (pairwise tree)
     double *red2_v;                   // [32] third column-sum partial per warp
     double *red3_v, *red3_s;          // [32] minimum / runner-up per warp
     double *hdr;                      // [8]  v_hi v_lo w_hi w_lo of the current window
@@ -765,7 +787,8 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_wom = take(sizeof(double) * d.nw_max);
     size_t o_rv = take(sizeof(double) * 32);
     size_t o_rs = take(sizeof(double) * 32);
-    size_t o_ri = take(sizeof(int) * 32);
+    size_t o_ri = take(sizeof(int) * 64);
+    size_t o_nd = take(sizeof(double) * 384);
     size_t o_r2 = take(sizeof(double) * 32);
     size_t o_r3 = take(sizeof(double) * 64);
     size_t o_hd = take(sizeof(double) * 8);
@@ -779,12 +802,13 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     if (s) {
         s->c0 = (double *)(base + o_c0); s->c1 = (double *)(base + o_c1);
         s->vtab = (double *)(base + o_vtab); s->vlast = (double *)(base + o_vlast);
-        s->c2n = (double *)(base + o_c2n);
+        s->c2 = (double *)(base + o_c2n);
         s->wcos = (double *)(base + o_wcos); s->wsin = (double *)(base + o_wsin);
         s->wth = (double *)(base + o_wth);
         s->wom = (double *)(base + o_wom);
         s->red_v = (double *)(base + o_rv); s->red_s = (double *)(base + o_rs);
         s->red_i = (int *)(base + o_ri);
+        s->node = (double *)(base + o_nd);
         s->red2_v = (double *)(base + o_r2); s->hdr = (double *)(base + o_hd);
         s->red3_v = (double *)(base + o_r3); s->red3_s = s->red3_v + 32;
         s->ihdr = (int *)(base + o_ih); s->pose = (RobotPose *)(base + o_po);
@@ -825,6 +849,23 @@ int crlk_make_dwa(const CrlkEnv *env, const CrlkDwaParams *in, DwaP *d)
     d->nw_max = arange_len(0.0, ww + in->w_res, in->w_res) + 2;
     CRLK_REQUIRE(d->n_sub >= 1 && d->n_outer >= 1 && d->n_sub * d->n_outer <= 4096, "dwa horizon");
     CRLK_REQUIRE((long)d->nv_max * d->nw_max <= 16384, "rollout grid too large (> 16384)");
+    // the column sums reproduce numpy's pairwise tree with a butterfly over its complete top levels:
+    // needs every leaf at depth Dmin or Dmin + 1 (true for all n <= 16384; checked once)
+    static int tree_ok = -1;
+    if (tree_ok < 0) {
+        int ok = 1;
+        for (int n = 1; n <= 16384 && ok; n++) {
+            const int dmin = pw_min_depth(n), dmax = pw_max_depth(n);
+            if (dmax - dmin > 1 || dmin > 7) ok = 0;
+            // a level-Dmin node is a leaf or splits into two leaves: walk the extreme paths' sizes
+            int lo = n, hi = n;
+            for (int k = 0; k < dmin; k++) { lo = pw_split(lo); hi = hi - pw_split(hi); }
+            if (hi > 128 && (hi - pw_split(hi) > 128)) ok = 0;
+            (void)lo;
+        }
+        tree_ok = ok;
+    }
+    CRLK_REQUIRE(tree_ok == 1, "internal: pairwise-sum tree shape assumption violated");
     return CRLK_OK;
 }
 
@@ -845,10 +886,18 @@ extern "C" int crlk_debug_phase_cycles(unsigned long long *out16, int reset)
 
 struct DwaResult {
     double v, w;
-    double S0, S1, S2, v_hi;   // column sums and window top: what the reported cost is made of
-    int idx, R;
+    double cost;               // the winner's cost_sum entry (dwa.py:79-81)
+    int idx, R;                // idx = -1, R = 0: empty rollout grid (state outside the velocity limits)
     int near_tie;
 };
+
+// A runner-up within this many ulp of the winning cost is reported as a near tie (see
+// dwa_control_block): the bound covers the last-bit differences between libm implementations of
+// arctan2 / sin / cos (numpy's SIMD loops, glibc, this file's table-driven atan2), each <= 2 ulp
+// on a heading cost, propagated through the column normalisation.
+#ifndef CRLK_TIE_ULPS
+#define CRLK_TIE_ULPS 32
+#endif
 
 // get_clearance for one pose by one thread (used only when use_clearance = 1).
 __device__ __forceinline__ double clearance_thread(const EnvP &e, const ObsSet &os, double x, double y,
@@ -899,6 +948,14 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     const double v1 = v_lo + d.v_res, vd = v1 - v_lo;
     const double w1 = w_lo + d.w_res, wd = w1 - w_lo;
     const int R = nv * nw;
+    if (R == 0) {
+        // np.arange came out empty: v or omega lies outside the vehicle limits by more than acc * dt
+        // (the reference fails on the empty cost table, dwa.py:76).  Block-uniform exit.
+        DwaResult res;
+        res.v = res.w = res.cost = CUDART_NAN;
+        res.idx = -1; res.R = 0; res.near_tie = 0;
+        return res;
+    }
     // velocity chains (one per v command) and heading chains (one per w command)
     for (int i = tid; i < nv; i += T) {
         double cv = arange_at(v_lo, v1, vd, i);
@@ -914,6 +971,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             else if (fixed) break;
         }
         sm.vlast[i] = cur;
+        sm.c2[i] = v_hi - cur;                     // speed cost of every rollout with this v command (dwa.py:72)
     }
     // heading chains: one task per (w command, sub-step) -- the omega / theta recurrences up to the
     // sub-step are cheap, the float64 sincos at its end is not, so the sub-steps run side by side
@@ -1046,45 +1104,6 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
         return pymin(c0, CRLK_TWO_PI - c0);
     };
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-#ifdef CRLK_ROWMAJOR
-    // Experimental (off by default, A/B with CRLK_DEFS=CRLK_ROWMAJOR): one v command per thread.
-    // For a fixed v command the cost is a non-decreasing function of the heading cost alone (same
-    // speed term, constant obstacle term), so a thread that walks w commands of ONE row only has to
-    // remember the row's two smallest heading costs: no c0 array, no second pass over all rollouts,
-    // velocity-chain values loop-invariant, cos / sin loads warp-uniform.
-    const bool rowmajor = !CLR && nv <= T;
-    double tb0 = CUDART_INF, tb1 = CUDART_INF;
-    int tjb = 0, ti = 0;
-    if (rowmajor) {
-        const int G = T / nv;
-        const int jg = tid / nv;
-        ti = tid - jg * nv;
-        if (jg < G) {
-            auto track = [&](double c, int j) {
-                if (c < tb0) { tb1 = tb0; tb0 = c; tjb = j; }       // j ascends: the first minimum stays
-                else if (c < tb1) tb1 = c;
-            };
-            int j = jg;
-            for (; j + G < nw; j += 2 * G) {
-                double xa, ya, xb, yb;
-                double ca = heading_cost(ti, j, xa, ya);
-                double cb = heading_cost(ti, j + G, xb, yb);
-                acc0 += ca;
-                acc0 += cb;
-                track(ca, j);
-                track(cb, j + G);
-            }
-            if (j < nw) {
-                double xa, ya;
-                double ca = heading_cost(ti, j, xa, ya);
-                acc0 += ca;
-                track(ca, j);
-            }
-            if (tb0 < CUDART_INF) sm.c0[ti * nw + tjb] = tb0;      // kept for the reported cost of the winner
-        }
-    } else
-#endif
     if (!CLR) {
         // two independent rollouts per iteration: the FP64 dependency chains overlap
         int r = tid;
@@ -1100,14 +1119,10 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             double cb = heading_cost(i1, j1, xb, yb);
             sm.c0[r] = ca;
             sm.c0[r + T] = cb;
-            acc0 += ca;
-            acc0 += cb;
         }
         if (r < R) {
             double xa, ya;
-            double ca = heading_cost(ri, rj, xa, ya);
-            sm.c0[r] = ca;
-            acc0 += ca;
+            sm.c0[r] = heading_cost(ri, rj, xa, ya);
         }
     } else {
         for (int r = tid; r < R; r += T) {
@@ -1115,9 +1130,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             ri += di; rj += dj;
             if (rj >= nw) { rj -= nw; ri++; }
             double x, y;
-            double ca = heading_cost(i, j, x, y);
-            sm.c0[r] = ca;
-            acc0 += ca;
+            sm.c0[r] = heading_cost(i, j, x, y);
             const double *vt = sm.vtab + i * spos;
             const double *wc = sm.wcos + j, *ws = sm.wsin + j;
             const int nwm = d.nw_max;
@@ -1140,122 +1153,169 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                     min_dis = pymin(dis, min_dis);
                 }
             }
-            double cc = 1.0 / min_dis;
-            sm.c1[r] = cc;
-            acc1 += cc;
+            sm.c1[r] = 1.0 / min_dis;
         }
     }
-    // speed column (dwa.py:72): v_hi - v_last depends on the v command only and repeats nw times
-    for (int i = tid; i < nv; i += T) acc2 += (double)nw * (v_hi - sm.vlast[i]);
-    // Column sums.  numpy adds each column in its pairwise order; here every thread adds its own
-    // terms, then warps and the block combine them -- a different association, so a sum may differ
-    // from numpy's in the last bits (relative 1e-15).  That can only reorder two rollouts whose
-    // costs already agree to ~1e-15, far inside the 1e-9 band the near-tie flag reports.
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-        acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-        if (CLR) acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-    }
-    if (lane == 0) { sm.red_v[warp] = acc0; sm.red_s[warp] = acc2; sm.red2_v[warp] = acc1; }
     __syncthreads();
     PHASE_MARK(2);
-    double S0 = (lane < T / 32) ? sm.red_v[lane] : 0.0;
-    double S2 = (lane < T / 32) ? sm.red_s[lane] : 0.0;
-    double S1 = (CLR && lane < T / 32) ? sm.red2_v[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        S0 += __shfl_xor_sync(0xffffffffu, S0, o);
-        S2 += __shfl_xor_sync(0xffffffffu, S2, o);
-        if (CLR) S1 += __shfl_xor_sync(0xffffffffu, S1, o);
-    }
-    if (!CLR) S1 = (double)R * (1.0 / 100.0);        // the constant obstacle column (dwa.py:64-69 disabled)
-    // weighted sum and first argmin (dwa.py:79-82), one pass: the normalising divisions become
-    // reciprocal multiplies (a few ulp off the reference's quotients, again only visible to costs
-    // that agree to ~1e-15); equal inputs give equal costs, so exact ties keep the first index.
-    const double inv0 = (S0 != 0.0) ? 1.0 / S0 : 1.0;
-    const double inv1 = (S1 != 0.0) ? 1.0 / S1 : 1.0;
-    const double inv2 = (S2 != 0.0) ? 1.0 / S2 : 1.0;
-    const double c1n_const = (S1 != 0.0) ? (1.0 / 100.0) / S1 : (1.0 / 100.0);
-    auto cost_of = [&](int r, int i) {
-        double c1a = CLR ? sm.c1[r] * inv1 : c1n_const;
-        return d.g_goal * (sm.c0[r] * inv0) + d.g_ob * c1a + d.g_speed * ((v_hi - sm.vlast[i]) * inv2);
-    };
-    double best = CUDART_INF, second = CUDART_INF;
-    int bi = 0x7fffffff;            // bits 0-15 rollout index, bits 16-30 its v index (saves an integer division)
-#ifdef CRLK_ROWMAJOR
-    if (rowmajor) {
-        if (tb0 < CUDART_INF) {
-            auto cost_val = [&](double c0v) {
-                return d.g_goal * (c0v * inv0) + d.g_ob * c1n_const + d.g_speed * ((v_hi - sm.vlast[ti]) * inv2);
-            };
-            best = cost_val(tb0);
-            bi = (ti * nw + tjb) | (ti << 16);
-            if (tb1 < CUDART_INF) {
-                second = cost_val(tb1);
-                // two different heading costs that round to the same cost: report it as a near tie
-                if (second == best && tb1 > tb0) second = best * (1.0 + 1e-12);
-            }
-        }
-    } else
-#endif
+
+    // Column sums exactly as np.sum forms them (dwa.py:76-78; see "numpy's pairwise summation" in
+    // crlk_device.cuh).  Eight lanes own one node of tree level Dmin: a leaf of <= 128 elements, or
+    // a node one split above two leaves.  Lane k is numpy's accumulator r[k].  The speed column
+    // v_hi - v_last repeats nw times per v command (dwa.py:72): element r reads c2[r / nw].
+    const int Dmin = pw_min_depth(R), M = 1 << Dmin;
     {
+        const int k8 = tid & 7;
+        const float inv_nw = 1.0f / (float)nw;
+        auto leaf = [&](int off, int n, double &a0, double &a1, double &a2) {
+            // sum of elements [off, off + n), n <= 128, of the three columns
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;                                   // 0.0 + a[k] == a[k]: r[k] = a[k]
+            const int n8 = n - (n & 7);
+            if (n >= 8) {
+                for (int i = k8; i < n8; i += 8) {
+                    const int r = off + i;
+                    const int iv = __float2int_rd(((float)r + 0.5f) * inv_nw);   // r / nw, exact for r <= 16384
+                    r0 += sm.c0[r];
+                    r1 += CLR ? sm.c1[r] : (1.0 / 100.0);
+                    r2 += sm.c2[iv];
+                }
+            }
+            // one shuffle site for every lane of the warp (groups with n < 8 pass zeros through)
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+                r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+                r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+            }
+            for (int i = (n >= 8 ? n8 : 0); i < n; i++) {                          // the sequential tail
+                const int r = off + i;
+                const int iv = __float2int_rd(((float)r + 0.5f) * inv_nw);
+                r0 += sm.c0[r];
+                r1 += CLR ? sm.c1[r] : (1.0 / 100.0);
+                r2 += sm.c2[iv];
+            }
+            a0 = r0; a1 = r1; a2 = r2;
+        };
+        const int ngroups_pass = T >> 3;
+        for (int g0 = 0; g0 < M; g0 += ngroups_pass) {                             // warp-uniform trip count
+            const int g = g0 + (tid >> 3);
+            int off = 0, n = (g < M) ? R : 0;
+            for (int b = Dmin - 1; b >= 0 && n > 0; b--) {
+                const int n2 = pw_split(n);
+                if ((g >> b) & 1) { off += n2; n -= n2; } else n = n2;
+            }
+            double a0, a1, a2;
+            // the split decision is uniform over the eight lanes of a group; the two branches run the
+            // same shuffle sequence per leaf, so a warp whose groups disagree executes leaf() twice
+            // with one side masked to n = 0
+            const bool split = n > 128;
+            const int n2 = split ? pw_split(n) : n;
+            leaf(off, n2, a0, a1, a2);
+            double b0, b1, b2;
+            leaf(off + n2, split ? n - n2 : 0, b0, b1, b2);
+            if (split) { a0 += b0; a1 += b1; a2 += b2; }
+            if (k8 == 0 && g < M) { sm.node[g] = a0; sm.node[128 + g] = a1; sm.node[256 + g] = a2; }
+        }
+    }
+    __syncthreads();
+    double S0, S1, S2;
+    {
+        // the complete top of the tree: every warp reduces the M node values itself (no third barrier)
+        double t0, t1, t2;
+        int steps;
+        if (M >= 32) {
+            const int per = M >> 5, base = lane * per;
+            auto local = [&](const double *a) {
+                if (per == 1) return a[base];
+                if (per == 2) return a[base] + a[base + 1];
+                return (a[base] + a[base + 1]) + (a[base + 2] + a[base + 3]);
+            };
+            t0 = local(sm.node); t1 = local(sm.node + 128); t2 = local(sm.node + 256);
+            steps = 5;
+        } else {
+            const bool in = lane < M;
+            t0 = in ? sm.node[lane] : 0.0; t1 = in ? sm.node[128 + lane] : 0.0; t2 = in ? sm.node[256 + lane] : 0.0;
+            steps = Dmin;
+        }
+        for (int sft = 0; sft < steps; sft++) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 1 << sft);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 1 << sft);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 1 << sft);
+        }
+        S0 = __shfl_sync(0xffffffffu, t0, 0);
+        S1 = __shfl_sync(0xffffffffu, t1, 0);
+        S2 = __shfl_sync(0xffffffffu, t2, 0);
+    }
+    PHASE_MARK(5);
+    // weighted sum and first argmin (dwa.py:76-82) in the reference's own arithmetic: every column
+    // entry divided by its column sum (correctly rounded quotient, div_rn_y), then
+    // (g_goal * c0 + g_ob * c1) + g_speed * c2 with every product and sum rounded separately.
+    const double y0 = (S0 != 0.0) ? 1.0 / S0 : 1.0;
+    const double y1 = (S1 != 0.0) ? 1.0 / S1 : 1.0;
+    const double y2 = (S2 != 0.0) ? 1.0 / S2 : 1.0;
+    const bool z0 = S0 != 0.0, z1 = S1 != 0.0, z2 = S2 != 0.0;
+    const double c1n_const = z1 ? (1.0 / 100.0) / S1 : (1.0 / 100.0);
+    auto cost_of = [&](int r, int i) {
+        const double c0 = sm.c0[r], c2 = sm.c2[i];
+        const double c0n = z0 ? div_rn_y(c0, S0, y0) : c0;
+        const double c1n = CLR ? (z1 ? div_rn_y(sm.c1[r], S1, y1) : sm.c1[r]) : c1n_const;
+        const double c2n = z2 ? div_rn_y(c2, S2, y2) : c2;
+        return (d.g_goal * c0n + d.g_ob * c1n) + d.g_speed * c2n;
+    };
+    // (minimum, its first index, runner-up, runner-up's index): the runner-up only feeds the near-tie report
+    double best = CUDART_INF, second = CUDART_INF;
+    int bi = 0x7fffffff, si = 0x7fffffff;   // bits 0-15 rollout index, bits 16-30 its v index (saves an integer division)
     ri = tid / nw; rj = tid - ri * nw;
     for (int r = tid; r < R; r += T) {
         const int i = ri;
         ri += di; rj += dj;
         if (rj >= nw) { rj -= nw; ri++; }
-        double c = cost_of(r, i);
-        if (c < best) { second = best; best = c; bi = r | (i << 16); }       // r ascends: the first minimum stays
-        else if (c < second) second = c;
+        const double c = cost_of(r, i);
+        if (c < best) { second = best; si = bi; best = c; bi = r | (i << 16); }       // r ascends: the first minimum stays
+        else if (c < second) { second = c; si = r | (i << 16); }
     }
-    }
-    // (minimum, its first index, runner-up) across the warp, then across the block by warp 0
+    auto merge = [&](double ob, int oi, double os2, int osi) {
+        // loser of the two minima, then the smallest of {loser, both runner-ups}
+        const bool owins = ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff));
+        double lv = owins ? best : ob;
+        int li = owins ? bi : oi;
+        if (owins) { best = ob; bi = oi; }
+        if (os2 < second) { second = os2; si = osi; }
+        if (lv < second) { second = lv; si = li; }
+    };
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        double os2 = __shfl_xor_sync(0xffffffffu, second, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        second = fmin(fmin(second, os2), fmax(best, ob));
-        if (ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff))) { best = ob; bi = oi; }
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const double os2 = __shfl_xor_sync(0xffffffffu, second, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int osi = __shfl_xor_sync(0xffffffffu, si, o);
+        merge(ob, oi, os2, osi);
     }
-    if (lane == 0) { sm.red3_v[warp] = best; sm.red3_s[warp] = second; sm.red_i[warp] = bi; }
+    if (lane == 0) { sm.red3_v[warp] = best; sm.red3_s[warp] = second; sm.red_i[warp] = bi; sm.red_i[32 + warp] = si; }
     __syncthreads();
-    PHASE_MARK(5);
-    if (T / 32 <= 8) {
-        // few warps: thread 0 walks the per-warp results itself (measured faster than a shuffle tree here)
-        if (tid == 0) {
-            best = sm.red3_v[0]; second = sm.red3_s[0]; bi = sm.red_i[0];
-#pragma unroll
-            for (int w = 1; w < T / 32; w++) {
-                double ob = sm.red3_v[w], os2 = sm.red3_s[w];
-                int oi = sm.red_i[w];
-                second = fmin(fmin(second, os2), fmax(best, ob));
-                if (ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff))) { best = ob; bi = oi; }
-            }
-        }
-    } else if (warp == 0) {
-        best = (lane < T / 32) ? sm.red3_v[lane] : CUDART_INF;
-        second = (lane < T / 32) ? sm.red3_s[lane] : CUDART_INF;
-        bi = (lane < T / 32) ? sm.red_i[lane] : 0x7fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            double os2 = __shfl_xor_sync(0xffffffffu, second, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            second = fmin(fmin(second, os2), fmax(best, ob));
-            if (ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff))) { best = ob; bi = oi; }
-        }
-    }
     PHASE_MARK(3);
     if (tid == 0) {
+        best = sm.red3_v[0]; second = sm.red3_s[0]; bi = sm.red_i[0]; si = sm.red_i[32];
+        for (int w = 1; w < T / 32; w++) merge(sm.red3_v[w], sm.red_i[w], sm.red3_s[w], sm.red_i[32 + w]);
         const int ix = bi & 0xffff;
         const int i = bi >> 16, j = ix - i * nw;
         sm.scal[4] = arange_at(v_lo, v1, vd, i);
         sm.scal[5] = arange_at(w_lo, w1, wd, j);
+        sm.scal[6] = best;
         sm.iscal[1] = ix;
-        double gap = second - best;
-        sm.iscal[2] = (gap > 0.0 && gap <= 1e-9 * fabs(best)) ? 1 : 0;
+        // Near-tie report.  The costs above are the reference's arithmetic applied to THIS build's
+        // heading costs; numpy's SIMD arctan2, glibc's and the table-driven one here differ by an ulp
+        // or two, which moves a cost by a few ulp.  A runner-up within CRLK_TIE_ULPS ulp of the
+        // winner could therefore win in the reference -- unless it is the same rollout twice (grid
+        // values beyond the window are clamped to the same command: identical inputs, identical
+        // cost in any arithmetic, and np.argmin keeps the first, as here).
+        int tie = 0;
+        if (si != 0x7fffffff && second - best <= (double)CRLK_TIE_ULPS * 2.220446049250313e-16 * fabs(best)) {
+            const int sx = si & 0xffff, s_i = si >> 16;
+            const bool same = sm.c0[sx] == sm.c0[ix] && sm.c2[s_i] == sm.c2[i] && (!CLR || sm.c1[sx] == sm.c1[ix]);
+            tie = same ? 0 : 1;
+        }
+        sm.iscal[2] = tie;
         PHASE_MARK(4);
         // trajectory row 1 of the winner (= motion_velocity(state, opt_v, d.dt), same operations)
         double row1[5];
@@ -1280,8 +1340,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     __syncthreads();
     PHASE_MARK(7);
     DwaResult res;
-    res.v = sm.scal[4]; res.w = sm.scal[5];
-    res.S0 = S0; res.S1 = S1; res.S2 = S2; res.v_hi = v_hi;
+    res.v = sm.scal[4]; res.w = sm.scal[5]; res.cost = sm.scal[6];
     res.idx = sm.iscal[1]; res.near_tie = sm.iscal[2]; res.R = R;
     return res;
 }
@@ -1310,20 +1369,13 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
             if (opt_idx) opt_idx[b] = r.idx;
-            if (opt_cost) {
-                // the winner's cost with the reference's divisions (dwa.py:76-81)
-                const int nw = (r.R > 0 && sm.ihdr[1] > 0) ? sm.ihdr[1] : 1;
-                const int i = r.idx / nw;
-                double c0n = (r.S0 != 0.0) ? sm.c0[r.idx] / r.S0 : sm.c0[r.idx];
-                double c1 = CLR ? sm.c1[r.idx] : 1.0 / 100.0;
-                double c1n = (r.S1 != 0.0) ? c1 / r.S1 : c1;
-                double c2 = r.v_hi - sm.vlast[i];
-                double c2n = (r.S2 != 0.0) ? c2 / r.S2 : c2;
-                opt_cost[b] = d.g_goal * c0n + d.g_ob * c1n + d.g_speed * c2n;
-            }
+            if (opt_cost) opt_cost[b] = r.cost;
             if (n_rollouts) n_rollouts[b] = r.R;
             if (near_tie) near_tie[b] = (uint8_t)r.near_tie;
-            if (opt_traj) {   // dwa.py:35-43 for the winner
+            if (opt_traj && r.R == 0) {
+                double *tr = opt_traj + (size_t)b * (d.n_outer + 1) * 5;
+                for (int k = 0; k < (d.n_outer + 1) * 5; k++) tr[k] = CUDART_NAN;
+            } else if (opt_traj) {   // dwa.py:35-43 for the winner
                 double s[5];
                 for (int k = 0; k < 5; k++) s[k] = s_state[k];
                 double *tr = opt_traj + (size_t)b * (d.n_outer + 1) * 5;
@@ -1468,6 +1520,11 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
                     for (int c = 0; c < 5; c++) path[(size_t)(k - 1) * 5 + c] = s[c];
                 if (ctrl_idx) ctrl_idx[k - 1] = ix;
             });
+        if (r.R == 0) {
+            // empty rollout grid (start state outside the velocity limits): nothing was executed
+            res.status = CRLK_EXT_INVALID; res.flags |= 8;
+            break;
+        }
         res.flags |= r.near_tie ? 2 : 0;
         res.rolls += (unsigned long long)r.R;
         res.steps = k;
@@ -1924,7 +1981,7 @@ __device__ void nn_block_reduce(double &d, int &i, double &s, double *sv, double
 //   f64 path (x32 == NULL): exact distances straight from the float64 arrays.
 __global__ void __launch_bounds__(NN_THREADS)
 k_nearest(const double *__restrict__ x64, const double *__restrict__ y64,
-          const float *__restrict__ x32, const float *__restrict__ y32, long long stride,
+          const float *__restrict__ x32, const float *__restrict__ y32, long long stride, int xy_step,
           const int *__restrict__ n_nodes, const double *__restrict__ targets, int target_stride,
           float band_abs, int splits, int vec_ok, NNPartial *partial)
 {
@@ -2009,7 +2066,7 @@ k_nearest(const double *__restrict__ x64, const double *__restrict__ y64,
             for (int c = threadIdx.x; c < s_cnt; c += NN_THREADS) {
                 if (s_cv[c] <= lim) {
                     int j = s_ci[c];
-                    double dx = x64[base + j] - tx, dy = y64[base + j] - ty;
+                    double dx = x64[(base + j) * xy_step] - tx, dy = y64[(base + j) * xy_step] - ty;
                     double dd = sqrt(fma(dy, dy, dx * dx));            // np.linalg.norm (rrt.py:159)
                     nn_merge(bd, bi, bs, dd, j, CUDART_INF);
                 }
@@ -2019,7 +2076,7 @@ k_nearest(const double *__restrict__ x64, const double *__restrict__ y64,
     if (exact_scan) {
         bd = CUDART_INF; bs = CUDART_INF; bi = 0x7fffffff;
         for (int j = lo + threadIdx.x; j < hi; j += NN_THREADS) {
-            double dx = x64[base + j] - tx, dy = y64[base + j] - ty;
+            double dx = x64[(base + j) * xy_step] - tx, dy = y64[(base + j) * xy_step] - ty;
             double dd = sqrt(fma(dy, dy, dx * dx));
             nn_merge(bd, bi, bs, dd, j, CUDART_INF);
         }
@@ -2066,7 +2123,7 @@ extern "C" int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes)
     return (int64_t)sizeof(NNPartial) * Q * nn_splits(Q, max_nodes);
 }
 
-extern "C" int crlk_nearest(const double *x64, const double *y64, const float *x32, const float *y32,
+extern "C" int crlk_nearest(const double *x64, const double *y64, int32_t xy_step, const float *x32, const float *y32,
                             int64_t stride, const int32_t *n_nodes, int32_t max_nodes,
                             double coord_bound, const double *targets, int32_t target_stride,
                             int32_t Q, int32_t *idx, double *dist, uint8_t *near_tie, void *scratch,
@@ -2076,7 +2133,7 @@ extern "C" int crlk_nearest(const double *x64, const double *y64, const float *x
     if (Q == 0) return CRLK_OK;
     CRLK_REQUIRE(x64 && y64 && n_nodes && targets && idx && dist && scratch, "NULL array");
     CRLK_REQUIRE((x32 == nullptr) == (y32 == nullptr), "x32/y32 must both be given or both NULL");
-    CRLK_REQUIRE(target_stride >= 2 && max_nodes >= 1 && stride >= max_nodes, "shape");
+    CRLK_REQUIRE(target_stride >= 2 && max_nodes >= 1 && stride >= max_nodes && xy_step >= 1, "shape");
     CRLK_REQUIRE(x32 == nullptr || coord_bound > 0, "coord_bound must be > 0 with the float32 scan");
     // guard band of the float32 screen: |d_f - d| <= delta = 8 * bound * 2^-24
     double delta = 8.0 * coord_bound * 5.9604644775390625e-08;
@@ -2085,7 +2142,7 @@ extern "C" int crlk_nearest(const double *x64, const double *y64, const float *x
     int vec_ok = (x32 != nullptr) && (stride % 4 == 0) && (((uintptr_t)x32 & 15) == 0) &&
                  (((uintptr_t)y32 & 15) == 0);
     CRLK_REQUIRE((long long)Q * splits < 2147483647LL, "grid too large");
-    k_nearest<<<Q * splits, NN_THREADS, 0, (cudaStream_t)stream>>>(x64, y64, x32, y32, (long long)stride,
+    k_nearest<<<Q * splits, NN_THREADS, 0, (cudaStream_t)stream>>>(x64, y64, x32, y32, (long long)stride, xy_step,
                                                             n_nodes, targets, target_stride,
                                                             band_abs, splits, vec_ok,
                                                             (NNPartial *)scratch);

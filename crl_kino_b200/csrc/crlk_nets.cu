@@ -1,5 +1,8 @@
 // libcrlk.so -- learned steering: actor MLP, estimator/classifier CNN and the
-// RL extend loop (float32; FMA contraction allowed, tolerance-based parity).
+// RL extend loop.  Compiled with --fmad=false like the other float64 units: k_rl_step shares the
+// float64 dynamics / footprint helpers of crlk_device.cuh with crlk_motion_velocity, crlk_gym_step
+// and crlk_valid_state, and must round exactly like them.  The float32 network code fuses
+// multiply-adds explicitly (fmaf); its parity is tolerance-based.
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -138,7 +141,7 @@ static bool policy_uses_tc(const CrlkPolicy *p)
 __global__ void __launch_bounds__(256)
 k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W, int K,
               const float *__restrict__ bias, const float *__restrict__ noise, long long noise_stride,
-              const int *__restrict__ noise_cursor, int noise_off, float eps, HeadP hp, int B,
+              const int *__restrict__ noise_cursor, int noise_off, int noise_rows, float eps, HeadP hp, int B,
               float *__restrict__ act, const int *__restrict__ n_rows_dev, const int *__restrict__ list)
 {
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -161,8 +164,10 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
         float z = (lane == 0 ? s0 : s1) + __ldg(&bias[lane]);
         z = tanhf(z);
         if (noise) {
+            // draws past the end of a query's stream count as zero (the host sizes the stream and
+            // checks the cursors, planner/batched.py; this only keeps the read inside the buffer)
             long long off = (long long)noise_off + (noise_cursor ? noise_cursor[q] : 0);
-            z = z + noise[(size_t)q * noise_stride + off * 2 + lane] * eps;
+            if (off < noise_rows) z = z + noise[(size_t)q * noise_stride + off * 2 + lane] * eps;
         }
         z = z * hp.scale[lane] + hp.bias[lane];
         z = fminf(fmaxf(z, hp.low[lane]), hp.high[lane]);
@@ -175,7 +180,8 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
 // in crlk_tc_layers_forward).  n_rows_dev / list (nullable): compacted batch of the
 // RL steer loop -- live row count on the device and the query of each row.
 static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs, const float *noise,
-                               long long noise_stride, const int *noise_cursor, int noise_off, float eps, int B,
+                               long long noise_stride, const int *noise_cursor, int noise_off, int noise_rows,
+                               float eps, int B,
                                float *act, void *workspace, cudaStream_t st, const int *n_rows_dev = nullptr,
                                const int *list = nullptr, int a_lo_kb = 0)
 {
@@ -210,8 +216,8 @@ static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs
         hp.low[k] = p->low[k]; hp.high[k] = p->high[k]; hp.scale[k] = p->scale[k]; hp.bias[k] = p->bias[k];
     }
     k_policy_head<<<(B + 7) / 8, 256, 0, st>>>(in, ld_in, p->d_w[L - 1], p->kpad[L - 1], p->d_b[L - 1],
-                                              noise, noise_stride, noise_cursor, noise_off, eps, hp, B, act,
-                                              n_rows_dev, list);
+                                              noise, noise_stride, noise_cursor, noise_off, noise_rows, eps, hp, B,
+                                              act, n_rows_dev, list);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -227,7 +233,7 @@ extern "C" int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_
     CRLK_REQUIRE(ld_obs >= p->kpad[0] && ld_obs % 4 == 0,
                  "ld_obs must be >= the input width rounded up to 16, zero padded");
     CRLK_REQUIRE(((uintptr_t)obs & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "16-byte alignment");
-    return policy_forward_impl(p, obs, ld_obs, noise, 2, nullptr, 0, eps, B, act, workspace, (cudaStream_t)stream);
+    return policy_forward_impl(p, obs, ld_obs, noise, 2, nullptr, 0, 1, eps, B, act, workspace, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------- estimator CNNs (R11)
@@ -889,7 +895,7 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
             rc = policy_forward_impl(p, tc ? nullptr : w.obs, 736,
                                      noise ? noise + (size_t)q0 * noise_rows * 2 : nullptr,
                                      (long long)noise_rows * 2, noise_cursor ? noise_cursor + q0 : nullptr,
-                                     k - 1, eps, n, w.act, w.mlp, h[i].s, cnt, list, 1);
+                                     k - 1, noise_rows, eps, n, w.act, w.mlp, h[i].s, cnt, list, 1);
             if (rc) return rc;
             k_rl_step<<<(n + 7) / 8, 256, 0, h[i].s>>>(env->p, x, env->os, tg, w.act, k, n, list, cnt,
                                                       w.list[k & 1], w.count + k, w.state, w.nn,

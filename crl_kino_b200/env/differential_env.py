@@ -43,7 +43,7 @@ class DifferentialDriveEnv(RobotEnv):
         self.env_bounds[0, 1] = env_bounds[1]
         self.env_bounds[1, 0] = env_bounds[2]
         self.env_bounds[1, 1] = env_bounds[3]
-        self.obs_list = []
+        self._obs_list = []
         self.base_dt = base_dt
         self._handle = None
         self._rects = np.zeros((0, 4), dtype=np.float32)
@@ -90,23 +90,36 @@ class DifferentialDriveEnv(RobotEnv):
         return b
 
     # ---- obstacles (differential_env.py:116-123) -------------------------
+    # The flat float32 [M, 4] table is the source of truth (it is what the device holds); the
+    # reference's list of RectObs objects is built from it on demand.
+    @property
+    def obs_list(self):
+        if self._obs_list is None:
+            from ..utils.rigid import RectObs
+            self._obs_list = [RectObs(r.reshape(2, 2)) for r in self._rects]
+        return self._obs_list
+
+    @obs_list.setter
+    def obs_list(self, obs_list):
+        self.set_obs(obs_list)
+
     def add_obs(self, obs):
         assert isinstance(obs, Obstacle), "Unsupported obstacle type"
-        self.obs_list.append(obs)
-        self._rects = rects_of(self.obs_list)
+        if self._obs_list is not None:
+            self._obs_list.append(obs)
+        self._rects = np.ascontiguousarray(np.vstack([self._rects, rects_of([obs])]), dtype=np.float32)
         self._dirty = True
 
     def set_obs(self, obs_list):
         if isinstance(obs_list, np.ndarray):       # flat float32 [M, 4] fast path
-            from ..utils.rigid import RectObs
             self._rects = rects_of(obs_list)
-            self.obs_list = [RectObs(r.reshape(2, 2)) for r in self._rects] if len(self._rects) <= 4096 else []
+            self._obs_list = None                  # built lazily (a dense map has 10^4 rectangles)
             self._dirty = True
             return
         for obs in obs_list:
             assert isinstance(obs, Obstacle), "Unsupported obstacle type"
-        self.obs_list = list(obs_list)
-        self._rects = rects_of(self.obs_list)
+        self._obs_list = list(obs_list)
+        self._rects = rects_of(self._obs_list)
         self._dirty = True
 
     # ---- dynamics ----------------------------------------------------------
@@ -124,7 +137,10 @@ class DifferentialDriveEnv(RobotEnv):
 
     def motion_base(self, state, input_u, dt):
         """differential_env.py:85-105: one sub-step; mutates and returns `state`."""
-        assert dt == self.base_dt, "motion_base runs at base_dt"
+        if dt != self.base_dt:
+            # the device integrates in base_dt sub-steps (the only way the reference itself calls
+            # motion_base, differential_env.py:71,81); other step sizes are not offered
+            raise NotImplementedError("motion_base is only available at dt == base_dt")
         out = ops.motion_velocity(self.handle, np.asarray(state, dtype=np.float64)[None],
                                   np.asarray(input_u, dtype=np.float64)[None, :2], dt, accel=True)
         state[:] = out[0].cpu().numpy()

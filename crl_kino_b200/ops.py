@@ -169,20 +169,28 @@ def dwa_control(env, dp, states, goals, want_traj=False):
     return dict(opt_v=opt_v, opt_idx=idx, opt_cost=cost, opt_traj=traj, n_rollouts=nroll, near_tie=tie)
 
 
-def nearest(x64, y64, n_nodes, targets, x32=None, y32=None, coord_bound=0.0, max_nodes=None):
-    """x64/y64 (and optional float32 copies): [Q, stride] SoA trees on the device."""
-    Q, stride = x64.shape
+def nearest(x64, y64, n_nodes, targets, x32=None, y32=None, coord_bound=0.0, max_nodes=None, states=None):
+    """x64/y64 (and optional float32 copies): [Q, stride] SoA trees on the device.  With `states`
+    ([Q, stride, 5] float64) and x64 = y64 = None the exact coordinates are read from columns 0 / 1
+    of the state table (no separate float64 coordinate arrays)."""
+    if states is not None:
+        Q, stride, _ = states.shape
+        d = states.device
+        px, py, step = C.c_void_p(states.data_ptr()), C.c_void_p(states.data_ptr() + 8), 5
+    else:
+        Q, stride = x64.shape
+        d = x64.device
+        px, py, step = _ptr(x64), _ptr(y64), 1
     targets = as_dev(targets).reshape(Q, -1)
-    n_nodes = n_nodes.to(device=x64.device, dtype=torch.int32).contiguous()
+    n_nodes = n_nodes.to(device=d, dtype=torch.int32).contiguous()
     if max_nodes is None:
         max_nodes = stride
-    d = x64.device
     idx = torch.empty(Q, dtype=torch.int32, device=d)
     dist = torch.empty(Q, dtype=torch.float64, device=d)
     tie = torch.empty(Q, dtype=torch.uint8, device=d)
     nbytes = lib().crlk_nearest_scratch_bytes(Q, int(max_nodes))
     scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=d)
-    check(lib().crlk_nearest(_ptr(x64), _ptr(y64), _ptr(x32), _ptr(y32), stride, _ptr(n_nodes),
+    check(lib().crlk_nearest(px, py, step, _ptr(x32), _ptr(y32), stride, _ptr(n_nodes),
                              int(max_nodes), float(coord_bound), _ptr(targets), targets.shape[1], Q,
                              _ptr(idx), _ptr(dist), _ptr(tie), _ptr(scratch), _stream()))
     return idx, dist, tie

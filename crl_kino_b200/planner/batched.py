@@ -13,19 +13,22 @@ from .. import ops
 
 
 class Forest:
-    """Q trees in SoA layout: x/y float64 [Q, cap] (+ float32 copies that the
-    nearest-node scan streams), full states float64 [Q, cap, 5], parent int32
-    [Q, cap], n_nodes int32 [Q]."""
+    """Q trees in HBM: full states float64 [Q, cap, 5] (the exact coordinates are its columns 0 / 1),
+    float32 copies x32 / y32 [Q, cap] that the nearest-node scan streams (8 B per node), parent
+    int32 [Q, cap], n_nodes int32 [Q].  with_xy64 adds separate float64 x / y arrays [Q, cap] (the
+    SoA view the device-resident planners index, crlk_rrt_append / crlk_plan_dwa); without them a
+    node costs 48 + 4 bytes instead of 64 + 4, which is what lets cfg5's 100,000-node trees of
+    32,768 queries fit one 180 GB GPU."""
 
-    def __init__(self, Q, capacity, device=None, with_f32=True):
+    def __init__(self, Q, capacity, device=None, with_f32=True, with_xy64=True, with_parent=True):
         d = device or ops.dev()
         self.Q, self.cap = Q, capacity
-        self.x = torch.zeros(Q, capacity, dtype=torch.float64, device=d)
-        self.y = torch.zeros(Q, capacity, dtype=torch.float64, device=d)
+        self.x = torch.zeros(Q, capacity, dtype=torch.float64, device=d) if with_xy64 else None
+        self.y = torch.zeros(Q, capacity, dtype=torch.float64, device=d) if with_xy64 else None
         self.x32 = torch.zeros(Q, capacity, dtype=torch.float32, device=d) if with_f32 else None
         self.y32 = torch.zeros(Q, capacity, dtype=torch.float32, device=d) if with_f32 else None
         self.states = torch.zeros(Q, capacity, 5, dtype=torch.float64, device=d)
-        self.parent = torch.full((Q, capacity), -1, dtype=torch.int32, device=d)
+        self.parent = torch.full((Q, capacity), -1, dtype=torch.int32, device=d) if with_parent else None
         self.n_nodes = torch.zeros(Q, dtype=torch.int32, device=d)
 
     def fill(self, states, n_nodes=None):
@@ -33,15 +36,28 @@ class Forest:
         s = ops.as_dev(states)
         N = s.shape[1]
         self.states[:, :N] = s
-        self.x[:, :N] = s[:, :, 0]
-        self.y[:, :N] = s[:, :, 1]
+        if self.x is not None:
+            self.x[:, :N] = s[:, :, 0]
+            self.y[:, :N] = s[:, :, 1]
         if self.x32 is not None:
             self.x32[:, :N] = s[:, :, 0].float()
             self.y32[:, :N] = s[:, :, 1].float()
         self.n_nodes[:] = N if n_nodes is None else ops.as_dev(n_nodes, torch.int32)
 
+    def nearest(self, targets, coord_bound, max_nodes=None):
+        """RRT.choose_parent (rrt.py:156-161) for one target per tree -> (idx, dist, near_tie)."""
+        if self.x is not None:
+            return ops.nearest(self.x, self.y, self.n_nodes, targets, x32=self.x32, y32=self.y32,
+                               coord_bound=coord_bound, max_nodes=max_nodes)
+        return ops.nearest(None, None, self.n_nodes, targets, x32=self.x32, y32=self.y32,
+                           coord_bound=coord_bound, max_nodes=max_nodes, states=self.states)
+
     def bytes_scanned_per_query(self):
         return 8 if self.x32 is not None else 16
+
+    def bytes_per_node(self):
+        return 40 + (16 if self.x is not None else 0) + (8 if self.x32 is not None else 0) + \
+            (4 if self.parent is not None else 0)
 
 
 class BatchedExtender:
@@ -56,7 +72,7 @@ class BatchedExtender:
         self.xp = ops.extend_params(t_max_extend, t_tree)
         self.coord_bound = env.coord_bound()
         Q = forest.Q
-        d = forest.x.device
+        d = forest.states.device
         self.from_states = torch.empty(Q, 5, dtype=torch.float64, device=d)
         self.stats = torch.zeros(4, dtype=torch.int64, device=d)
         self.out = None
@@ -84,8 +100,7 @@ class BatchedExtender:
             if ev is not None:
                 ev[i].record()
         mark(0)
-        idx, dist, tie = ops.nearest(f.x, f.y, f.n_nodes, samples, x32=f.x32, y32=f.y32,
-                                     coord_bound=self.coord_bound, max_nodes=self.max_nodes)
+        idx, dist, tie = f.nearest(samples, self.coord_bound, max_nodes=self.max_nodes)
         mark(1)
         ops.gather_rows(f.states, idx, out=self.from_states)
         mark(2)
@@ -113,7 +128,7 @@ class BatchedExtender:
 
     # ---- pipelined host-buffer entry points ------------------------------------------
     def _pipe_init(self):
-        d = self.forest.x.device
+        d = self.forest.states.device
         self._pipe = []
         for _ in range(2):
             self._pipe.append(dict(

@@ -39,6 +39,7 @@ class RRT(ABC):
         self.verbose = True
         self.n_extend_calls = 0
         self.n_control_steps = 0
+        self.flags_seen = 0          # OR of the extensions' report bits (near-boundary, near-tie)
 
     def planning(self):
         """rrt.py:51-89."""
@@ -87,6 +88,16 @@ class RRT(ABC):
             "The start or goal states are not valid"
         self.start = self.Node(start)
         self.goal = self.Node(goal)
+        self._check_window(self.start.state)
+
+    def _check_window(self, state):
+        """A state whose v or omega lies outside the vehicle limits by more than acc * dt has an
+        empty DWA grid; the reference fails on it inside DWA.control (dwa.py:76).  Fail early."""
+        e, dt = self.robot_env, self.dwa.dt
+        v, w = float(state[3]), float(state[4])
+        if (min(v + e.max_acc_v * dt, e.max_v) + self.dwa.v_res <= max(v - e.max_acc_v * dt, e.min_v) or
+                min(w + e.max_acc_w * dt, e.max_w) + self.dwa.w_res <= max(w - e.max_acc_w * dt, -e.max_w)):
+            raise ValueError("state velocity outside the limits: the dynamic window is empty")
 
     def _segments_to_nodes(self, from_node, path, n_steps, node_steps, first_path_has_start):
         """Rebuild the reference's Node objects from an extension's flat output."""
@@ -120,6 +131,9 @@ class RRT(ABC):
         self.n_control_steps += n_steps
         self.last_extend = dict(n_steps=n_steps, status=int(out["status"][0].item()),
                                 flags=int(out["flags"][0].item()))
+        self.flags_seen |= self.last_extend["flags"]
+        if self.last_extend["status"] == 3:          # CRLK_EXT_INVALID
+            raise ValueError("state velocity outside the limits: the dynamic window is empty")
         new_node_list = self._segments_to_nodes(from_node, path, n_steps, node_steps, False)
         self.node_list += new_node_list
         return new_node_list

@@ -137,3 +137,67 @@ def device_sample_stream(state_bounds, goals, n, seed, goal_sample_rate=5):
     pick_goal = np.floor(u[:, :, 5] * 101.0).astype(np.int64) <= goal_sample_rate
     out[pick_goal] = np.repeat(goals[:, None, :], n, 1)[pick_goal]
     return out
+
+
+# ---------------------------------------------------------------- cfg4 batches (bench / parity)
+
+def clearance_raster(rects, pad, res=0.125, lo=-22.0, hi=22.0):
+    """Boolean raster [n, n]: True where some obstacle rectangle comes within `pad` of the raster
+    cell (conservative: every rectangle is grown by pad and rounded outwards to whole cells)."""
+    gx = np.arange(lo, hi + res, res)
+    occ = np.zeros((len(gx), len(gx)), dtype=bool)
+    for l, b, r, t in np.asarray(rects, dtype=np.float64):
+        i0, i1 = np.searchsorted(gx, [l - pad, r + pad])
+        j0, j1 = np.searchsorted(gx, [b - pad, t + pad])
+        occ[max(i0 - 1, 0):i1 + 1, max(j0 - 1, 0):j1 + 1] = True
+    return gx, occ
+
+
+def raster_free(gx, occ, xy):
+    ii = np.clip(np.searchsorted(gx, xy[:, 0]) - 1, 0, len(gx) - 1)
+    jj = np.clip(np.searchsorted(gx, xy[:, 1]) - 1, 0, len(gx) - 1)
+    return ~occ[ii, jj]
+
+
+def cfg4_workload(Q=1024, tree_nodes=1024, n_batches=25, seed=100, cells=10000, cand=96):
+    """BASELINE config 4, generated on the host with numpy / scipy only so that every arm of
+    bench.py (GPU, CPU port) and the tests work on the SAME data: the dense map, Q trees of
+    `tree_nodes` free nodes at rest, and n_batches x Q accepted samples -- valid states (rrt.py:66)
+    whose nearest tree node lies in [1, 20) (rrt.py:69).  Free / valid are decided by conservative
+    rasters: no obstacle within 1.5 m of a tree node (clearance > 0.5, the reference's reset rule,
+    differential_gym.py:229) and none within 0.95 m of a sample (> footprint circumradius + 0.05:
+    valid at any heading).  Only ~5 % of the valid candidates have no tree node within 1 m, so each
+    (query, batch) slot draws `cand` candidates and keeps the first accepted one."""
+    from scipy.spatial import cKDTree
+    rects = dense_map(n_cells=cells)
+    rng = np.random.default_rng(seed)
+    gx, occ_node = clearance_raster(rects, 1.5)
+    _, occ_sample = clearance_raster(rects, 0.95)
+    nodes = []
+    have = 0
+    while have < Q * tree_nodes:
+        c = random_states(rng, 1 << 18)
+        c = c[raster_free(gx, occ_node, c)]
+        nodes.append(c)
+        have += len(c)
+    trees = np.concatenate(nodes)[:Q * tree_nodes].reshape(Q, tree_nodes, 5)
+    trees[:, :, 3:] = 0.0
+    batches = np.zeros((n_batches, Q, 5))
+    for q in range(Q):
+        kd = cKDTree(trees[q, :, :2])
+        # one generator per (query, batch): a batch does not depend on how many batches are drawn
+        gens = [np.random.default_rng([seed, q, b]) for b in range(n_batches)]
+        need = np.ones(n_batches, dtype=bool)
+        while need.any():
+            todo = np.flatnonzero(need)
+            c = np.stack([random_states(gens[b], cand, moving=True) for b in todo]).reshape(-1, 5)
+            ok = raster_free(gx, occ_sample, c)
+            d = np.full(len(c), np.inf)
+            d[ok] = kd.query(c[ok, :2])[0]
+            ok &= (d >= 1.0 + 1e-9) & (d < 20.0 - 1e-9)
+            ok = ok.reshape(len(todo), cand)
+            first = ok.argmax(axis=1)
+            hit = ok.any(axis=1)
+            batches[todo[hit], q] = c.reshape(len(todo), cand, 5)[hit, first[hit]]
+            need[todo[hit]] = False
+    return dict(rects=rects, trees=trees, batches=batches)

@@ -42,6 +42,7 @@ extern "C" {
 #define CRLK_EXT_TIMEOUT 0    /* n_max_extend steps executed */
 #define CRLK_EXT_COLLISION 1  /* valid_state_check failed; open segment dropped */
 #define CRLK_EXT_REACHED 2    /* ||xy - target|| <= reach_radius */
+#define CRLK_EXT_INVALID 3    /* empty DWA grid: start state outside the velocity limits (the reference raises) */
 
 typedef struct CrlkEnv CrlkEnv;          /* DifferentialDriveEnv + obstacle set */
 typedef struct CrlkPolicy CrlkPolicy;    /* DDPG actor MLP */
@@ -131,12 +132,17 @@ int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals
  *   opt_cost  dev f64[B]   (nullable)
  *   opt_traj  dev f64[B x traj_rows x 5] (nullable); traj_rows from crlk_dwa_traj_rows
  *   n_rollouts dev i32[B]  (nullable) realised grid size nv * nw
- *   near_tie  dev u8[B]    (nullable) second-best cost within 1e-9 relative.
- * The three cost columns are normalised by their sums (dwa.py:76-78); the kernel adds each column in
- * a different association than numpy's pairwise sum and multiplies by the reciprocal, so a
- * normalised cost can differ from the reference's by ~1e-15 relative: opt_idx can differ from
- * np.argmin only between rollouts whose costs agree to that level -- all of which near_tie reports.
- * opt_cost is evaluated for the winner with the reference's divisions. */
+ *   near_tie  dev u8[B]    (nullable) a DIFFERENT rollout's cost lies within 32 ulp of the winner's.
+ * Costs are formed in the reference's own arithmetic: each column summed in numpy's pairwise order
+ * (np.sum, dwa.py:76-78), every entry divided by its column sum (correctly rounded), then
+ * (gain0 * c0 + gain1 * c1) + gain2 * c2 with each operation rounded once (dwa.py:79-81), first
+ * minimum (np.argmin, :82).  Given the same heading costs the result is therefore the reference's,
+ * bit for bit.  The heading costs themselves come from arctan2 / sin / cos, whose last bit differs
+ * between numpy's SIMD loops, glibc and this library (<= 2 ulp each); near_tie marks exactly the
+ * decisions that such a last-bit difference could flip.  Identical rollouts (grid values beyond the
+ * window clamp to the same command) are not near ties: np.argmin and this kernel both keep the first.
+ * An empty grid (v or omega outside the limits by more than acc * dt; the reference raises on the
+ * empty cost table) gives opt_idx = -1, n_rollouts = 0 and NaN opt_v / opt_cost / opt_traj. */
 int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, const double *states,
                      const double *goals, int32_t goal_stride, int32_t B, double *opt_v,
                      int32_t *opt_idx, double *opt_cost, double *opt_traj, int32_t *n_rollouts,
@@ -150,7 +156,10 @@ int crlk_dwa_max_rollouts(const CrlkEnv *env, const CrlkDwaParams *dwa);
 
 /* Q independent trees in SoA form.  Tree q occupies elements [q*stride,
  * q*stride + n_nodes[q]) of each array.
- *   x64, y64   dev f64   exact coordinates (rescoring)
+ *   x64, y64   dev f64   exact coordinates (rescoring); node j of tree q is element
+ *                        (q*stride + j) * xy_step: xy_step = 1 for two SoA arrays, 5 when x64 / y64
+ *                        point at columns 0 / 1 of a [Q x stride x 5] state table (no second copy
+ *                        of the coordinates: 48 instead of 64 bytes per node with the f32 copies)
  *   x32, y32   dev f32   the same coordinates rounded to float32 (the scanned
  *                        copy: 8 bytes per node); nullable => scan f64 directly
  *   coord_bound upper bound of |coordinate| over the trees and targets (e.g. the
@@ -158,7 +167,7 @@ int crlk_dwa_max_rollouts(const CrlkEnv *env, const CrlkDwaParams *dwa);
  *   targets    dev f64[Q x target_stride]
  *   idx        dev i32[Q]; dist dev f64[Q]; near_tie dev u8[Q] (nullable)
  *   scratch    dev bytes, crlk_nearest_scratch_bytes(Q, max_nodes) of them. */
-int crlk_nearest(const double *x64, const double *y64, const float *x32, const float *y32,
+int crlk_nearest(const double *x64, const double *y64, int32_t xy_step, const float *x32, const float *y32,
                  int64_t stride, const int32_t *n_nodes, int32_t max_nodes, double coord_bound,
                  const double *targets, int32_t target_stride, int32_t Q, int32_t *idx, double *dist, uint8_t *near_tie,
                  void *scratch, void *stream);
@@ -174,7 +183,8 @@ int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes);
  *   node_step  dev i32[Q x (n_max_extend/n_tree + 1)]  1-based step of each emitted node
  *   n_nodes    dev i32[Q]
  *   ctrl_idx   dev i32[Q x n_max_extend] (nullable) chosen rollout index per step
- *   flags      dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin
+ *   flags      dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin (see
+ *              crlk_dwa_control), bit3 empty DWA grid (status CRLK_EXT_INVALID, nothing executed)
  *   active     dev u8[Q] (nullable) 0 => skip this pair (n_steps = 0, n_nodes = 0)
  *   stats      dev u64[3] (nullable) ACCUMULATED (+=): extensions run, control steps
  *              executed, rollouts scored -- the work counters behind bench.py's roofline. */
@@ -327,6 +337,9 @@ int crlk_gym_step(const CrlkEnv *env, double *states, const double *goals, int32
 /* Test hook: the atan2 of the rollout scoring loop (dwa.py:58 `np.arctan2`), evaluated for n
  * argument pairs; y, x, out dev f64[n].  The kernels use a table-driven atan2 (<= 1.5 ulp). */
 int crlk_debug_atan2(const double *y, const double *x, int32_t n, double *out, void *stream);
+/* Test hook: fast[i] = the correctly rounded quotient a[i] / b[i] as the cost normalisation forms it
+ * (one multiply + two fused corrections on y = 1 / b), exact[i] = a[i] / b[i] by the division operator. */
+int crlk_debug_div(const double *a, const double *b, int32_t n, double *fast, double *exact, void *stream);
 
 /* ---- whole-query planning on the device: RRT.planning (planner/rrt.py:51-89), DWA steering ---- */
 

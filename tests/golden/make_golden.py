@@ -826,10 +826,102 @@ def g_formats():
     save("formats", **out)
 
 
+# ------------------------------------------------- contract-size runs (BASELINE configs 1 and 3)
+
+def _plan_dwa_one(a):
+    """One full RRT.planning run of the unmodified reference (worker of a process pool)."""
+    mname, start, goal, seed, iters = a
+    maps = load_maps()
+    env = make_env(maps[mname])
+    planner = RRT(env, max_iter=iters)
+    planner.set_start_and_goal(np.array(start, dtype=float), np.array(goal, dtype=float))
+    rec = tap_samples(planner)
+    random.seed(seed); np.random.seed(seed)
+    steps = {"n": 0, "ext": 0}
+    oc = planner.dwa.control
+    ost = planner.steer
+
+    def ctrl(x, g, _s=steps, _oc=oc):
+        _s["n"] += 1
+        return _oc(x, g)
+
+    def steer(*a, _s=steps, **k):
+        _s["ext"] += 1
+        return ost(*a, **k)
+    planner.dwa.control = ctrl
+    planner.steer = steer
+    tic = time.time()
+    with quiet():
+        path = planner.planning()
+    el = time.time() - tic
+    states, parents, plen = pack_tree(planner)
+    return dict(samples=np.array(rec), node_states=states, parents=parents, plen=plen, path=np.array(path),
+                reach=np.array(planner.reach_exactly), ctrl_steps=np.array(steps["n"]),
+                extensions=np.array(steps["ext"]), ref_seconds=np.array(el),
+                planning_time=np.array(planner.planning_time))
+
+
+def _pool_runs(jobs, workers):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_plan_dwa_one, jobs, chunksize=1)
+
+
+def g_plan_dwa_full():
+    """BASELINE config 1 at contract size (examples/test.py:144-160): test_env1, start
+    [-5,-15,0,0,0] -> goal [10,10,0,0,0], RRT defaults (max_iter 500, rrt.py:35), seeds 0..9."""
+    jobs = [("test_env1", [-5, -15, 0, 0, 0], [10, 10, 0, 0, 0], s, 500) for s in range(10)]
+    res = _pool_runs(jobs, int(os.environ.get("GOLDEN_WORKERS", "5")))
+    out = {"n_runs": np.array(len(jobs)), "max_iter": np.array(500)}
+    for k, (job, r) in enumerate(zip(jobs, res)):
+        out[f"run{k}_seed"] = np.array(job[3])
+        out[f"run{k}_start"] = np.array(job[1], dtype=float)
+        out[f"run{k}_goal"] = np.array(job[2], dtype=float)
+        for key, v in r.items():
+            out[f"run{k}_{key}"] = v
+        print(f"plan_dwa_full seed {job[3]}: {len(r['node_states'])} nodes, {len(r['samples'])} samples, "
+              f"{int(r['extensions'])} extensions, {int(r['ctrl_steps'])} control steps, reach={bool(r['reach'])}, "
+              f"{float(r['ref_seconds']):.1f}s")
+    save("plan_dwa_full", **out)
+
+
+def g_plan_cfg3():
+    """BASELINE config 3 (examples/benchmark.py:56-75) with the reference's own RRT (DWA steering):
+    all 12 ordered (start, goal) pairs of benchmark_position_test_env{1,2}.pkl on test_env{1,2}.pkl,
+    max_iter 500, seed = 100 * env + pair index."""
+    jobs, meta = [], []
+    for e, mname in ((1, "test_env1"), (2, "test_env2")):
+        pos = pickle.load(open(os.path.join(REF, "examples", f"benchmark_position_test_env{e}.pkl"), "rb"))
+        pos = np.asarray(pos, dtype=float)
+        k = 0
+        for i in range(len(pos)):
+            for j in range(len(pos)):
+                if i == j:
+                    continue
+                jobs.append((mname, pos[i], pos[j], 100 * e + k, 500))
+                meta.append((e, i, j))
+                k += 1
+    res = _pool_runs(jobs, int(os.environ.get("GOLDEN_WORKERS", "5")))
+    out = {"n_runs": np.array(len(jobs)), "max_iter": np.array(500)}
+    for k, (job, m, r) in enumerate(zip(jobs, meta, res)):
+        out[f"run{k}_env"] = np.array(m[0]); out[f"run{k}_i"] = np.array(m[1]); out[f"run{k}_j"] = np.array(m[2])
+        out[f"run{k}_seed"] = np.array(job[3])
+        out[f"run{k}_start"] = np.array(job[1], dtype=float)
+        out[f"run{k}_goal"] = np.array(job[2], dtype=float)
+        for key, v in r.items():
+            out[f"run{k}_{key}"] = v
+        # benchmark.py:69-75
+        out[f"run{k}_runtime"] = np.array(0.2 * (len(r["path"]) - 1) if bool(r["reach"]) else -1.0)
+        print(f"plan_cfg3 env{m[0]} {m[1]}->{m[2]}: {len(r['node_states'])} nodes, {len(r['samples'])} samples, "
+              f"{int(r['extensions'])} extensions, reach={bool(r['reach'])}, {float(r['ref_seconds']):.1f}s")
+    save("plan_cfg3", **out)
+
+
 ALL = dict(fixtures=g_fixtures, numerics=g_numerics, motion=g_motion, dwa=g_dwa,
            dwa_clearance=g_dwa_clearance, geometry=g_geometry, obs=g_obs, nearest=g_nearest,
            steer_dwa=g_steer_dwa, plan_dwa=g_plan_dwa, policy=g_policy, estimator=g_estimator,
-           steer_rl=g_steer_rl, plan_rl=g_plan_rl, gym=g_gym, circle=g_circle, formats=g_formats)
+           steer_rl=g_steer_rl, plan_rl=g_plan_rl, gym=g_gym, circle=g_circle, formats=g_formats,
+           plan_dwa_full=g_plan_dwa_full, plan_cfg3=g_plan_cfg3)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -255,3 +255,67 @@ def test_fused_rrt_device_sampling():
         sb_, pb = b.tree(q)
         assert np.array_equal(sa, sb_) and np.array_equal(pa, pb)
     assert int(np_(a.forest.n_nodes).sum()) > 3 * Q
+
+
+def _check_against_reference_runs(planner_cls, g, runs, env, **kw):
+    """Plan the recorded reference runs `runs` of golden file `g` together (recorded sample streams)
+    and compare trees, parents, reach flags and final paths with the reference's."""
+    starts = np.array([g[f"run{r}_start"] for r in runs])
+    goals = np.array([g[f"run{r}_goal"] for r in runs])
+    S = max(len(g[f"run{r}_samples"]) for r in runs)
+    streams = np.zeros((len(runs), S, 5))
+    for i, r in enumerate(runs):
+        s = g[f"run{r}_samples"]
+        streams[i, :len(s)] = s
+        streams[i, len(s):] = goals[i]          # never consumed: the query is done by then
+    p = planner_cls(env, starts, goals, max_iter=int(g["max_iter"]), **kw)
+    reached = p.plan(streams)
+    flags = np_(p.flags) if hasattr(p, "flags") else np.zeros(len(runs), dtype=np.uint8)
+    same = 0
+    for i, r in enumerate(runs):
+        states, parents = p.tree(i)
+        ref = g[f"run{r}_node_states"]
+        ok = len(states) == len(ref) and np.allclose(states, ref, rtol=1e-9, atol=1e-11)
+        if not ok:
+            assert flags[i] & 3, f"run {r} differs from the reference without a near-tie / near-boundary report"
+            continue
+        assert np.array_equal(parents, g[f"run{r}_parents"])
+        assert reached[i] == bool(g[f"run{r}_reach"])
+        np.testing.assert_allclose(np.array(p.final_course(i)), g[f"run{r}_path"], rtol=1e-9, atol=1e-11)
+        if planner_cls.__name__ == "FusedRRT":
+            assert int(np_(p.cursor)[i]) == len(g[f"run{r}_samples"])       # same number of draws consumed
+        same += 1
+    return same
+
+
+def test_fused_rrt_reference_runs_contract_size():
+    """BASELINE config 1 at the reference's size (examples/test.py:144-160; rrt.py:35 max_iter 500;
+    seeds 0..9, up to 500 extensions / 5,458 control steps / 190 nodes per query): all ten reference
+    runs planned in ONE launch of crlk_plan_dwa from the recorded sample streams."""
+    from crl_kino_b200.planner.batched import FusedRRT
+    g = golden("plan_dwa_full")
+    env, _ = make_envs(fixture_map("test_env1"))
+    same = _check_against_reference_runs(FusedRRT, g, list(range(10)), env)
+    assert same >= 9, f"only {same}/10 runs identical to the reference"
+
+
+@pytest.mark.parametrize("e", (1, 2))
+def test_fused_rrt_benchmark_positions_vs_reference(e):
+    """BASELINE config 3 (examples/benchmark.py:56-75): the 12 ordered (start, goal) pairs of
+    benchmark_position_test_env{e}.pkl on test_env{e}.pkl, planned by the reference's own RRT
+    (max_iter 500) -- here in one launch, same trees and paths."""
+    from crl_kino_b200.planner.batched import FusedRRT
+    g = golden("plan_cfg3")
+    runs = [r for r in range(int(g["n_runs"])) if int(g[f"run{r}_env"]) == e]
+    env, _ = make_envs(fixture_map(f"test_env{e}"))
+    same = _check_against_reference_runs(FusedRRT, g, runs, env)
+    assert same >= len(runs) - 1, f"only {same}/{len(runs)} runs identical to the reference"
+
+
+def test_lockstep_rrt_reference_runs_contract_size():
+    """The lock-step planner on three of the contract-size reference runs (seeds 1, 3, 6)."""
+    from crl_kino_b200.planner.batched import BatchedRRT
+    g = golden("plan_dwa_full")
+    env, _ = make_envs(fixture_map("test_env1"))
+    same = _check_against_reference_runs(BatchedRRT, g, [1, 3, 6], env)
+    assert same == 3

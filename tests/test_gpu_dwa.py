@@ -32,7 +32,7 @@ def test_dwa_golden(name):
     assert not bad.any(), np.where(bad)
     same = idx == g[name + "_idx"]
     assert np.array_equal(np_(r["opt_v"])[same], g[name + "_optv"][same])      # grid values: bit exact
-    np.testing.assert_allclose(np_(r["opt_cost"])[same], g[name + "_cmin"][same], rtol=1e-10)
+    np.testing.assert_allclose(np_(r["opt_cost"])[same], g[name + "_cmin"][same], rtol=1e-13)
     np.testing.assert_allclose(np_(r["opt_traj"])[same], g[name + "_traj"][same], rtol=1e-12, atol=1e-13)
     v, traj = d.control(g[name + "_states"][0], g[name + "_goals"][0])         # reference signature
     assert np.array_equal(v, g[name + "_optv"][0])
@@ -72,7 +72,7 @@ def test_dwa_vs_oracle_random(name):
     assert tie.sum() <= max(2, n // 50)
     same = np_(r["opt_idx"]) == ref["opt_idx"]
     assert np.array_equal(np_(r["opt_v"])[same], ref["opt_v"][same])
-    np.testing.assert_allclose(np_(r["opt_cost"])[same], ref["opt_cost"][same], rtol=1e-10)
+    np.testing.assert_allclose(np_(r["opt_cost"])[same], ref["opt_cost"][same], rtol=1e-13)
 
 
 def test_dwa_clearance_vs_oracle_dense_map():
@@ -124,3 +124,50 @@ def test_rollout_atan2_accuracy():
     assert np.all(np.signbit(got) == np.signbit(ref))
     assert err.max() <= 3.0, f"worst error {err.max()} ulp at y={y[err.argmax()]}, x={x[err.argmax()]}"
     assert np.mean(err <= 1.0) > 0.95
+
+
+def test_cost_normalisation_quotient_is_correctly_rounded():
+    """The cost columns are divided by their sums with one multiply and two fused corrections on the
+    reciprocal (div_rn_y); it must return exactly what the division operator returns (dwa.py:78)."""
+    import ctypes as C
+    import torch
+    from crl_kino_b200._lib import check, lib
+    rng = np.random.default_rng(3)
+    n = 1 << 21
+    a = rng.uniform(0.0, np.pi, n)
+    b = rng.uniform(1e-3, 2e4, n)
+    a[:1000] = 0.0
+    a[1000:2000] = rng.uniform(-1.0, 1.0, 1000)                       # speed costs can be negative
+    b[2000:3000] = np.nextafter(2.0 ** rng.integers(-3, 14, 1000), 0)  # significands of all ones
+    a[3000:4000] = b[3000:4000]
+    a[4000:300000] = rng.uniform(0, 1, 296000) ** 8 * np.pi            # many small heading costs
+    da, db = torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda()
+    fast, exact = torch.empty_like(da), torch.empty_like(da)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    check(lib().crlk_debug_div(p(da), p(db), n, p(fast), p(exact), None))
+    assert np.array_equal(np_(exact), a / b)
+    assert np.array_equal(np_(fast), a / b)
+
+
+def test_dwa_empty_window_is_reported():
+    """v outside the limits by more than acc * dt: np.arange is empty and the reference raises
+    (dwa.py:76 on the empty cost table); here opt_idx = -1 / n_rollouts = 0 / NaN, and an extension
+    from such a state ends at once with CRLK_EXT_INVALID and flag bit 3 (no out-of-range reads)."""
+    from crl_kino_b200 import ops
+    env, _ = make_envs(fixture_map("test_env1"))
+    d = _dwa(env, dt=0.2, v_res=0.02)
+    s = np.array([[0.0, 0.0, 0.0, 2.0, 0.0], [0.0, 0.0, 0.0, 0.3, 0.0], [0.0, 0.0, 0.0, 0.0, 9.0]])
+    g = np.array([[5.0, 5.0, 0, 0, 0]] * 3)
+    r = d.control_batch(s, g, want_traj=True)
+    assert np_(r["opt_idx"]).tolist()[0] == -1 and np_(r["opt_idx"])[2] == -1 and np_(r["opt_idx"])[1] >= 0
+    assert np_(r["n_rollouts"]).tolist()[0] == 0 and np_(r["n_rollouts"])[1] > 0
+    assert np.isnan(np_(r["opt_v"])[0]).all() and np.isnan(np_(r["opt_traj"])[0]).all()
+    assert np.isfinite(np_(r["opt_v"])[1]).all()
+    out = ops.extend_dwa(env.handle, d.params(), ops.extend_params(), s, g)
+    assert np_(out["status"]).tolist()[0] == 3 and np_(out["n_steps"])[0] == 0 and np_(out["flags"])[0] & 8
+    assert np_(out["status"])[2] == 3
+    assert np_(out["n_steps"])[1] > 0 and not (np_(out["flags"])[1] & 8)
+    from crl_kino_b200.planner.rrt import RRT
+    p = RRT(env)
+    with pytest.raises(ValueError):
+        p.set_start_and_goal(np.array([-5, -15, 0, 2.0, 0.0]), np.array([10, 10, 0, 0, 0.0]))

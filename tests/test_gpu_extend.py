@@ -170,3 +170,30 @@ def test_pipelined_host_api_equals_synchronous():
             assert np.array_equal(a[k], b[k]), k
         for q in range(Q):
             assert np.array_equal(a["path"][q, :ns[q]], b["path"][q, :ns[q]])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_rrt_class_contract_size(seed):
+    """examples/test.py --case rrt as shipped (max_iter 500, rrt.py:35) through the drop-in RRT with
+    the reference's own RNG seeding: the same tree as the unmodified reference (golden plan_dwa_full)."""
+    from crl_kino_b200.planner.rrt import RRT
+    g = golden("plan_dwa_full")
+    env, _ = make_envs(fixture_map("test_env1"))
+    p = RRT(env)
+    p.verbose = False
+    p.set_start_and_goal(g[f"run{seed}_start"], g[f"run{seed}_goal"])
+    random.seed(seed)
+    np.random.seed(seed)
+    path = p.planning()
+    index = {id(n): i for i, n in enumerate(p.node_list)}
+    parents = np.array([-1 if n.parent is None else index[id(n.parent)] for n in p.node_list])
+    states = np.array([n.state for n in p.node_list])
+    same = len(states) == len(g[f"run{seed}_node_states"]) and np.array_equal(parents, g[f"run{seed}_parents"])
+    if not same:
+        assert p.flags_seen & 3, "tree differs from the reference without a near-tie / near-boundary report"
+        pytest.skip("a reported near-tie / near-boundary decision went the other way")
+    assert p.n_extend_calls == int(g[f"run{seed}_extensions"])
+    assert p.n_control_steps == int(g[f"run{seed}_ctrl_steps"])
+    np.testing.assert_allclose(states, g[f"run{seed}_node_states"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(np.array(path), g[f"run{seed}_path"], rtol=1e-9, atol=1e-11)
+    assert p.reach_exactly == bool(g[f"run{seed}_reach"])

@@ -14,7 +14,7 @@ rng = np.random.default_rng(0)
 clr = lambda c: env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
 cand = free_states(clr, rng, 4000, 2.5); cand[:, 3:] = 0
 tg = cand.copy(); ang = rng.uniform(-np.pi, np.pi, len(cand)); tg[:, 0] += 15*np.cos(ang); tg[:, 1] += 15*np.sin(ang)
-names = ["wait-prev", "tables", "rollouts+sums", "f:warp0-reduce", "f:cost", "costs+argmin", "f:row1", "f:closing-barrier", "collision", "f:epilogue"]
+names = ["wait-prev", "tables", "rollouts", "costs+argmin", "f:merge+tie", "column sums", "f:row1", "f:closing-barrier", "collision", "f:epilogue"]
 raw = ctypes.CDLL(lib()._name)
 for Q in ((1, 296) if os.environ.get('USE_CLEARANCE') else (1, 444, 1776)):
     f, g = ops.as_dev(cand[:Q]), ops.as_dev(tg[:Q])
