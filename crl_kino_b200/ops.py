@@ -333,33 +333,42 @@ def estimator_choose_parent(env, est, states, n_nodes, targets, max_nodes=None, 
     return idx, cost
 
 
+def extend_rl_outputs(xp, Q, d, want_actions=False):
+    per = xp.n_max_extend // xp.n_tree + 1
+    return dict(path=torch.empty(Q, xp.n_max_extend, 5, dtype=torch.float64, device=d),
+                n_steps=torch.empty(Q, dtype=torch.int32, device=d),
+                status=torch.empty(Q, dtype=torch.int32, device=d),
+                node_step=torch.zeros(Q, per, dtype=torch.int32, device=d),
+                n_nodes=torch.empty(Q, dtype=torch.int32, device=d),
+                flags=torch.empty(Q, dtype=torch.uint8, device=d),
+                actions=torch.zeros(Q, xp.n_max_extend, 2, dtype=torch.float32, device=d)
+                if want_actions else None)
+
+
 def extend_rl(env, pol, xp, from_states, targets, noise=None, eps=0.0, active=None, want_actions=False,
-              noise_cursor=None):
+              noise_cursor=None, out=None, workspace=None):
+    """RRT_RL.steer (rrt_rl.py:22-63) for Q (from, target) pairs.  out / workspace: reuse the output
+    tensors / the scratch buffer of an earlier call (same Q or larger workspace)."""
     from_states = as_dev(from_states).reshape(-1, 5)
     Q = from_states.shape[0]
     targets = as_dev(targets).reshape(Q, 5)
     d = from_states.device
-    per = xp.n_max_extend // xp.n_tree + 1
-    out = dict(path=torch.empty(Q, xp.n_max_extend, 5, dtype=torch.float64, device=d),
-               n_steps=torch.empty(Q, dtype=torch.int32, device=d),
-               status=torch.empty(Q, dtype=torch.int32, device=d),
-               node_step=torch.zeros(Q, per, dtype=torch.int32, device=d),
-               n_nodes=torch.empty(Q, dtype=torch.int32, device=d),
-               flags=torch.empty(Q, dtype=torch.uint8, device=d),
-               actions=torch.zeros(Q, xp.n_max_extend, 2, dtype=torch.float32, device=d)
-               if want_actions else None)
+    if out is None:
+        out = extend_rl_outputs(xp, Q, d, want_actions)
     noise_rows = 0
     if noise is not None:
         noise = as_dev(noise, torch.float32).reshape(Q, -1, 2)
         noise_rows = noise.shape[1]
-    nbytes = lib().crlk_extend_rl_workspace_bytes(pol.h, Q)
-    ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=d)
+    nbytes = int(lib().crlk_extend_rl_workspace_bytes(pol.h, Q)) + 256
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else out.get("_ws")
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=d)
     off = (-ws.data_ptr()) % 256
     check(lib().crlk_extend_rl(env.h, pol.h, C.byref(xp), _ptr(from_states), _ptr(targets), Q,
                                _ptr(noise), noise_rows, _ptr(noise_cursor), float(eps), _ptr(out["path"]),
                                _ptr(out["n_steps"]),
                                _ptr(out["status"]), _ptr(out["node_step"]), _ptr(out["n_nodes"]),
-                               _ptr(out["actions"]), _ptr(out["flags"]), _ptr(active),
+                               _ptr(out.get("actions")), _ptr(out["flags"]), _ptr(active),
                                C.c_void_p(ws.data_ptr() + off), _stream()))
     out["_ws"] = ws
     return out

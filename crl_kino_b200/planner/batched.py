@@ -63,8 +63,9 @@ class Forest:
 class BatchedExtender:
     """nearest -> gather -> extend for Q queries per call."""
 
-    def __init__(self, env, forest, dwa=None, policy=None, eps=0.0, t_max_extend=10.0, t_tree=5.0):
+    def __init__(self, env, forest, dwa=None, policy=None, eps=0.0, t_max_extend=10.0, t_tree=5.0, rl_chunk=8192):
         self.env = env
+        self.rl_chunk = rl_chunk      # policy steering: queries per crlk_extend_rl pass (bounds its workspace)
         self.forest = forest
         self.dwa = dwa
         self.policy = policy
@@ -74,7 +75,7 @@ class BatchedExtender:
         Q = forest.Q
         d = forest.states.device
         self.from_states = torch.empty(Q, 5, dtype=torch.float64, device=d)
-        self.stats = torch.zeros(4, dtype=torch.int64, device=d)
+        self.stats = torch.zeros(8, dtype=torch.int64, device=d)      # crlk_extend_dwa work counters (include/crlk.h)
         self.out = None
         self.max_nodes = forest.cap
         # pinned staging for the host-buffer entry point
@@ -89,7 +90,9 @@ class BatchedExtender:
                            nearest_idx=torch.empty(Q, dtype=torch.int32).pin_memory(),
                            flags=torch.empty(Q, dtype=torch.uint8).pin_memory())
         self.extend_targets = None    # extend toward these instead of the samples (cfg5)
-        self.launches_per_step = 4 if policy is None else 3 + self.xp.n_max_extend * (2 + len(policy.actor.weights)) + 1
+        chunks = (Q + rl_chunk - 1) // rl_chunk
+        self.launches_per_step = 4 if policy is None else \
+            2 + chunks * (2 + self.xp.n_max_extend * (2 + len(policy.actor.weights)) * (2 if min(Q, rl_chunk) >= 2048 else 1))
 
     def step(self, samples, events=None):
         """samples: float64 CUDA [Q, 5].  Returns the extension outputs (CUDA tensors)."""
@@ -109,11 +112,25 @@ class BatchedExtender:
                                       out=self.out, stats=self.stats)
         else:
             tg = samples if self.extend_targets is None else self.extend_targets
-            self.out = ops.extend_rl(self.env.handle, self.policy.actor.handle, self.xp, self.from_states,
-                                     tg, None, self.eps)
+            self.out = self._extend_rl_chunked(tg)
         mark(3)
         self.out["nearest_idx"], self.out["nearest_dist"] = idx, dist
         return self.out
+
+    def _extend_rl_chunked(self, targets):
+        """crlk_extend_rl over the batch in passes of rl_chunk queries (outputs written in place)."""
+        Q, c = self.forest.Q, self.rl_chunk
+        if Q <= c:
+            return ops.extend_rl(self.env.handle, self.policy.actor.handle, self.xp, self.from_states, targets,
+                                 None, self.eps, out=self.out)
+        out = self.out if self.out is not None else ops.extend_rl_outputs(self.xp, Q, self.from_states.device)
+        for q0 in range(0, Q, c):
+            q1 = min(Q, q0 + c)
+            view = {k: (v[q0:q1] if torch.is_tensor(v) else v) for k, v in out.items() if not k.startswith("_")}
+            r = ops.extend_rl(self.env.handle, self.policy.actor.handle, self.xp, self.from_states[q0:q1],
+                              targets[q0:q1], None, self.eps, out=view, workspace=out.get("_ws"))
+            out["_ws"] = r["_ws"]
+        return out
 
     def step_host(self, samples_np):
         """Host-buffer entry point: numpy [Q, 5] in, dict of numpy views out

@@ -28,7 +28,7 @@ def inputs(args, name):
         obs = cio.load_obstacles(os.path.join(args.data, "data", "obstacles", f"test_{name}.pkl"))
         pos = cio.load_positions(os.path.join(args.data, "examples", f"benchmark_position_test_{name}.pkl"))
         return obs, pos
-    fx = np.load(os.path.join(ROOT, "tests", "golden", "fixtures.npz"))
+    fx = np.load(os.path.join(ROOT, "data", "fixtures.npz"))
     return fx["map_test_" + name], fx["positions_" + name]
 
 

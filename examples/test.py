@@ -9,7 +9,7 @@
     python examples/test.py --case batch --queries 64 # many RRT queries in one launch (FusedRRT)
 
 Maps come from --data DIR (the reference's data/obstacles/*.pkl, read as they are) or, by default,
-from the copies of test_env1 / test_env2 kept in tests/golden/fixtures.npz.  Trees and paths are
+from the copies of test_env1 / test_env2 kept in data/fixtures.npz.  Trees and paths are
 written as pickles the reference's own scripts can load (--out DIR).
 """
 import argparse
@@ -30,7 +30,7 @@ from crl_kino_b200.utils import io as cio  # noqa: E402
 def load_map(args, name):
     if args.data:
         return cio.load_obstacles(os.path.join(args.data, name + ".pkl"))
-    fx = np.load(os.path.join(ROOT, "tests", "golden", "fixtures.npz"))
+    fx = np.load(os.path.join(ROOT, "data", "fixtures.npz"))
     return fx["map_" + name]
 
 
@@ -42,7 +42,7 @@ def make_policy(seed=0):
 
 def make_estimator():
     from crl_kino_b200.estimator import load_estimator
-    w = np.load(os.path.join(ROOT, "tests", "golden", "estimator_weights.npz"))
+    w = np.load(os.path.join(ROOT, "data", "estimator_weights.npz"))
     return load_estimator({k[4:]: w[k] for k in w.files if k.startswith("est.")},
                           {k[4:]: w[k] for k in w.files if k.startswith("cls.")})
 

@@ -28,8 +28,12 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+DATA = os.path.join(ROOT, "data")        # reference maps / start-goal sets / estimator weights (inputs, not expectations)
+
+
 def golden(name):
-    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    d = DATA if name in ("fixtures", "estimator_weights") else GOLDEN
+    return np.load(os.path.join(d, name + ".npz"), allow_pickle=False)
 
 
 @pytest.fixture(scope="session")

@@ -40,8 +40,11 @@ import crl_kino.policy.dwa as dwa_mod  # noqa: E402
 from tianshou.policy import DDPGPolicy  # noqa: E402
 
 
+DATA = os.path.join(os.path.dirname(os.path.dirname(HERE)), "data")   # inputs shared with bench.py / examples
+
+
 def save(name, **arrs):
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(DATA if name in ("fixtures", "estimator_weights") else HERE, name + ".npz")
     np.savez_compressed(path, **arrs)
     print(f"wrote {path}: {os.path.getsize(path)/1024:.1f} KiB")
 
