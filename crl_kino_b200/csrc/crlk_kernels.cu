@@ -1556,7 +1556,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
              const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
              double *path, int *n_steps, int *status, int *node_step, int *n_nodes, int *ctrl_idx,
              uint8_t *flags, const uint8_t *__restrict__ active, int *work_counter,
-             unsigned long long *stats)
+             unsigned long long *stats, const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DwaSmem sm;
@@ -1570,7 +1570,10 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
         __syncthreads();
-        if (tid == 0) s_q = atomicAdd(work_counter, 1);
+        if (tid == 0) {
+            const int w = atomicAdd(work_counter, 1);
+            s_q = (w < Q && order) ? order[w] : w;
+        }
         __syncthreads();
         const int q = s_q;
         if (q >= Q) break;
@@ -1637,6 +1640,75 @@ static int get_work_counter(int device, int **out, cudaStream_t stream)
     return CRLK_OK;
 }
 
+// Longest-processing-time-first order of a batch of extensions.  An extension toward a target d
+// metres away needs at least (d - reach) / (v_max * dt) control steps unless it collides first, and
+// one CTA runs its steps one after the other: the launch cannot end before its longest extension
+// does, so those must start first.  One CTA buckets the queries by distance (1/8 m bins, descending);
+// the order inside a bin is whatever the atomics give (scheduling only: results do not depend on it).
+#define LPT_BINS 256
+__global__ void __launch_bounds__(1024)
+k_lpt_order(const double *__restrict__ from_states, const double *__restrict__ targets,
+            const uint8_t *__restrict__ active, int Q, int *order)
+{
+    __shared__ int s_bin[LPT_BINS];
+    __shared__ int s_warp[32];
+    for (int b = threadIdx.x; b < LPT_BINS; b += blockDim.x) s_bin[b] = 0;
+    __syncthreads();
+    auto key = [&](int q) {
+        if (active && !active[q]) return LPT_BINS - 1;                       // inactive pairs go last
+        const float dx = (float)(from_states[5 * (size_t)q] - targets[5 * (size_t)q]);
+        const float dy = (float)(from_states[5 * (size_t)q + 1] - targets[5 * (size_t)q + 1]);
+        const int k = (int)(sqrtf(dx * dx + dy * dy) * 8.0f);
+        return LPT_BINS - 2 - min(max(k, 0), LPT_BINS - 2);                  // far targets -> low bins -> first
+    };
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) atomicAdd(&s_bin[key(q)], 1);
+    __syncthreads();
+    // exclusive prefix over the 256 bins by the first 256 threads
+    int v = (threadIdx.x < LPT_BINS) ? s_bin[threadIdx.x] : 0, inc = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x < LPT_BINS) {
+        int base = 0;
+        for (int w = 0; w < warp; w++) base += s_warp[w];
+        s_bin[threadIdx.x] = base + inc - v;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) order[atomicAdd(&s_bin[key(q)], 1)] = q;
+}
+
+// Scratch for the order arrays: a ring of ints per device, one slice per launch (like the work counters).
+#define ORDER_RING (1 << 22)
+static int *g_order_ring[64] = {nullptr};
+static unsigned long long g_order_next[64] = {0};
+
+static int get_order_slice(int device, int n, int **out)
+{
+    *out = nullptr;
+    if (device < 0 || device >= 64 || n > ORDER_RING) return CRLK_OK;       // no ordering: plain queue order
+    if (!g_order_ring[device]) {
+        int *p = nullptr;
+        CRLK_CUDA(cudaMalloc(&p, sizeof(int) * (size_t)ORDER_RING));
+        int *expected = nullptr;
+        if (!__atomic_compare_exchange_n(&g_order_ring[device], &expected, p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE))
+            cudaFree(p);
+    }
+    for (;;) {
+        unsigned long long cur = __atomic_load_n(&g_order_next[device], __ATOMIC_RELAXED);
+        unsigned long long off = cur % ORDER_RING;
+        unsigned long long start = (off + (unsigned long long)n <= ORDER_RING) ? cur : cur + (ORDER_RING - off);
+        if (__atomic_compare_exchange_n(&g_order_next[device], &cur, start + (unsigned long long)n, false,
+                                        __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) {
+            *out = g_order_ring[device] + (start % ORDER_RING);
+            return CRLK_OK;
+        }
+    }
+}
+
 extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
                                const double *from_states, const double *targets, int32_t Q,
                                double *path, int32_t *n_steps, int32_t *status, int32_t *node_step,
@@ -1670,9 +1742,19 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
     int *counter = nullptr;
     rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
     if (rc) return rc;
+    int *order = nullptr;
+    static const char *no_lpt = getenv("CRLK_NO_LPT");
+    if (Q > grid && !no_lpt) {                       // with a CTA per pair there is nothing to order
+        rc = get_order_slice(dev, Q, &order);
+        if (rc) return rc;
+        if (order) {
+            k_lpt_order<<<1, 1024, 0, (cudaStream_t)stream>>>(from_states, targets, active, Q, order);
+            CRLK_LAUNCH_CHECK();
+        }
+    }
     kern<<<grid, threads, smem, (cudaStream_t)stream>>>(
         env->p, d, x, env->os, from_states, targets, Q, path, n_steps, status, node_step,
-        n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats);
+        n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats, order);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
