@@ -217,8 +217,9 @@ def parity_block(gpu, ref, n):
             "near_boundary": int(((fl & 1) != 0).sum()), "near_tie": int(((fl & 2) != 0).sum()),
             "diverged": int((~same & (fl == 0)).sum()), "diverged_reported": int((~same & (fl != 0)).sum()),
             "worst_path_rel_err_of_identical": worst,
-            "contract": "indices / flags bit-exact, paths <= 1e-4 relative (checked at 1e-9); cases within 1e-6 of an "
-                        "obstacle boundary or with two different rollouts within 32 ulp of the winning cost are reported"}
+            "contract": "indices / flags bit-exact, paths <= 1e-4 relative (checked at 1e-9 and bitwise); reported separately: "
+                        "states within 1e-6 of an obstacle boundary (near_boundary) and argmin decisions that one misrounded "
+                        "last bit of the C library's atan2 could change (near_tie, include/crlk.h crlk_dwa_control)"}
 
 
 def python_reference_cfg1(max_iter=30, seeds=(0, 1)):

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "crlk_rrt_append": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, F64, F64, P, P, P, P, P, P, P, P]),
     "crlk_debug_atan2": (C.c_int, [P, P, I32, P, P]),
     "crlk_debug_div": (C.c_int, [P, P, I32, P, P, P]),
+    "crlk_debug_sincos": (C.c_int, [P, I32, P, P, P]),
     "crlk_gym_step": (C.c_int, [P, P, P, I32, P, F64, P, I32, P, P, P, P, I32, P, P]),
     "crlk_plan_dwa": (C.c_int, [P, P, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P, P]),
     "crlk_sample_stream": (C.c_int, [P, P, I32, I32, P, P]),

@@ -61,12 +61,58 @@ __device__ __forceinline__ double acc_substep(double cur, double a, double acc, 
     return u;
 }
 
+// ------------------------------------------------- correctly rounded atan2 / sincos
+#include "crlk_cr_tables.h"
+
+// full tables in global memory (read-only path): the sincos table and the slow path of atan2
+__device__ const unsigned long long g_cr_atan_bits[CRLK_CR_ATAN_NK * CRLK_CR_ATAN_FIELDS] = CRLK_CR_ATAN_INIT;
+__device__ const unsigned long long g_cr_sc_bits[CRLK_CR_SC_NK * 4] = CRLK_CR_SC_INIT;
+#define CRM_ATAN_FULL(tab) ((const double *)g_cr_atan_bits)
+#include "crlk_crmath.h"
+
+#define CRLK_ATAN_SMEM_DOUBLES (CRLK_CR_ATAN_NK * CRLK_CR_ATAN_FAST_FIELDS)
+
+// Stages the fast-path fields of the atan table in shared memory ([field][interval]: lanes that
+// fall into different intervals read different banks); tid / n = the loading group's thread index / size.
+__device__ __forceinline__ void load_atan_table(double *dst, int tid, int n)
+{
+    for (int i = tid; i < CRLK_ATAN_SMEM_DOUBLES; i += n) dst[i] = __longlong_as_double((long long)g_cr_atan_bits[i]);
+}
+
+// 1 / a for a normal, positive a: hardware seed (about 20 bits) + two Newton steps.
+__device__ __forceinline__ double crlk_rcp_pos(double a) { return crm_rcp(a); }
+
+static __device__ __noinline__ double crlk_atan2_special(double y, double x) { return atan2(y, x); }
+
+// atan2 of the rollout scoring loop (dwa.py:58), correctly rounded (crlk_crmath.h): the same bits
+// as the C library's result that np.arctan2 returns for Python scalars, up to the library's own
+// rare misroundings (7.5e-4 of random arguments, tools/cr_check.cpp).  `tab`: load_atan_table's
+// copy in shared memory.  Zero, tiny, huge and NaN arguments take the library path.
+__device__ __forceinline__ double crlk_atan2(double y, double x, const double *tab)
+{
+    const double ay = fabs(y), ax = fabs(x);
+    const double mx = ay > ax ? ay : ax, mn = ay > ax ? ax : ay;
+    // the fast path wants 1e-280 < mx < 1e280 and a normal quotient: integer range tests on the
+    // exponent fields (biased exponents 93 .. 1953); NaN, infinities, zero and subnormals fail them
+    const unsigned ex = ((unsigned)__double2hiint(mx) >> 20) & 0x7ffu;
+    const unsigned en = ((unsigned)__double2hiint(mn) >> 20) & 0x7ffu;
+    if (ex - 93u > 1860u || en + 900u < ex || en == 0u) return crlk_atan2_special(y, x);
+    return crm_atan2_core(y, x, tab);
+}
+
+// sin and cos of a heading, correctly rounded for |th| <= 3.15 (math.sin / math.cos of
+// differential_env.py:98-99 on a normalised angle); other arguments take the library path.
+__device__ __forceinline__ void crlk_sincos(double th, double *sn, double *cs)
+{
+    if (!crm_sincos_core(th, (const double *)g_cr_sc_bits, sn, cs)) sincos(th, sn, cs);
+}
+
 // Pose update of one sub-step (differential_env.py:97-103) given the new (u0, u1).
 __device__ __forceinline__ void pose_substep(double *s, double u0, double u1, double dt)
 {
     double th = normalize_angle(s[2] + u1 * dt);
     double sn, cs;
-    sincos(th, &sn, &cs);
+    crlk_sincos(th, &sn, &cs);
     s[2] = th;
     s[0] = s[0] + u0 * cs * dt;
     s[1] = s[1] + u0 * sn * dt;
@@ -83,53 +129,6 @@ __device__ __forceinline__ void motion_velocity_dev(const EnvP &e, double *s, do
         double u1 = vel_substep(s[4], cw, e.max_acc_w, -e.max_w, e.max_w, e.base_dt);
         pose_substep(s, u0, u1, e.base_dt);
     }
-}
-
-// ---------------------------------------------------------------------- atan2
-#include "crlk_atan_table.h"
-
-// 1 / a for a normal, positive a: hardware seed (about 20 bits) + two Newton steps.
-__device__ __forceinline__ double crlk_rcp_pos(double a)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    r = fma(fma(-a, r, 1.0), r, r);
-    r = fma(fma(-a, r, 1.0), r, r);
-    return r;
-}
-
-// atan2 for the rollout scoring loop (dwa.py:58), about 30 float64 instructions instead of
-// the library's ~65: q = min/max of |y|, |x| by a Newton division with residual correction,
-// then the degree-10 Taylor polynomial of atan about the nearest multiple of 1/16 (`tab`:
-// (CRLK_ATAN_DEG + 1) x CRLK_ATAN_NK coefficients, shared memory), then the octant fix-ups.
-// Worst error 1.5 ulp against a 200-bit reference (tools/gen_atan_table.py; measured on the
-// device by tests/test_gpu_dwa.py) -- the library's bound is 2 ulp, numpy's own SIMD arctan2
-// differs from libm in the last bit for 8 % of inputs.  Zero, tiny, huge and NaN arguments take
-// the library path.
-static __device__ __noinline__ double crlk_atan2_special(double y, double x) { return atan2(y, x); }
-
-__device__ __forceinline__ double crlk_atan2(double y, double x, const double *tab)
-{
-    const double ay = fabs(y), ax = fabs(x);
-    // max / min of two non-negative numbers with one comparison (fmax / fmin carry NaN handling)
-    const bool steep = ay > ax;
-    const double mx = steep ? ay : ax, mn = steep ? ax : ay;
-    // the fast path wants 1e-280 < mx < 1e280: one integer range test on the exponent field
-    // (biased exponents 93 .. 1953); NaN, infinities, zero and subnormals fail it
-    const unsigned ex = ((unsigned)__double2hiint(mx) >> 20) & 0x7ffu;
-    if (ex - 93u > 1860u) return crlk_atan2_special(y, x);
-    const double r = crlk_rcp_pos(mx);
-    double q = mn * r;
-    q = fma(fma(-mx, q, mn), r, q);
-    const int k = __double2int_rn(q * 16.0);
-    const double t = fma(-(double)k, 0.0625, q);
-    const double *a = tab + k;                         // tab[coefficient][interval]
-    double p = a[CRLK_ATAN_DEG * CRLK_ATAN_NK];
-#pragma unroll
-    for (int n = CRLK_ATAN_DEG - 1; n >= 0; n--) p = fma(p, t, a[n * CRLK_ATAN_NK]);
-    if (steep) p = 1.5707963267948966 - p;
-    if (__double2hiint(x) < 0) p = 3.141592653589793 - p;            // x < 0 or x == -0.0 (atan2(+-0, -0) = +-pi)
-    return copysign(p, y);
 }
 
 // ------------------------------------------------------------------ geometry
@@ -157,7 +156,7 @@ __device__ __forceinline__ void robot_pose_setup(const EnvP &e, double x, double
                                                  RobotPose &g)
 {
     double sn, cs;
-    sincos(th, &sn, &cs);
+    crlk_sincos(th, &sn, &cs);
     g.x = x; g.y = y; g.c = cs; g.s = sn;
     const double bx[4] = {(double)e.rl, (double)e.rl, (double)e.rr, (double)e.rr};
     const double by[4] = {(double)e.rb, (double)e.rt, (double)e.rt, (double)e.rb};

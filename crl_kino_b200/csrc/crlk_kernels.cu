@@ -495,7 +495,7 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
     double x = st[0], y = st[1], th = st[2];
     if (threadIdx.x == 0) {           // one float64 sincos per observation, not per thread
         double sn0, cs0;
-        sincos(th, &sn0, &cs0);
+        crlk_sincos(th, &sn0, &cs0);
         s_cs[0] = cs0; s_cs[1] = sn0;
         s_near = 0;
     }
@@ -690,22 +690,10 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
 #define PLAN_MIN_BLOCKS 4
 #endif
 
-__device__ __constant__ unsigned long long c_atan_bits[CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1)] = CRLK_ATAN_TAB_INIT;
-
-// copy the atan coefficient table into shared memory (call before the first barrier of the kernel)
-__device__ __forceinline__ void load_atan_table(double *dst)
-{
-    // stored [coefficient][interval]: lanes that fall into different intervals read different banks
-    for (int i = threadIdx.x; i < CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1); i += blockDim.x) {
-        const int k = i / (CRLK_ATAN_DEG + 1), n = i - k * (CRLK_ATAN_DEG + 1);
-        dst[n * CRLK_ATAN_NK + k] = __longlong_as_double((long long)c_atan_bits[i]);
-    }
-}
-
 __global__ void k_debug_atan2(const double *__restrict__ y, const double *__restrict__ x, int n, double *out)
 {
-    __shared__ double tab[CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1)];
-    load_atan_table(tab);
+    __shared__ double tab[CRLK_ATAN_SMEM_DOUBLES];
+    load_atan_table(tab, threadIdx.x, blockDim.x);
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = crlk_atan2(y[i], x[i], tab);
@@ -717,6 +705,22 @@ extern "C" int crlk_debug_atan2(const double *y, const double *x, int32_t n, dou
     CRLK_REQUIRE(n >= 0 && (n == 0 || (y && x && out)), "NULL array");
     if (n == 0) return CRLK_OK;
     k_debug_atan2<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, x, n, out);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
+__global__ void k_debug_sincos(const double *__restrict__ th, int n, double *sn, double *cs)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) crlk_sincos(th[i], &sn[i], &cs[i]);
+}
+
+// Test hook: the sincos of the heading chains and footprints (differential_env.py:98-99), n angles.
+extern "C" int crlk_debug_sincos(const double *th, int32_t n, double *sn, double *cs, void *stream)
+{
+    CRLK_REQUIRE(n >= 0 && (n == 0 || (th && sn && cs)), "NULL array");
+    if (n == 0) return CRLK_OK;
+    k_debug_sincos<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(th, n, sn, cs);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -794,7 +798,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_hd = take(sizeof(double) * 8);
     size_t o_ih = take(sizeof(int) * 4);
     size_t o_po = take(sizeof(RobotPose));
-    size_t o_at = take(sizeof(double) * CRLK_ATAN_NK * (CRLK_ATAN_DEG + 1));
+    size_t o_at = take(sizeof(double) * CRLK_ATAN_SMEM_DOUBLES);
     size_t o_cl = take(d.use_clearance ? sizeof(float4) * CL_CAP : 0);
     size_t o_cn = take(sizeof(int) * 4);
     size_t o_sc = take(sizeof(double) * 16);
@@ -891,20 +895,38 @@ struct DwaResult {
     int near_tie;
 };
 
-// A runner-up within this many ulp of the winning cost is reported as a near tie (see
-// dwa_control_block): the bound covers the last-bit differences between libm implementations of
-// arctan2 / sin / cos (numpy's SIMD loops, glibc, this file's table-driven atan2), each <= 2 ulp
-// on a heading cost, propagated through the column normalisation.
-#ifndef CRLK_TIE_ULPS
-#define CRLK_TIE_ULPS 32
-#endif
-
 // get_clearance for one pose by one thread (used only when use_clearance = 1).
 __device__ __forceinline__ double clearance_thread(const EnvP &e, const ObsSet &os, double x, double y,
                                                    double th, double bound = CRLK_CLEARANCE_CAP)
 {
     return clearance_grid_thread(e, os, x, y, th, nullptr, nullptr, bound);
 }
+
+// The set of threads that runs one control step together.  GrpCta<T>: the whole CTA of T threads
+// (plain __syncthreads; everything folds at compile time).  GrpPart: `n` threads of a CTA (a
+// multiple of 32, warp aligned) that synchronise on their own named barrier, so that two parts of
+// one CTA can run two control steps side by side, or join into one part of twice the size
+// (k_extend_dwa_pair).
+template <int T> struct GrpCta {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int size() const { return T; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int sync_or(int p) const { return __syncthreads_or(p); }
+};
+struct GrpPart {
+    int t, n, bar;
+    __device__ __forceinline__ int tid() const { return t; }
+    __device__ __forceinline__ int size() const { return n; }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory"); }
+    __device__ __forceinline__ int sync_or(int p) const
+    {
+        int r;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\t"
+                     "selp.s32 %0, 1, 0, q;\n\t}"
+                     : "=r"(r) : "r"(p), "r"(bar), "r"(n) : "memory");
+        return r;
+    }
+};
 
 // DWA.control (dwa.py:45-86) by one CTA of DWA_THREADS threads.  `st` (5
 // doubles) and the goal must be block-uniform.  Every thread returns the result.
@@ -918,12 +940,12 @@ static __device__ __noinline__ void advance_state_general(const EnvP &e, const d
     robot_pose_setup(e, s[0], s[1], s[2], *pose);
 }
 
-template <int T, bool CLR, class Epi>
-__device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSet &os,
+template <class G, bool CLR, class Epi>
+__device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d, const ObsSet &os,
                                        const double *st, double gx, double gy,
                                        const DwaSmem &sm, Epi epilogue)
 {
-    const int tid = threadIdx.x;
+    const int tid = g.tid(), T = g.size();
     const int lane = tid & 31, warp = tid >> 5;
     const double dt = e.base_dt;
     // dynamic window over d.dt (dwa.py:46, differential_env.py:107-114) and the grid sizes: one
@@ -941,7 +963,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
     const int S = d.n_sub * d.n_outer, spos = sm.spos;
 
     PHASE_START();
-    __syncthreads();   // previous users of the shared tables are done; the header is visible
+    g.sync();   // previous users of the shared tables are done; the header is visible
     PHASE_MARK(0);
     const double v_hi = sm.hdr[0], v_lo = sm.hdr[1], w_lo = sm.hdr[3];
     const int nv = sm.ihdr[0], nw = sm.ihdr[1];
@@ -985,7 +1007,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             th = normalize_angle(th + cur * dt);
         }
         double sn, cs;
-        sincos(th, &sn, &cs);
+        crlk_sincos(th, &sn, &cs);
         sm.wcos[ks * d.nw_max + j] = cs;          // [sub-step][w command]: neighbouring rollouts, neighbouring banks
         sm.wsin[ks * d.nw_max + j] = sn;
         if ((ks + 1) % d.n_sub == 0) sm.wth[j * d.n_outer + (ks + 1) / d.n_sub - 1] = th;
@@ -1033,7 +1055,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         const float guess = (float)((prev > 0.0 && prev < 20.0) ? prev + 0.25 : 1.0);
         const float ra = guess * 1.0001f + e.rc + 2.0f * CRLK_CULL_MARGIN;   // covers every obstacle closer than `guess` to the footprint
         gather(ra);
-        __syncthreads();
+        g.sync();
         const int n0 = sm.cl_n[0];
         double mine = CRLK_CLEARANCE_CAP;
         if (n0 <= CL_CAP) {
@@ -1049,24 +1071,24 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         }
         mine = warp_min_d(mine);
         if (lane == 0) sm.red_v[warp] = mine;
-        __syncthreads();
+        g.sync();
         double c_l = (lane < T / 32) ? sm.red_v[lane] : CRLK_CLEARANCE_CAP;
         c_l = warp_min_d(c_l);
         // an obstacle outside the gathered radius is farther than ra - rc from the footprint
         const bool settled = n0 <= CL_CAP && (c_l < 0.0 || c_l <= (double)(ra - e.rc) - 4.0 * CRLK_CULL_MARGIN);
         if (!settled) {
             if (tid == T - 1) sm.hdr[4] = clearance_thread(e, os, st[0], st[1], st[2]);
-            __syncthreads();
+            g.sync();
             c_l = sm.hdr[4];
         }
         clr0 = pymax(c_l, 0.001);
         const float rl = (float)fmin(clr0, CRLK_CLEARANCE_CAP) * 1.0001f + e.rc + reach + 2.0f * CRLK_CULL_MARGIN;
-        __syncthreads();                                          // everyone has read cl_n / the first list
+        g.sync();                                          // everyone has read cl_n / the first list
         if (tid == 0) { sm.cl_n[0] = 0; sm.hdr[5] = c_l; }
-        __syncthreads();
+        g.sync();
         gather(rl);
     }
-    __syncthreads();
+    g.sync();
     PHASE_MARK(1);
     const int cl_n = CLR ? sm.cl_n[0] : 0;
 #ifdef CRLK_PHASE_TIMING
@@ -1156,7 +1178,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             sm.c1[r] = 1.0 / min_dis;
         }
     }
-    __syncthreads();
+    g.sync();
     PHASE_MARK(2);
 
     // Column sums exactly as np.sum forms them (dwa.py:76-78; see "numpy's pairwise summation" in
@@ -1217,7 +1239,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
             if (k8 == 0 && g < M) { sm.node[g] = a0; sm.node[128 + g] = a1; sm.node[256 + g] = a2; }
         }
     }
-    __syncthreads();
+    g.sync();
     double S0, S1, S2;
     {
         // the complete top of the tree: every warp reduces the M node values itself (no third barrier)
@@ -1292,7 +1314,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         merge(ob, oi, os2, osi);
     }
     if (lane == 0) { sm.red3_v[warp] = best; sm.red3_s[warp] = second; sm.red_i[warp] = bi; sm.red_i[32 + warp] = si; }
-    __syncthreads();
+    g.sync();
     PHASE_MARK(3);
     if (tid == 0) {
         best = sm.red3_v[0]; second = sm.red3_s[0]; bi = sm.red_i[0]; si = sm.red_i[32];
@@ -1303,17 +1325,39 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
         sm.scal[5] = arange_at(w_lo, w1, wd, j);
         sm.scal[6] = best;
         sm.iscal[1] = ix;
-        // Near-tie report.  The costs above are the reference's arithmetic applied to THIS build's
-        // heading costs; numpy's SIMD arctan2, glibc's and the table-driven one here differ by an ulp
-        // or two, which moves a cost by a few ulp.  A runner-up within CRLK_TIE_ULPS ulp of the
-        // winner could therefore win in the reference -- unless it is the same rollout twice (grid
-        // values beyond the window are clamped to the same command: identical inputs, identical
-        // cost in any arithmetic, and np.argmin keeps the first, as here).
+        // Near-tie report.  The costs above are the reference's arithmetic applied to this build's
+        // heading costs, which are the C library's bits except where the library itself misrounds
+        // (7.5e-4 of its atan2 results, one ulp; crlk_crmath.h).  Such a last bit moves the heading
+        // column's sum by an ulp in about one control step in a hundred, and with it every cost.  A
+        // decision is reported when that could change it:
+        //   * winner and runner-up have DIFFERENT heading costs and lie within 8 ulp of each other
+        //     (their own last bits could decide); or
+        //   * they share the heading cost bit for bit (the rollout grid's last velocity row repeats
+        //     the one before it whenever the window ends at max_v: same first step, same atan2
+        //     arguments, speed terms one ulp apart) and the winner changes when the column sum moves
+        //     by one ulp either way (a rounding that merges the two costs, or stops merging them,
+        //     hands the decision to the first index).
+        // Identical rollouts (same heading AND speed cost: commands clamped to the same value) are
+        // never near ties: np.argmin and this kernel both keep the first.
         int tie = 0;
-        if (si != 0x7fffffff && second - best <= (double)CRLK_TIE_ULPS * 2.220446049250313e-16 * fabs(best)) {
+        if (si != 0x7fffffff && second - best <= 8.0 * 2.220446049250313e-16 * fabs(best)) {
             const int sx = si & 0xffff, s_i = si >> 16;
-            const bool same = sm.c0[sx] == sm.c0[ix] && sm.c2[s_i] == sm.c2[i] && (!CLR || sm.c1[sx] == sm.c1[ix]);
-            tie = same ? 0 : 1;
+            const bool same_c0 = sm.c0[sx] == sm.c0[ix] && (!CLR || sm.c1[sx] == sm.c1[ix]);
+            if (!same_c0) tie = 1;
+            else if (sm.c2[s_i] != sm.c2[i]) {
+                for (int dir = -1; dir <= 1 && !tie; dir += 2) {
+                    const double S0p = __longlong_as_double(__double_as_longlong(S0) + dir);
+                    auto cost_p = [&](int r, int iv) {
+                        const double c0n = (S0p != 0.0) ? sm.c0[r] / S0p : sm.c0[r];
+                        const double c1n = CLR ? (z1 ? sm.c1[r] / S1 : sm.c1[r]) : c1n_const;
+                        const double c2n = z2 ? sm.c2[iv] / S2 : sm.c2[iv];
+                        return (d.g_goal * c0n + d.g_ob * c1n) + d.g_speed * c2n;
+                    };
+                    const double cw = cost_p(ix, i), cr = cost_p(sx, s_i);
+                    const bool winner_stays = cw < cr || (cw == cr && ix < sx);
+                    if (!winner_stays) tie = 1;
+                }
+            }
         }
         sm.iscal[2] = tie;
         PHASE_MARK(4);
@@ -1337,7 +1381,7 @@ __device__ DwaResult dwa_control_block(const EnvP &e, const DwaP &d, const ObsSe
                  sm.wsin[(d.n_sub - 1) * d.nw_max + j]);
     }
     PHASE_MARK(9);
-    __syncthreads();
+    g.sync();
     PHASE_MARK(7);
     DwaResult res;
     res.v = sm.scal[4]; res.w = sm.scal[5]; res.cost = sm.scal[6];
@@ -1356,15 +1400,15 @@ k_dwa_control(EnvP e, DwaP d, ObsSet os,
     DwaSmem sm;
     dwa_carve(d, smem_raw, &sm);
     __shared__ double s_state[5];
-    load_atan_table(sm.atab);
+    load_atan_table(sm.atab, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) sm.hdr[5] = -1.0;                       // no previous control step yet
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 5) s_state[threadIdx.x] = states[5 * (size_t)b + threadIdx.x];
         __syncthreads();
         double gx = goals[(size_t)goal_stride * b], gy = goals[(size_t)goal_stride * b + 1];
-        DwaResult r = dwa_control_block<T, CLR>(e, d, os, s_state, gx, gy, sm,
-                                                [](double, double, int, const double *, double, double) {});
+        DwaResult r = dwa_control_block<GrpCta<T>, CLR>(GrpCta<T>(), e, d, os, s_state, gx, gy, sm,
+                                                        [](double, double, int, const double *, double, double) {});
         if (threadIdx.x == 0) {
             opt_v[2 * (size_t)b] = r.v;
             opt_v[2 * (size_t)b + 1] = r.w;
@@ -1452,9 +1496,10 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
 // thread screens its share of the grid cells around the pose in FP32 and tests its survivors
 // exactly in FP64.  Returns bit0 = collision, bit1 = the decision is within 1e-6 of the 0.05
 // threshold (reported, not claimed).  Ends with block-wide barriers.
-__device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose *gp)
+template <class G>
+__device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, const RobotPose *gp)
 {
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = grp.tid(), T = grp.size();
     const RobotPose g = *gp;
     const double x = g.x, y = g.y;
     float px = (float)x, py = (float)y;
@@ -1474,10 +1519,10 @@ __device__ int collision_block(const EnvP &e, const ObsSet &os, const RobotPose 
     });
     // barrier-fused reductions; most poses are not within the threshold band of any obstacle's
     // bounding circle, so no thread ran an exact test and one barrier settles it
-    if (!__syncthreads_or(coll | definite | marginal)) return 0;
-    int any_coll = __syncthreads_or(coll);
-    int any_def = __syncthreads_or(definite);
-    int any_mar = __syncthreads_or(marginal);
+    if (!grp.sync_or(coll | definite | marginal)) return 0;
+    int any_coll = grp.sync_or(coll);
+    int any_def = grp.sync_or(definite);
+    int any_mar = grp.sync_or(marginal);
     return (any_coll ? 1 : 0) | ((any_mar && !any_def) ? 2 : 0);
 }
 
@@ -1493,8 +1538,8 @@ struct ExtResult {
 // step) is called by EVERY thread (uniformly) when a node is emitted at `step`
 // with the node's state in s_state; it returns false to stop the extension
 // (capacity exhausted).  Every thread returns the same result.
-template <int T, bool CLR, class OnNode>
-__device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &x, const ObsSet &os,
+template <class G, bool CLR, class OnNode>
+__device__ ExtResult extend_dwa_block(const G &g, const EnvP &e, const DwaP &d, const ExtP &x, const ObsSet &os,
                                       const DwaSmem &sm, double *s_state, double gx,
                                       double gy, double *path, int *ctrl_idx, OnNode on_node)
 {
@@ -1504,7 +1549,7 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
         // rrt.py:116-118: control, then thread 0 advances the state inside the control block's
         // closing section: s_state (nobody reads it any more) and the footprint of the new state
         // for the validity test, both visible after the block's closing barrier
-        DwaResult r = dwa_control_block<T, CLR>(e, d, os, s_state, gx, gy, sm,
+        DwaResult r = dwa_control_block<G, CLR>(g, e, d, os, s_state, gx, gy, sm,
             [&](double cv, double cw, int ix, const double *row1, double cs1, double sn1) {
                 double s[5];
                 if (x.n_sub_step == d.n_sub) {
@@ -1530,7 +1575,7 @@ __device__ ExtResult extend_dwa_block(const EnvP &e, const DwaP &d, const ExtP &
         res.steps = k;
         // rrt.py:121: valid_state_check on the new state
         PHASE_START();
-        int col = collision_block(e, os, sm.pose);
+        int col = collision_block(g, e, os, sm.pose);
         PHASE_MARK(8);
         if (col & 2) res.flags |= 1;
         col &= 1;
@@ -1565,7 +1610,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
     __shared__ int s_q;
     const int per = x.n_max_extend / x.n_tree + 1;
     const int tid = threadIdx.x;
-    load_atan_table(sm.atab);
+    load_atan_table(sm.atab, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) sm.hdr[5] = -1.0;                       // no previous control step yet
     for (;;) {
         // dynamic work distribution: extensions finish after very different step counts
@@ -1587,7 +1632,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
         if (tid < 5) s_state[tid] = from_states[5 * (size_t)q + tid];
         __syncthreads();
         const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
-        ExtResult r = extend_dwa_block<T, CLR>(e, d, x, os, sm, s_state, gx, gy,
+        ExtResult r = extend_dwa_block<GrpCta<T>, CLR>(GrpCta<T>(), e, d, x, os, sm, s_state, gx, gy,
                                        path + (size_t)q * x.n_max_extend * 5,
                                        ctrl_idx ? ctrl_idx + (size_t)q * x.n_max_extend : nullptr,
                                        [&](int kn, int step) {
@@ -1603,6 +1648,183 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
                 atomicAdd(&stats[2], r.rolls);                         // rollouts scored
             }
         }
+    }
+}
+
+// ---- the same extensions by CTAs of two 256-thread parts that can join ------------------------
+//
+// A batch of extensions ends when its longest one does, and an extension is a chain of up to
+// n_max_extend control steps that only one group of threads can walk.  One part (256 threads) per
+// extension gives the best throughput while there is work for every part; the latency of a control
+// step, though, is nearly halved when 512 threads share its rollouts, cost pass and column sums.
+// So every SM runs ONE CTA of two parts:
+//   * the CTA's first work item -- with the longest-first order, one of the batch's longest
+//     extensions -- is run by both parts together from its first step;
+//   * afterwards each part pulls its own items from the queue;
+//   * a part that finds the queue empty offers itself to its neighbour (s_idle) and waits on the
+//     join barrier; the neighbour sees the offer in the closing section of its current control step
+//     and takes it at the top of the next one: the rest of that extension runs on 512 threads.
+// Results do not depend on which threads computed them: the rollout grid is strided over whatever
+// thread count the group has, and every reduction is order-exact (first minimum; numpy's pairwise
+// sum tree).
+#define PAIR_PART 256
+#define PAIR_BAR_JOIN 3
+
+struct PairXchg {
+    double gx, gy;
+    unsigned long long rolls;
+    int k, nn, status, steps, flags, q, worker, done;
+};
+
+template <bool CLR>
+__global__ void __launch_bounds__(2 * PAIR_PART, 1)
+k_extend_dwa_pair(EnvP e, DwaP d, ExtP x, ObsSet os,
+                  const double *__restrict__ from_states, const double *__restrict__ targets, int Q,
+                  double *path, int *n_steps, int *status, int *node_step, int *n_nodes, int *ctrl_idx,
+                  uint8_t *flags, const uint8_t *__restrict__ active, int *work_counter,
+                  unsigned long long *stats, const int *__restrict__ order, int part_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_state[2][5];
+    __shared__ int s_q[2], s_dec[2], s_tmp[2];
+    __shared__ int s_idle;                 // 0, or 1 + the part that waits on the join barrier
+    __shared__ PairXchg s_x;
+    const int part = threadIdx.x / PAIR_PART, ltid = threadIdx.x - part * PAIR_PART;
+    const int per = x.n_max_extend / x.n_tree + 1;
+    DwaSmem sm;
+    dwa_carve(d, smem_raw + (size_t)part * part_bytes, &sm);
+    load_atan_table(sm.atab, ltid, PAIR_PART);
+    if (ltid == 0) { sm.hdr[5] = -1.0; s_dec[part] = 0; }
+    if (threadIdx.x == 0) { s_idle = 0; s_x.done = 0; }
+    __syncthreads();
+
+    GrpPart g{ltid, PAIR_PART, 1 + part};
+    int mine = part;                       // whose tables / state this thread currently works on
+    bool first = true, dry = false;
+    for (;;) {
+        int q, k0 = 1;
+        double gx, gy;
+        ExtResult res;
+        res.nn = 0; res.status = CRLK_EXT_TIMEOUT; res.steps = 0; res.flags = 0; res.rolls = 0;
+        bool skip = false;
+        if (first) {
+            // the CTA's first item: both parts, on part 0's tables
+            first = false;
+            if (threadIdx.x == 0) {
+                const int w = atomicAdd(work_counter, 1);
+                s_q[0] = (w < Q && order) ? order[w] : w;
+            }
+            __syncthreads();
+            q = s_q[0];
+            if (q >= Q) return;
+            g = GrpPart{(int)threadIdx.x, 2 * PAIR_PART, 0};
+            mine = 0;
+            dwa_carve(d, smem_raw, &sm);
+        } else {
+            if (g.n != PAIR_PART) {        // back to two parts after a joined item
+                g = GrpPart{ltid, PAIR_PART, 1 + part};
+                mine = part;
+                dwa_carve(d, smem_raw + (size_t)part * part_bytes, &sm);
+                __syncthreads();
+            }
+            g.sync();
+            if (ltid == 0) {
+                const int w = atomicAdd(work_counter, 1);
+                s_q[part] = (w < Q && order) ? order[w] : w;
+            }
+            g.sync();
+            q = s_q[part];
+            if (q >= Q) {
+                // queue empty: offer this part to the neighbour, or -- if the neighbour already
+                // waits -- release it; either way the CTA is finished once the barrier opens
+                if (ltid == 0) s_tmp[part] = atomicCAS(&s_idle, 0, 1 + part);
+                g.sync();
+                const bool helper = s_tmp[part] == 0;
+                if (!helper && ltid == 0) { s_x.done = 1; __threadfence_block(); }
+                asm volatile("bar.sync %0, %1;" ::"r"(PAIR_BAR_JOIN), "r"(2 * PAIR_PART) : "memory");
+                if (!helper || s_x.done) return;
+                // joined: continue the neighbour's extension from its next control step
+                mine = s_x.worker;
+                dwa_carve(d, smem_raw + (size_t)mine * part_bytes, &sm);
+                g = GrpPart{PAIR_PART + ltid, 2 * PAIR_PART, 0};
+                q = s_x.q; k0 = s_x.k; gx = s_x.gx; gy = s_x.gy;
+                res.nn = s_x.nn; res.status = s_x.status; res.steps = s_x.steps; res.flags = s_x.flags;
+                res.rolls = s_x.rolls;
+                dry = true;
+                skip = true;               // state and targets are already in place
+            }
+        }
+        double *st = s_state[mine];
+        if (!skip) {
+            if (active && !active[q]) {
+                if (g.tid() == 0) {
+                    n_steps[q] = 0; status[q] = CRLK_EXT_TIMEOUT; n_nodes[q] = 0;
+                    if (flags) flags[q] = 0;
+                }
+                continue;
+            }
+            if (g.tid() < 5) st[g.tid()] = from_states[5 * (size_t)q + g.tid()];
+            g.sync();
+            gx = targets[5 * (size_t)q]; gy = targets[5 * (size_t)q + 1];
+        }
+        double *qpath = path + (size_t)q * x.n_max_extend * 5;
+        int *qctrl = ctrl_idx ? ctrl_idx + (size_t)q * x.n_max_extend : nullptr;
+        // RRT.steer (rrt.py:99-135), as extend_dwa_block, with the join test at the top of a step
+        for (int k = k0; k <= x.n_max_extend; k++) {
+            if (g.n == PAIR_PART && s_dec[mine]) {
+                if (ltid == 0) {
+                    s_x.gx = gx; s_x.gy = gy; s_x.rolls = res.rolls; s_x.k = k; s_x.nn = res.nn;
+                    s_x.status = res.status; s_x.steps = res.steps; s_x.flags = res.flags; s_x.q = q;
+                    s_x.worker = mine; s_x.done = 0;
+                    __threadfence_block();
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(PAIR_BAR_JOIN), "r"(2 * PAIR_PART) : "memory");
+                g = GrpPart{ltid, 2 * PAIR_PART, 0};
+                dry = true;
+            }
+            const bool watch = g.n == PAIR_PART;
+            DwaResult r = dwa_control_block<GrpPart, CLR>(g, e, d, os, st, gx, gy, sm,
+                [&](double cv, double cw, int ix, const double *row1, double cs1, double sn1) {
+                    double s[5];
+                    if (x.n_sub_step == d.n_sub) {
+                        for (int c = 0; c < 5; c++) s[c] = row1[c];
+                        robot_pose_from_cs(e, s[0], s[1], cs1, sn1, *sm.pose);
+                    } else {
+                        advance_state_general(e, st, cv, cw, x.n_sub_step, s, sm.pose);
+                    }
+                    for (int c = 0; c < 5; c++) st[c] = s[c];
+                    for (int c = 0; c < 5; c++) qpath[(size_t)(k - 1) * 5 + c] = s[c];
+                    if (qctrl) qctrl[k - 1] = ix;
+                    if (watch) s_dec[mine] = *(volatile int *)&s_idle;     // an offer from the other part?
+                });
+            if (r.R == 0) { res.status = CRLK_EXT_INVALID; res.flags |= 8; break; }
+            res.flags |= r.near_tie ? 2 : 0;
+            res.rolls += (unsigned long long)r.R;
+            res.steps = k;
+            int col = collision_block(g, e, os, sm.pose);                              // rrt.py:121
+            if (col & 2) res.flags |= 1;
+            if (col & 1) { res.status = CRLK_EXT_COLLISION; break; }
+            double ddx = st[0] - gx, ddy = st[1] - gy;
+            double dist = sqrt(fma(ddy, ddy, ddx * ddx));                            // rrt.py:124
+            if (dist <= x.reach_radius) {
+                if (g.tid() == 0) node_step[(size_t)q * per + res.nn] = k;
+                res.nn++; res.status = CRLK_EXT_REACHED; break;
+            }
+            if (k % x.n_tree == 0) {                                                 // rrt.py:128
+                if (g.tid() == 0) node_step[(size_t)q * per + res.nn] = k;
+                res.nn++;
+            }
+        }
+        if (g.tid() == 0) {
+            n_steps[q] = res.steps; status[q] = res.status; n_nodes[q] = res.nn;
+            if (flags) flags[q] = (uint8_t)res.flags;
+            if (stats) {
+                atomicAdd(&stats[0], 1ull);
+                atomicAdd(&stats[1], (unsigned long long)res.steps);
+                atomicAdd(&stats[2], res.rolls);
+            }
+        }
+        if (dry) return;                   // joined because the queue was empty: nothing left to pull
     }
 }
 
@@ -1728,13 +1950,36 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
                  "NULL array");
     size_t smem = crlk_dwa_smem_bytes(d);
     const bool wide = dwa_use_wide(Q);
+    int dev = env->device, sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const char *pair_env = getenv("CRLK_DWA_PAIR");
+    const size_t part_bytes = (smem + 127) & ~(size_t)127;
+    if (!wide && pair_env && atoi(pair_env) != 0 && 2 * part_bytes <= 200 * 1024) {
+        // more work items than SMs: CTAs of two joinable parts, longest extensions first
+        auto pk = d.use_clearance ? k_extend_dwa_pair<true> : k_extend_dwa_pair<false>;
+        rc = set_smem_attr((const void *)pk, 2 * part_bytes);
+        if (rc) return rc;
+        int grid = sms < Q ? sms : Q;
+        int *counter = nullptr, *order = nullptr;
+        rc = get_work_counter(dev, &counter, (cudaStream_t)stream);
+        if (rc) return rc;
+        rc = get_order_slice(dev, Q, &order);
+        if (rc) return rc;
+        if (order) {
+            k_lpt_order<<<1, 1024, 0, (cudaStream_t)stream>>>(from_states, targets, active, Q, order);
+            CRLK_LAUNCH_CHECK();
+        }
+        pk<<<grid, 2 * PAIR_PART, 2 * part_bytes, (cudaStream_t)stream>>>(
+            env->p, d, x, env->os, from_states, targets, Q, path, n_steps, status, node_step,
+            n_nodes, ctrl_idx, flags, active, counter, (unsigned long long *)stats, order, (int)part_bytes);
+        CRLK_LAUNCH_CHECK();
+        return CRLK_OK;
+    }
     auto kern = d.use_clearance ? (wide ? k_extend_dwa<DWA_WIDE_THREADS, 1, true> : k_extend_dwa<DWA_THREADS, DWA_MIN_BLOCKS, true>)
                                 : (wide ? k_extend_dwa<DWA_WIDE_THREADS, 1, false> : k_extend_dwa<DWA_THREADS, DWA_MIN_BLOCKS, false>);
     const int threads = wide ? DWA_WIDE_THREADS : DWA_THREADS;
     rc = set_smem_attr((const void *)kern, smem);
     if (rc) return rc;
-    int dev = env->device, sms = 148, per_sm = 1;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     CRLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sms * per_sm;
@@ -1870,7 +2115,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
     __shared__ double s_state[5];
     __shared__ int s_q;
     const int tid = threadIdx.x;
-    load_atan_table(sm.atab);
+    load_atan_table(sm.atab, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) sm.hdr[5] = -1.0;                       // no previous control step yet
     for (;;) {
         __syncthreads();
@@ -1895,7 +2140,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
             __syncthreads();
             double *prow = f.pool ? f.pool + ((size_t)f.pool_cap * q + pool_used) * 5 : nullptr;
             int prev_step = 0;
-            ExtResult r = extend_dwa_block<T, CLR>(e, d, x, os, sm, s_state, tx, ty, prow, nullptr,
+            ExtResult r = extend_dwa_block<GrpCta<T>, CLR>(GrpCta<T>(), e, d, x, os, sm, s_state, tx, ty, prow, nullptr,
                 [&](int kn, int step) {
                     if (n >= f.stride) { over = true; return false; }
                     if (tid < 5) f.states[(tb + n) * 5 + tid] = s_state[tid];
@@ -1937,7 +2182,7 @@ k_plan_dwa(EnvP e, DwaP d, ExtP x, ObsSet os, CrlkForestView f, PlanP pp,
             cur++;
             if (tid == 0) robot_pose_setup(e, sx, sy, sth, *sm.pose);
             __syncthreads();
-            int col = collision_block(e, os, sm.pose);                                // rrt.py:66
+            int col = collision_block(GrpCta<T>(), e, os, sm.pose);                   // rrt.py:66
             if (col & 2) fl |= 1;
             if (col & 1) continue;
             int idx;

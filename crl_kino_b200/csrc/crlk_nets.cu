@@ -512,7 +512,7 @@ k_estimator_nodes(ObsGrid og, ObsSet os, const float *__restrict__ params, const
     const double *st = states + ((size_t)stride * q + nidx) * 5;
     const double x = st[0], y = st[1];
     double sn, cs;
-    sincos(st[2], &sn, &cs);
+    crlk_sincos(st[2], &sn, &cs);
     bool nearp = false;
     for (int p = threadIdx.x; p < OBS_NPTS; p += CNN_THREADS) {
         int ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;

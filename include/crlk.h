@@ -132,15 +132,18 @@ int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals
  *   opt_cost  dev f64[B]   (nullable)
  *   opt_traj  dev f64[B x traj_rows x 5] (nullable); traj_rows from crlk_dwa_traj_rows
  *   n_rollouts dev i32[B]  (nullable) realised grid size nv * nw
- *   near_tie  dev u8[B]    (nullable) a DIFFERENT rollout's cost lies within 32 ulp of the winner's.
- * Costs are formed in the reference's own arithmetic: each column summed in numpy's pairwise order
- * (np.sum, dwa.py:76-78), every entry divided by its column sum (correctly rounded), then
- * (gain0 * c0 + gain1 * c1) + gain2 * c2 with each operation rounded once (dwa.py:79-81), first
- * minimum (np.argmin, :82).  Given the same heading costs the result is therefore the reference's,
- * bit for bit.  The heading costs themselves come from arctan2 / sin / cos, whose last bit differs
- * between numpy's SIMD loops, glibc and this library (<= 2 ulp each); near_tie marks exactly the
- * decisions that such a last-bit difference could flip.  Identical rollouts (grid values beyond the
- * window clamp to the same command) are not near ties: np.argmin and this kernel both keep the first.
+ *   near_tie  dev u8[B]    (nullable) the decision hangs on a last bit the C library may round differently (below).
+ * Costs are formed in the reference's own arithmetic: heading costs from a correctly rounded atan2 on
+ * positions integrated with correctly rounded sin / cos (the C library calls behind np.arctan2 /
+ * math.sin / math.cos on Python scalars, dwa.py:58, differential_env.py:98-99), each column summed in
+ * numpy's pairwise order (np.sum, dwa.py:76-78), every entry divided by its column sum (correctly
+ * rounded), then (gain0 * c0 + gain1 * c1) + gain2 * c2 with each operation rounded once
+ * (dwa.py:79-81), first minimum (np.argmin, :82).  The result is the reference's bit for bit, except
+ * where the C library itself misrounds (7.5e-4 of its atan2 results, by one ulp).  near_tie marks the
+ * decisions such a bit could change: a runner-up with a different heading cost within 8 ulp of the
+ * winner, or one with the same heading cost that overtakes the winner when the heading column's sum
+ * moves by one ulp.  Identical rollouts (grid values beyond the window clamp to the same command) are
+ * not near ties: np.argmin and this kernel both keep the first.
  * An empty grid (v or omega outside the limits by more than acc * dt; the reference raises on the
  * empty cost table) gives opt_idx = -1, n_rollouts = 0 and NaN opt_v / opt_cost / opt_traj. */
 int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, const double *states,
@@ -335,8 +338,12 @@ int crlk_gym_step(const CrlkEnv *env, double *states, const double *goals, int32
                   uint8_t *near_boundary, void *stream);
 
 /* Test hook: the atan2 of the rollout scoring loop (dwa.py:58 `np.arctan2`), evaluated for n
- * argument pairs; y, x, out dev f64[n].  The kernels use a table-driven atan2 (<= 1.5 ulp). */
+ * argument pairs; y, x, out dev f64[n].  Correctly rounded (double-double evaluation with a rounding
+ * test, csrc/crlk_crmath.h): the bits the C library returns, up to the library's own rare misroundings. */
 int crlk_debug_atan2(const double *y, const double *x, int32_t n, double *out, void *stream);
+/* Test hook: sin / cos as the heading chains and footprints evaluate them (math.sin / math.cos of
+ * differential_env.py:98-99; correctly rounded for |th| <= 3.15); th, sn, cs dev f64[n]. */
+int crlk_debug_sincos(const double *th, int32_t n, double *sn, double *cs, void *stream);
 /* Test hook: fast[i] = the correctly rounded quotient a[i] / b[i] as the cost normalisation forms it
  * (one multiply + two fused corrections on y = 1 / b), exact[i] = a[i] / b[i] by the division operator. */
 int crlk_debug_div(const double *a, const double *b, int32_t n, double *fast, double *exact, void *stream);

@@ -16,7 +16,7 @@ cand = free_states(clr, rng, 4000, 2.5); cand[:, 3:] = 0
 tg = cand.copy(); ang = rng.uniform(-np.pi, np.pi, len(cand)); tg[:, 0] += 15*np.cos(ang); tg[:, 1] += 15*np.sin(ang)
 names = ["wait-prev", "tables", "rollouts", "costs+argmin", "f:merge+tie", "column sums", "f:row1", "f:closing-barrier", "collision", "f:epilogue"]
 raw = ctypes.CDLL(lib()._name)
-for Q in ((1, 296) if os.environ.get('USE_CLEARANCE') else (1, 444, 1776)):
+for Q in ((1, 296) if os.environ.get('USE_CLEARANCE') else tuple(int(v) for v in os.environ.get('PHASE_Q', '1,444,1776').split(','))):
     f, g = ops.as_dev(cand[:Q]), ops.as_dev(tg[:Q])
     buf = (ctypes.c_ulonglong * 16)()
     ops.extend_dwa(env.handle, dp, xp, f, g); torch.cuda.synchronize()
