@@ -754,7 +754,7 @@ struct DwaSmem {
     double *wcos, *wsin, *wth, *wom;
     double *red_v, *red_s;            // [32] column-sum partials per warp (heading, speed); nearest_block scratch
     int *red_i;                       // [64] index of the per-warp minimum, then of the per-warp runner-up
-    double *node;                     // [3][128] level-Dmin node sums of the three cost columns (pairwise tree)
+    double *node;                     // [3][256] leaf sums of the three cost columns (pairwise tree)
     double *red2_v;                   // [32] third column-sum partial per warp
     double *red3_v, *red3_s;          // [32] minimum / runner-up per warp
     double *hdr;                      // [8]  v_hi v_lo w_hi w_lo of the current window
@@ -792,7 +792,7 @@ __host__ __device__ inline size_t dwa_carve(const DwaP &d, unsigned char *base, 
     size_t o_rv = take(sizeof(double) * 32);
     size_t o_rs = take(sizeof(double) * 32);
     size_t o_ri = take(sizeof(int) * 64);
-    size_t o_nd = take(sizeof(double) * 384);
+    size_t o_nd = take(sizeof(double) * 768);
     size_t o_r2 = take(sizeof(double) * 32);
     size_t o_r3 = take(sizeof(double) * 64);
     size_t o_hd = take(sizeof(double) * 8);
@@ -1126,6 +1126,31 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
         double c0 = fabs(ang - sm.wth[j * d.n_outer]);
         return pymin(c0, CRLK_TWO_PI - c0);
     };
+    // Column sums are formed exactly as np.sum forms them (dwa.py:76-78; "numpy's pairwise
+    // summation" in crlk_device.cuh): the tree's leaves (<= 128 elements) are added by eight strided
+    // accumulators -- eight lanes here, lane k is numpy's r[k] -- and combined pairwise above.
+    // Level Dmin of the tree is complete; its nodes are leaves or split once more into two leaves.
+    // A "unit" is one leaf: unit u belongs to node u >> ush (ush = 1 when nodes split).
+    const int Dmin = pw_min_depth(R), M = 1 << Dmin;
+    int nmax = R;
+    for (int b = 0; b < Dmin; b++) nmax -= pw_split(nmax);
+    const int ush = nmax > 128 ? 1 : 0, U = M << ush;
+    const int k8 = tid & 7, ngroups = T >> 3;
+    const float inv_nw = 1.0f / (float)nw;
+    // (offset, length) of unit u's leaf; length 0 past the end or for the absent half of an unsplit node
+    auto unit_span = [&](int u, int &off, int &n) {
+        const int gnode = u >> ush;
+        off = 0; n = (u < U) ? R : 0;
+        for (int b = Dmin - 1; b >= 0 && n > 0; b--) {
+            const int n2 = pw_split(n);
+            if ((gnode >> b) & 1) { off += n2; n -= n2; } else n = n2;
+        }
+        if (ush) {
+            const bool split = n > 128;
+            const int n2 = split ? pw_split(n) : n;
+            if (u & 1) { off += n2; n = split ? n - n2 : 0; } else n = n2;
+        }
+    };
     if (!CLR) {
         // two independent rollouts per iteration: the FP64 dependency chains overlap
         int r = tid;
@@ -1180,20 +1205,17 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
     }
     g.sync();
     PHASE_MARK(2);
-
-    // Column sums exactly as np.sum forms them (dwa.py:76-78; see "numpy's pairwise summation" in
-    // crlk_device.cuh).  Eight lanes own one node of tree level Dmin: a leaf of <= 128 elements, or
-    // a node one split above two leaves.  Lane k is numpy's accumulator r[k].  The speed column
-    // v_hi - v_last repeats nw times per v command (dwa.py:72): element r reads c2[r / nw].
-    const int Dmin = pw_min_depth(R), M = 1 << Dmin;
     {
-        const int k8 = tid & 7;
-        const float inv_nw = 1.0f / (float)nw;
-        auto leaf = [&](int off, int n, double &a0, double &a1, double &a2) {
-            // sum of elements [off, off + n), n <= 128, of the three columns
-            double r0 = 0.0, r1 = 0.0, r2 = 0.0;                                   // 0.0 + a[k] == a[k]: r[k] = a[k]
+        // the summation pass over the stored columns; the speed column v_hi - v_last repeats nw times
+        // per v command (dwa.py:72): element r reads c2[r / nw]
+        for (int u0 = 0; u0 < U; u0 += ngroups) {             // warp-uniform trip count
+            const int u = u0 + (tid >> 3);
+            int off, n;
+            unit_span(u, off, n);
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
             const int n8 = n - (n & 7);
             if (n >= 8) {
+#pragma unroll 4
                 for (int i = k8; i < n8; i += 8) {
                     const int r = off + i;
                     const int iv = __float2int_rd(((float)r + 0.5f) * inv_nw);   // r / nw, exact for r <= 16384
@@ -1216,47 +1238,30 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
                 r1 += CLR ? sm.c1[r] : (1.0 / 100.0);
                 r2 += sm.c2[iv];
             }
-            a0 = r0; a1 = r1; a2 = r2;
-        };
-        const int ngroups_pass = T >> 3;
-        for (int g0 = 0; g0 < M; g0 += ngroups_pass) {                             // warp-uniform trip count
-            const int g = g0 + (tid >> 3);
-            int off = 0, n = (g < M) ? R : 0;
-            for (int b = Dmin - 1; b >= 0 && n > 0; b--) {
-                const int n2 = pw_split(n);
-                if ((g >> b) & 1) { off += n2; n -= n2; } else n = n2;
-            }
-            double a0, a1, a2;
-            // the split decision is uniform over the eight lanes of a group; the two branches run the
-            // same shuffle sequence per leaf, so a warp whose groups disagree executes leaf() twice
-            // with one side masked to n = 0
-            const bool split = n > 128;
-            const int n2 = split ? pw_split(n) : n;
-            leaf(off, n2, a0, a1, a2);
-            double b0, b1, b2;
-            leaf(off + n2, split ? n - n2 : 0, b0, b1, b2);
-            if (split) { a0 += b0; a1 += b1; a2 += b2; }
-            if (k8 == 0 && g < M) { sm.node[g] = a0; sm.node[128 + g] = a1; sm.node[256 + g] = a2; }
+            if (k8 == 0 && u < U) { sm.node[u] = r0; sm.node[256 + u] = r1; sm.node[512 + u] = r2; }
         }
     }
     g.sync();
     double S0, S1, S2;
     {
-        // the complete top of the tree: every warp reduces the M node values itself (no third barrier)
+        // the complete top of the tree: every warp reduces the M node values itself (no third barrier).
+        // Node g = its leaf, or the sum of its two leaves (an absent second leaf contributed 0.0).
+        auto nodeval = [&](const double *a, int gn) { return ush ? a[2 * gn] + a[2 * gn + 1] : a[gn]; };
         double t0, t1, t2;
         int steps;
         if (M >= 32) {
             const int per = M >> 5, base = lane * per;
             auto local = [&](const double *a) {
-                if (per == 1) return a[base];
-                if (per == 2) return a[base] + a[base + 1];
-                return (a[base] + a[base + 1]) + (a[base + 2] + a[base + 3]);
+                if (per == 1) return nodeval(a, base);
+                if (per == 2) return nodeval(a, base) + nodeval(a, base + 1);
+                return (nodeval(a, base) + nodeval(a, base + 1)) + (nodeval(a, base + 2) + nodeval(a, base + 3));
             };
-            t0 = local(sm.node); t1 = local(sm.node + 128); t2 = local(sm.node + 256);
+            t0 = local(sm.node); t1 = local(sm.node + 256); t2 = local(sm.node + 512);
             steps = 5;
         } else {
             const bool in = lane < M;
-            t0 = in ? sm.node[lane] : 0.0; t1 = in ? sm.node[128 + lane] : 0.0; t2 = in ? sm.node[256 + lane] : 0.0;
+            t0 = in ? nodeval(sm.node, lane) : 0.0; t1 = in ? nodeval(sm.node + 256, lane) : 0.0;
+            t2 = in ? nodeval(sm.node + 512, lane) : 0.0;
             steps = Dmin;
         }
         for (int sft = 0; sft < steps; sft++) {
@@ -1287,14 +1292,16 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
     // (minimum, its first index, runner-up, runner-up's index): the runner-up only feeds the near-tie report
     double best = CUDART_INF, second = CUDART_INF;
     int bi = 0x7fffffff, si = 0x7fffffff;   // bits 0-15 rollout index, bits 16-30 its v index (saves an integer division)
-    ri = tid / nw; rj = tid - ri * nw;
-    for (int r = tid; r < R; r += T) {
-        const int i = ri;
-        ri += di; rj += dj;
-        if (rj >= nw) { rj -= nw; ri++; }
-        const double c = cost_of(r, i);
-        if (c < best) { second = best; si = bi; best = c; bi = r | (i << 16); }       // r ascends: the first minimum stays
-        else if (c < second) { second = c; si = r | (i << 16); }
+    {
+        ri = tid / nw; rj = tid - ri * nw;
+        for (int r = tid; r < R; r += T) {
+            const int i = ri;
+            ri += di; rj += dj;
+            if (rj >= nw) { rj -= nw; ri++; }
+            const double c = cost_of(r, i);
+            if (c < best) { second = best; si = bi; best = c; bi = r | (i << 16); }       // r ascends: the first minimum stays
+            else if (c < second) { second = c; si = r | (i << 16); }
+        }
     }
     auto merge = [&](double ob, int oi, double os2, int osi) {
         // loser of the two minima, then the smallest of {loser, both runner-ups}
@@ -1345,15 +1352,16 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
             const bool same_c0 = sm.c0[sx] == sm.c0[ix] && (!CLR || sm.c1[sx] == sm.c1[ix]);
             if (!same_c0) tie = 1;
             else if (sm.c2[s_i] != sm.c2[i]) {
+                // same heading (and obstacle) cost: only the common first part of the two costs moves
+                const double c0 = sm.c0[ix];
+                const double c1n = CLR ? (z1 ? div_rn_y(sm.c1[ix], S1, y1) : sm.c1[ix]) : c1n_const;
+                const double k2w = d.g_speed * (z2 ? div_rn_y(sm.c2[i], S2, y2) : sm.c2[i]);
+                const double k2r = d.g_speed * (z2 ? div_rn_y(sm.c2[s_i], S2, y2) : sm.c2[s_i]);
                 for (int dir = -1; dir <= 1 && !tie; dir += 2) {
                     const double S0p = __longlong_as_double(__double_as_longlong(S0) + dir);
-                    auto cost_p = [&](int r, int iv) {
-                        const double c0n = (S0p != 0.0) ? sm.c0[r] / S0p : sm.c0[r];
-                        const double c1n = CLR ? (z1 ? sm.c1[r] / S1 : sm.c1[r]) : c1n_const;
-                        const double c2n = z2 ? sm.c2[iv] / S2 : sm.c2[iv];
-                        return (d.g_goal * c0n + d.g_ob * c1n) + d.g_speed * c2n;
-                    };
-                    const double cw = cost_p(ix, i), cr = cost_p(sx, s_i);
+                    const double c0n = (S0p != 0.0) ? div_rn_y(c0, S0p, 1.0 / S0p) : c0;
+                    const double head = d.g_goal * c0n + d.g_ob * c1n;
+                    const double cw = head + k2w, cr = head + k2r;
                     const bool winner_stays = cw < cr || (cw == cr && ix < sx);
                     if (!winner_stays) tie = 1;
                 }
@@ -1496,6 +1504,14 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
 // thread screens its share of the grid cells around the pose in FP32 and tests its survivors
 // exactly in FP64.  Returns bit0 = collision, bit1 = the decision is within 1e-6 of the 0.05
 // threshold (reported, not claimed).  Ends with block-wide barriers.
+// The exact footprint test, out of line: it runs for the few obstacles that survive the FP32
+// screens, and inlined it is a fifth of the extend kernels' code (eight float64 divisions).
+static __device__ __noinline__ double dis2obs_exact_cold(const EnvP &e, const RobotPose &g, float4 o, bool &definite,
+                                                         bool &marginal)
+{
+    return dis2obs_exact(e, g, o, definite, marginal);
+}
+
 template <class G>
 __device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, const RobotPose *gp)
 {
@@ -1513,7 +1529,7 @@ __device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, co
     grid_visit_rows(os, px, py, thr, tid, T, [&](float4 r) {
         if (aabb_center_d2(r, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, r) <= cthr) {
             bool d, m;
-            coll |= dis2obs_exact(e, g, r, d, m) < 0.0;
+            coll |= dis2obs_exact_cold(e, g, r, d, m) < 0.0;
             definite |= d; marginal |= m;
         }
     });
