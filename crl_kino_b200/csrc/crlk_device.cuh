@@ -661,6 +661,16 @@ __device__ __forceinline__ void body_to_world(double cs, double sn, double x, do
 // intervals, rigid.py:158-166).  A point inside an obstacle always falls in a
 // cell of that obstacle's range (the cell function is monotone), so this equals
 // the scan over all obstacles.  `near` is OR-ed with "within 1e-9 of a face".
+// The raster screen of a sample point alone: 0 = free, 1 = inside an obstacle, 2 = the raster cell is
+// only partly covered (or the point lies outside the raster): local_map_occupied decides.
+__device__ __forceinline__ unsigned local_map_raster(const ObsSet &os, double px, double py)
+{
+    const float rx = ((float)px - os.gx0) * os.rinv, ry = ((float)py - os.gy0) * os.rinv;
+    if (rx >= 0.f && ry >= 0.f && rx < (float)os.rnx && ry < (float)os.rny)
+        return __ldg(&os.raster[(int)ry * os.rnx + (int)rx]);
+    return 2u;
+}
+
 template <bool WANT_NEAR = true>
 __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, double py, bool &near)
 {

@@ -126,6 +126,24 @@ __device__ __forceinline__ void crlk_split3(float x, __nv_bfloat16 &a, __nv_bflo
 }
 #endif
 
+// parameter block of the fused RL policy step (k_rl_advance, crlk_kernels.cu)
+struct RlAdvP {
+    const float *h; int ld_h;                 // last hidden activation, compacted rows
+    const float *w, *bias; int K;             // head weights [2][K], bias [2]
+    const float *noise; long long noise_stride; const int *noise_cursor; int noise_off, noise_rows; float eps;
+    float low[2], high[2], scale[2], hbias[2];
+    const double *targets;                    // [Q][5]
+    const int *list_in, *count_in;            // rows of this step
+    int *list_out, *count_out;                // rows of the next step
+    double *state; int *nn;                   // per query: current state, nodes emitted
+    double *path; int *n_steps, *status, *node_step, *n_nodes; float *actions; uint8_t *flags;
+    float *obs32; int ld32;                   // SIMT path (nullable)
+    void *planes_v; int Mpad, Kp;      // tensor-core path (nullable)
+    int k, n;                                 // 1-based step, rows capacity
+};
+
+int crlk_rl_advance(const CrlkEnv *env, const ExtP *x, const void *params, int first, void *stream);
+
 // tensor-core MLP (crlk_mlp_tc.cu)
 struct CrlkPolicyTc;
 int crlk_tc_supported(const int *dims, int n_layers);

@@ -1844,6 +1844,268 @@ k_extend_dwa_pair(EnvP e, DwaP d, ExtP x, ObsSet os,
     }
 }
 
+// ---------------------------------------------- one policy step of the RL extension, fused
+//
+// RRT_RL.steer (rrt_rl.py:40-58) per live row of a compacted batch, one CTA per row:
+//   head      action = clamp(tanh(W h + b) (+ eps * noise) * scale + bias)   (net.py:145-153, ddpg.py:126-130)
+//             from the last hidden activation h (float32 [rows][ld_h]) of the policy GEMMs;
+//   motion    env.step's state update (differential_gym.py:139): one thread, float64;
+//   validity  valid_state_check of the new state (rrt_rl.py:48) by the whole CTA (collision_block);
+//   planner   path row, collision / reach / node-every-n_tree bookkeeping (rrt_rl.py:48-57); a query
+//             that keeps extending takes the next free row of the NEXT step's batch;
+//   observe   env._obs() of the new state (differential_gym.py:141,180-187) written straight into that
+//             row of the first layer's bf16 operand planes (or float32 rows on the SIMT path), with
+//             the cos / sin of the heading the motion step just computed.
+// FIRST = true is the call before step 1: no head / motion / validity, only the observation of
+// the start states (rrt_rl.py:34) into row b.
+#define RLA_QUEUE 64
+#ifndef RLA_MIN_BLOCKS
+#define RLA_MIN_BLOCKS 4
+#endif
+template <bool FIRST>
+__global__ void __launch_bounds__(256, RLA_MIN_BLOCKS)
+k_rl_advance(EnvP e, ExtP x, ObsSet os, ObsGrid og, RlAdvP a)
+{
+    // one WARP per row, eight rows per CTA, no block-wide barrier: the float64 motion step of a row
+    // runs on one lane while the other warps of the SM work on their rows
+    __shared__ RobotPose s_pose[8];
+    __shared__ int s_queue[8][RLA_QUEUE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= a.n || b >= *a.count_in) return;
+    const int q = a.list_in[b];
+    const int per = x.n_max_extend / x.n_tree + 1;
+    int slot = b;
+    double st0, st1, st3, st4, cs, sn;       // state x, y, v, omega and the heading's cos / sin (lane 0)
+    if (!FIRST) {
+        // ---- head: two dot products over K
+        const float *hr = a.h + (size_t)b * a.ld_h;
+        float s0 = 0.f, s1 = 0.f;
+        for (int k = lane; k < a.K; k += 32) {
+            const float v = hr[k];
+            s0 = fmaf(v, __ldg(&a.w[k]), s0);
+            s1 = fmaf(v, __ldg(&a.w[a.K + k]), s1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        RobotPose &g = s_pose[warp];
+        if (lane == 0) {
+            float act[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                float z = tanhf((c == 0 ? s0 : s1) + __ldg(&a.bias[c]));
+                if (a.noise) {
+                    // draws past the end of a query's stream count as zero (the host sizes the stream)
+                    const long long off = (long long)a.noise_off + (a.noise_cursor ? a.noise_cursor[q] : 0);
+                    if (off < a.noise_rows) z = z + a.noise[(size_t)q * a.noise_stride + off * 2 + c] * a.eps;
+                }
+                z = z * a.scale[c] + a.hbias[c];
+                act[c] = fminf(fmaxf(z, a.low[c]), a.high[c]);
+            }
+            // ---- motion (differential_gym.py:139): the float32 action promoted to float64
+            double s[5];
+            for (int c = 0; c < 5; c++) s[c] = a.state[5 * (size_t)q + c];
+            cs = 1.0; sn = 0.0;
+            for (int kk = 0; kk < x.n_sub_step; kk++) {
+                const double u0 = vel_substep(s[3], (double)act[0], e.max_acc_v, e.min_v, e.max_v, e.base_dt);
+                const double u1 = vel_substep(s[4], (double)act[1], e.max_acc_w, -e.max_w, e.max_w, e.base_dt);
+                const double th = normalize_angle(s[2] + u1 * e.base_dt);
+                crlk_sincos(th, &sn, &cs);
+                s[2] = th;
+                s[0] = s[0] + u0 * cs * e.base_dt;
+                s[1] = s[1] + u0 * sn * e.base_dt;
+                s[3] = u0; s[4] = u1;
+            }
+            if (x.n_sub_step == 0) crlk_sincos(s[2], &sn, &cs);
+            for (int c = 0; c < 5; c++) {
+                a.state[5 * (size_t)q + c] = s[c];
+                a.path[((size_t)q * x.n_max_extend + (a.k - 1)) * 5 + c] = s[c];
+            }
+            st0 = s[0]; st1 = s[1]; st3 = s[3]; st4 = s[4];
+            robot_pose_from_cs(e, s[0], s[1], cs, sn, g);
+            if (a.actions) {
+                a.actions[((size_t)q * x.n_max_extend + (a.k - 1)) * 2] = act[0];
+                a.actions[((size_t)q * x.n_max_extend + (a.k - 1)) * 2 + 1] = act[1];
+            }
+            a.n_steps[q] = a.k;
+        }
+        __syncwarp();
+        // ---- validity of the new state (rrt_rl.py:48): the warp screens the grid cells around the
+        // footprint in FP32 and tests the survivors exactly in FP64
+        const float px = (float)g.x, py = (float)g.y;
+        const float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN, thr2 = thr * thr;
+        const float cf = (float)g.c, sf = (float)g.s;
+        const float lbthr = (float)(CRLK_COLLISION_DIS + 2.0 * CRLK_NEAR_EPS);
+        int *queue = s_queue[warp];
+        const float4 *__restrict__ rects = os.rects;
+        bool coll = false, definite = false, marginal = false;
+        int count = 0;
+        auto drain = [&]() {
+            for (int b0 = 0; b0 < count; b0 += 32)
+                if (b0 + lane < count) {
+                    bool dd, mm;
+                    coll |= dis2obs_exact_cold(e, g, __ldg(&rects[queue[b0 + lane]]), dd, mm) < 0.0;
+                    definite |= dd; marginal |= mm;
+                }
+            count = 0;
+        };
+        grid_visit(os, px, py, thr, lane, 32, [&](int o, bool in) {
+            const float4 rr = __ldg(&rects[in ? o : 0]);
+            const bool keep = in && aabb_center_d2(rr, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, rr) <= lbthr;
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (mask) {
+                const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                if (keep) queue[pos] = o;
+                count += __popc(mask);
+                __syncwarp();
+                if (count > RLA_QUEUE - 32) { drain(); __syncwarp(); }
+            }
+        });
+        __syncwarp();
+        drain();
+        coll = __any_sync(0xffffffffu, coll);
+        definite = __any_sync(0xffffffffu, definite);
+        marginal = __any_sync(0xffffffffu, marginal);
+        int sl = -1;
+        if (lane == 0) {
+            if (marginal && !definite && a.flags) a.flags[q] |= 1;
+            const double gx = a.targets[5 * (size_t)q], gy = a.targets[5 * (size_t)q + 1];
+            const double ddx = st0 - gx, ddy = st1 - gy;
+            const double dist = sqrt(fma(ddy, ddy, ddx * ddx));
+            bool go_on = true;
+            int nn = a.nn[q];
+            if (coll) {
+                a.status[q] = CRLK_EXT_COLLISION; go_on = false;
+            } else if (dist <= x.reach_radius) {
+                a.node_step[(size_t)q * per + nn] = a.k;
+                nn++; a.status[q] = CRLK_EXT_REACHED; go_on = false;
+            } else if (a.k % x.n_tree == 0) {
+                a.node_step[(size_t)q * per + nn] = a.k;
+                nn++;
+            }
+            a.nn[q] = nn; a.n_nodes[q] = nn;
+            if (go_on && a.k < x.n_max_extend) {
+                sl = atomicAdd(a.count_out, 1);
+                a.list_out[sl] = q;
+            }
+        }
+        slot = __shfl_sync(0xffffffffu, sl, 0);
+        if (slot < 0) return;
+    } else if (lane == 0) {
+        st0 = a.state[5 * (size_t)q]; st1 = a.state[5 * (size_t)q + 1];
+        st3 = a.state[5 * (size_t)q + 3]; st4 = a.state[5 * (size_t)q + 4];
+        crlk_sincos(a.state[5 * (size_t)q + 2], &sn, &cs);
+    }
+    // ---- observation of the (new) state into row `slot`: lane = column of the 27 x 27 sample grid,
+    // one grid row per iteration (no index division, the lane's lateral offset is loop invariant).
+    // Most points are settled by the occupancy raster; the few that fall into partly covered raster
+    // cells are queued and decided afterwards with all lanes busy (decided in place they would stall
+    // the whole warp on one or two lanes: 58 % of the iterations had such a point).
+    const double px0 = __shfl_sync(0xffffffffu, st0, 0), py0 = __shfl_sync(0xffffffffu, st1, 0);
+    const double ccs = __shfl_sync(0xffffffffu, cs, 0), ssn = __shfl_sync(0xffffffffu, sn, 0);
+    __nv_bfloat16 *planes = (__nv_bfloat16 *)a.planes_v;
+    __nv_bfloat16 *p0 = planes ? planes + (size_t)slot * a.Kp : nullptr;
+    auto put = [&](int p, bool occ) {
+        const float v = occ ? 0.f : 1.f;
+        if (a.obs32) a.obs32[(size_t)slot * a.ld32 + 4 + p] = v;
+        if (p0) p0[4 + p] = __float2bfloat16_rn(v);
+    };
+    {
+        const bool on = lane < OBS_SIDE;
+        const double by = arange_at(og.lr0, og.lr1, og.lrd, on ? lane : 0);
+        const double nsby = __dmul_rn(-ssn, by), csby = __dmul_rn(ccs, by);
+        int *mq = s_queue[warp];                     // the collision queue is idle by now
+        int nq = 0;
+        auto point = [&](int ib, double byv_ns, double byv_cs, double &px, double &py) {
+            const double bx = arange_at(og.ba0, og.ba1, og.bad, ib);
+            px = __dadd_rn(__dadd_rn(__dmul_rn(ccs, bx), byv_ns), px0);    // body_to_world (differential_gym.py:83)
+            py = __dadd_rn(__dadd_rn(__dmul_rn(ssn, bx), byv_cs), py0);
+        };
+        auto drain = [&]() {
+            __syncwarp();
+            for (int i = lane; i < nq; i += 32) {
+                const int p = mq[i], ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;
+                const double byq = arange_at(og.lr0, og.lr1, og.lrd, il);
+                double px, py;
+                point(ib, __dmul_rn(-ssn, byq), __dmul_rn(ccs, byq), px, py);
+                bool nearp = false;
+                put(p, local_map_occupied<true>(os, px, py, nearp));     // the exact cell walk
+            }
+            nq = 0;
+            __syncwarp();
+        };
+        static_assert(OBS_SIDE % 3 == 0, "three grid rows per iteration");
+        for (int ib = 0; ib < OBS_SIDE; ib += 3) {
+            // three independent raster loads in flight before the first vote (a vote is a
+            // convergence point: the compiler does not move loads across it)
+            unsigned cls[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                double px, py;
+                point(ib + u, nsby, csby, px, py);
+                cls[u] = on ? local_map_raster(os, px, py) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int p = (ib + u) * OBS_SIDE + lane;
+                if (on && cls[u] < 2u) put(p, cls[u] != 0u);
+                const bool mixed = on && cls[u] >= 2u;
+                const unsigned mask = __ballot_sync(0xffffffffu, mixed);
+                if (mask) {
+                    if (mixed) mq[nq + __popc(mask & ((1u << lane) - 1u))] = p;
+                    nq += __popc(mask);
+                    if (nq > RLA_QUEUE - 32) drain();
+                }
+            }
+        }
+        drain();
+    }
+    if (planes) {
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+        for (int c = 4 + OBS_NPTS + lane; c < a.Kp; c += 32) p0[c] = z;
+        for (int c = 4 + lane; c < 64; c += 32) {
+            planes[((size_t)a.Mpad + slot) * a.Kp + c] = z;
+            planes[((size_t)2 * a.Mpad + slot) * a.Kp + c] = z;
+        }
+    }
+    if (lane == 0) {
+        const double *gl = a.targets + 5 * (size_t)q;
+        const double qx = gl[0] - st0, qy = gl[1] - st1;      // differential_gym.py:186-187 as R^T (g - t)
+        const float hv[4] = {(float)(cs * qx + sn * qy), (float)((-sn) * qx + cs * qy), (float)st3, (float)st4};
+        if (a.obs32) {
+            float *o = a.obs32 + (size_t)slot * a.ld32;
+            for (int c = 0; c < 4; c++) o[c] = hv[c];
+            for (int c = 4 + OBS_NPTS; c < a.ld32; c++) o[c] = 0.f;
+        }
+        if (planes) {
+            for (int c = 0; c < 4; c++) {
+                __nv_bfloat16 a0, a1, a2;
+                crlk_split3(hv[c], a0, a1, a2);
+                p0[c] = a0;
+                planes[((size_t)a.Mpad + slot) * a.Kp + c] = a1;
+                planes[((size_t)2 * a.Mpad + slot) * a.Kp + c] = a2;
+            }
+        }
+    }
+}
+
+// Launcher (crlk_nets.cu fills the parameter block; RlAdvP is repeated there as an opaque blob).
+int crlk_rl_advance(const CrlkEnv *env, const ExtP *x, const void *params, int first, void *stream)
+{
+    const RlAdvP *a = (const RlAdvP *)params;
+    if (a->n <= 0) return CRLK_OK;
+    const int grid = (a->n + 7) / 8;
+    if (first)
+        k_rl_advance<true><<<grid, 256, 0, (cudaStream_t)stream>>>(env->p, *x, env->os, make_obs_grid(), *a);
+    else
+        k_rl_advance<false><<<grid, 256, 0, (cudaStream_t)stream>>>(env->p, *x, env->os, make_obs_grid(), *a);
+    CRLK_LAUNCH_CHECK();
+    return CRLK_OK;
+}
+
 int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x)
 {
     CRLK_REQUIRE(in != nullptr, "extend params NULL");

@@ -179,17 +179,15 @@ k_policy_head(const float *__restrict__ A, int lda, const float *__restrict__ W,
 // operand planes already placed in the workspace (crlk_tc_input_planes; a_lo_kb as
 // in crlk_tc_layers_forward).  n_rows_dev / list (nullable): compacted batch of the
 // RL steer loop -- live row count on the device and the query of each row.
-static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs, const float *noise,
-                               long long noise_stride, const int *noise_cursor, int noise_off, int noise_rows,
-                               float eps, int B,
-                               float *act, void *workspace, cudaStream_t st, const int *n_rows_dev = nullptr,
-                               const int *list = nullptr, int a_lo_kb = 0)
+// Hidden layers: the last hidden activation (float32 rows) through *out / *ld_out.
+static int policy_hidden_impl(const CrlkPolicy *p, const float *obs, int ld_obs, int B, void *workspace,
+                              cudaStream_t st, const int *n_rows_dev, int a_lo_kb, const float **out, int *ld_out)
 {
     const int L = p->n_layers;
     const float *in = obs;
     int ld_in = ld_obs;
     if (policy_uses_tc(p)) {
-        // hidden layers on the tensor cores (tcgen05, bf16 x 3 split, float32 accumulate)
+        // hidden layers on the tensor cores (tcgen05, bf16 split operands, float32 accumulate)
         int rc = obs ? crlk_tc_hidden_forward(p->tc, obs, ld_obs, B, workspace, p->d_b, &in, &ld_in, st)
                      : crlk_tc_layers_forward(p->tc, B, workspace, p->d_b, n_rows_dev, a_lo_kb, &in, &ld_in, st);
         if (rc) return rc;
@@ -211,6 +209,22 @@ static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs
             ld_in = ldc;
         }
     }
+    *out = in;
+    *ld_out = ld_in;
+    return CRLK_OK;
+}
+
+static int policy_forward_impl(const CrlkPolicy *p, const float *obs, int ld_obs, const float *noise,
+                               long long noise_stride, const int *noise_cursor, int noise_off, int noise_rows,
+                               float eps, int B,
+                               float *act, void *workspace, cudaStream_t st, const int *n_rows_dev = nullptr,
+                               const int *list = nullptr, int a_lo_kb = 0)
+{
+    const int L = p->n_layers;
+    const float *in = nullptr;
+    int ld_in = 0;
+    int rc = policy_hidden_impl(p, obs, ld_obs, B, workspace, st, n_rows_dev, a_lo_kb, &in, &ld_in);
+    if (rc) return rc;
     HeadP hp;
     for (int k = 0; k < 2; k++) {
         hp.low[k] = p->low[k]; hp.high[k] = p->high[k]; hp.scale[k] = p->scale[k]; hp.bias[k] = p->bias[k];
@@ -625,7 +639,6 @@ extern "C" int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstima
 
 // ------------------------------------------------ RL extend (rrt_rl.py:22-63)
 
-#define WQ_CAP_RL 64
 
 struct RlWs {
     double *state;     // [Q][5]
@@ -659,20 +672,31 @@ static size_t rl_carve(const CrlkPolicy *p, int Q, unsigned char *base, RlWs *w)
     return off;
 }
 
-// Large batches are run as two halves on two streams (see crlk_extend_rl).
+// Large batches are run as 2 or 4 slices on as many streams (see crlk_extend_rl).
+#define RL_MAX_SPLIT 4
 static int rl_splits(int Q)
 {
     static const char *env = getenv("CRLK_RL_SPLIT");
-    if (env) return atoi(env) >= 2 ? 2 : 1;
+    if (env) { int v = atoi(env); return v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     return Q >= 2048 ? 2 : 1;
+}
+
+static void rl_slice(int Q, int ns, int i, int *q0, int *n)
+{
+    const int base = (Q + ns - 1) / ns;
+    *q0 = i * base < Q ? i * base : Q;
+    *n = (*q0 + base <= Q) ? base : Q - *q0;
 }
 
 extern "C" int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q)
 {
     if (!p || Q <= 0) return 0;
-    int64_t one = (int64_t)rl_carve(p, Q, nullptr, nullptr);
-    int64_t two = 2 * (int64_t)rl_carve(p, (Q + 1) / 2, nullptr, nullptr) + 512;
-    return one > two ? one : two;
+    int64_t best = (int64_t)rl_carve(p, Q, nullptr, nullptr);
+    for (int ns = 2; ns <= RL_MAX_SPLIT; ns *= 2) {
+        int64_t v = (int64_t)ns * ((int64_t)rl_carve(p, (Q + ns - 1) / ns, nullptr, nullptr) + 256) + 512;
+        if (v > best) best = v;
+    }
+    return best;
 }
 
 // count[] is zeroed before this launch; the active queries become step 1's row list.
@@ -702,98 +726,6 @@ __global__ void k_rl_init(const double *__restrict__ from_states, const uint8_t 
     }
 }
 
-// One warp per live row: apply the action (differential_gym.py:139), then the
-// planner's checks (rrt_rl.py:48-57); queries that keep extending are appended
-// to the next step's row list.
-__global__ void __launch_bounds__(256)
-k_rl_step(EnvP e, ExtP x, ObsSet os, const double *__restrict__ targets,
-          const float *__restrict__ act, int k, int Q, const int *__restrict__ list_in,
-          const int *__restrict__ count_in, int *list_out, int *count_out, double *state, int *nn,
-          double *path, int *n_steps, int *status, int *node_step, int *n_nodes, float *actions,
-          uint8_t *flags)
-{
-    __shared__ int s_queue[8][WQ_CAP_RL];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int row = blockIdx.x * 8 + warp;
-    if (row >= Q || row >= *count_in) return;
-    const int q = list_in[row];
-    const int per = x.n_max_extend / x.n_tree + 1;
-    double s[5];
-    for (int c = 0; c < 5; c++) s[c] = state[5 * (size_t)q + c];
-    // the float32 action promoted to float64 (differential_env.py:67-70)
-    double cv = (double)act[2 * (size_t)row], cw = (double)act[2 * (size_t)row + 1];
-    motion_velocity_dev(e, s, cv, cw, x.n_sub_step);
-    // collision test (flag only)
-    RobotPose g;
-    robot_pose_setup(e, s[0], s[1], s[2], g);
-    float px = (float)s[0], py = (float)s[1];
-    float thr = e.rc + (float)CRLK_COLLISION_DIS + CRLK_CULL_MARGIN;
-    float thr2 = thr * thr;
-    int *queue = s_queue[warp];
-    const float4 *__restrict__ rects = os.rects;
-    bool coll = false, definite = false, marginal = false;
-    int count = 0;
-    const float cf = (float)g.c, sf = (float)g.s;
-    const float lbthr = (float)(CRLK_COLLISION_DIS + 2.0 * CRLK_NEAR_EPS);
-    grid_visit(os, px, py, thr, lane, 32, [&](int o, bool in) {
-        const float4 rr = __ldg(&rects[in ? o : 0]);
-        bool keep = in && aabb_center_d2(rr, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, rr) <= lbthr;
-        unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (mask) {
-            int pos = count + __popc(mask & ((1u << lane) - 1u));
-            if (keep) queue[pos] = o;
-            count += __popc(mask);
-            __syncwarp();
-            if (count > WQ_CAP_RL - 32) {
-                for (int b0 = 0; b0 < count; b0 += 32)
-                    if (b0 + lane < count) {
-                        bool d, m;
-                        coll |= dis2obs_exact(e, g, __ldg(&rects[queue[b0 + lane]]), d, m) < 0.0;
-                        definite |= d; marginal |= m;
-                    }
-                count = 0;
-                __syncwarp();
-            }
-        }
-    });
-    __syncwarp();
-    for (int b0 = 0; b0 < count; b0 += 32)
-        if (b0 + lane < count) {
-            bool d, m;
-            coll |= dis2obs_exact(e, g, __ldg(&rects[queue[b0 + lane]]), d, m) < 0.0;
-            definite |= d; marginal |= m;
-        }
-    coll = __any_sync(0xffffffffu, coll);
-    definite = __any_sync(0xffffffffu, definite);
-    marginal = __any_sync(0xffffffffu, marginal);
-    if (lane != 0) return;
-    for (int c = 0; c < 5; c++) {
-        state[5 * (size_t)q + c] = s[c];
-        path[((size_t)q * x.n_max_extend + (k - 1)) * 5 + c] = s[c];
-    }
-    if (actions) {
-        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2] = act[2 * (size_t)row];
-        actions[((size_t)q * x.n_max_extend + (k - 1)) * 2 + 1] = act[2 * (size_t)row + 1];
-    }
-    n_steps[q] = k;
-    if (flags && marginal && !definite) flags[q] |= 1;
-    const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
-    double ddx = s[0] - gx, ddy = s[1] - gy;
-    double dist = sqrt(fma(ddy, ddy, ddx * ddx));
-    bool go_on = true;
-    if (coll) {
-        status[q] = CRLK_EXT_COLLISION; go_on = false;
-    } else if (dist <= x.reach_radius) {
-        node_step[(size_t)q * per + nn[q]] = k;
-        nn[q] += 1; n_nodes[q] = nn[q];
-        status[q] = CRLK_EXT_REACHED; go_on = false;
-    } else if (k % x.n_tree == 0) {
-        node_step[(size_t)q * per + nn[q]] = k;
-        nn[q] += 1; n_nodes[q] = nn[q];
-    }
-    if (go_on && k < x.n_max_extend) list_out[atomicAdd(count_out, 1)] = q;
-}
-
 // every executed step consumed one noise draw (net.py:147-150)
 __global__ void k_advance_cursor(int *cursor, const int *__restrict__ n_steps, const uint8_t *__restrict__ active,
                                  int Q)
@@ -803,19 +735,21 @@ __global__ void k_advance_cursor(int *cursor, const int *__restrict__ n_steps, c
 }
 
 #include <mutex>
-struct RlSide { cudaStream_t stream; cudaEvent_t fork, join; };
+struct RlSide { cudaStream_t stream[RL_MAX_SPLIT - 1]; cudaEvent_t fork, join[RL_MAX_SPLIT - 1]; };
 static RlSide g_rl_side[64];
 static std::mutex g_rl_mutex[64];      // the fork / launch / join sequence of one device is not re-entrant
 
-// The second stream of the split RL extend and its fork / join events, per device.
+// The side streams of the split RL extend and their fork / join events, per device.
 static int rl_side(int device, RlSide **out)
 {
     CRLK_REQUIRE(device >= 0 && device < 64, "device index");
     RlSide *s = &g_rl_side[device];
-    if (!s->stream) {
-        CRLK_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    if (!s->fork) {
+        for (int i = 0; i < RL_MAX_SPLIT - 1; i++) {
+            CRLK_CUDA(cudaStreamCreateWithFlags(&s->stream[i], cudaStreamNonBlocking));
+            CRLK_CUDA(cudaEventCreateWithFlags(&s->join[i], cudaEventDisableTiming));
+        }
         CRLK_CUDA(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
-        CRLK_CUDA(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
     }
     *out = s;
     return CRLK_OK;
@@ -853,24 +787,24 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
     const int ns = rl_splits(Q);
     RlSide *side = nullptr;
     std::unique_lock<std::mutex> guard;
-    if (ns == 2) {
+    if (ns > 1) {
         CRLK_REQUIRE(env->device >= 0 && env->device < 64, "device index");
         guard = std::unique_lock<std::mutex>(g_rl_mutex[env->device]);
         rc = rl_side(env->device, &side);
         if (rc) return rc;
         CRLK_CUDA(cudaEventRecord(side->fork, st));
-        CRLK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        for (int i = 1; i < ns; i++) CRLK_CUDA(cudaStreamWaitEvent(side->stream[i - 1], side->fork, 0));
     }
-    struct Half { int q0, n; cudaStream_t s; RlWs w; void *planes; int Mpad, Kp; } h[2];
+    struct Half { int q0, n; cudaStream_t s; RlWs w; void *planes; int Mpad, Kp; } h[RL_MAX_SPLIT];
     const bool tc = policy_uses_tc(p);
     unsigned char *wsb = (unsigned char *)workspace;
     for (int i = 0; i < ns; i++) {
-        h[i].q0 = (ns == 1) ? 0 : i * ((Q + 1) / 2);
-        h[i].n = (ns == 1) ? Q : (i == 0 ? (Q + 1) / 2 : Q - (Q + 1) / 2);
-        h[i].s = (i == 0) ? st : side->stream;
-        size_t used = rl_carve(p, h[i].n, wsb, &h[i].w);
+        rl_slice(Q, ns, i, &h[i].q0, &h[i].n);
+        h[i].s = (i == 0) ? st : side->stream[i - 1];
+        size_t used = rl_carve(p, h[i].n > 0 ? h[i].n : 1, wsb, &h[i].w);
         wsb += (used + 255) & ~(size_t)255;
         h[i].planes = nullptr; h[i].Mpad = 0; h[i].Kp = 0;
+        if (h[i].n <= 0) continue;
         if (tc) crlk_tc_input_planes(p->tc, h[i].w.mlp, h[i].n, &h[i].planes, &h[i].Mpad, &h[i].Kp);
         const int q0 = h[i].q0, n = h[i].n;
         CRLK_CUDA(cudaMemsetAsync(h[i].w.count, 0, sizeof(int) * (x.n_max_extend + 2), h[i].s));
@@ -880,35 +814,56 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
                                                       flags ? flags + q0 : nullptr);
         CRLK_LAUNCH_CHECK();
     }
+    // Per step and slice: the policy's hidden layers on the compacted batch (tensor cores), then ONE
+    // kernel for head + motion + validity + bookkeeping + the next observation (k_rl_advance).  The
+    // survivors' row list and count stay on the device; kernels read the count and skip rows past it.
+    RlAdvP a[RL_MAX_SPLIT];
+    const int L = p->n_layers;
+    for (int i = 0; i < ns; i++) {
+        if (h[i].n <= 0) continue;
+        const int q0 = h[i].q0;
+        RlWs &w = h[i].w;
+        RlAdvP &r = a[i];
+        r.h = nullptr; r.ld_h = 0;
+        r.w = p->d_w[L - 1]; r.bias = p->d_b[L - 1]; r.K = p->kpad[L - 1];
+        r.noise = noise ? noise + (size_t)q0 * noise_rows * 2 : nullptr;
+        r.noise_stride = (long long)noise_rows * 2;
+        r.noise_cursor = noise_cursor ? noise_cursor + q0 : nullptr;
+        r.noise_off = 0; r.noise_rows = noise_rows; r.eps = eps;
+        for (int c = 0; c < 2; c++) { r.low[c] = p->low[c]; r.high[c] = p->high[c]; r.scale[c] = p->scale[c]; r.hbias[c] = p->bias[c]; }
+        r.targets = targets + 5 * (size_t)q0;
+        r.list_in = w.list[0]; r.count_in = w.count; r.list_out = nullptr; r.count_out = nullptr;
+        r.state = w.state; r.nn = w.nn;
+        r.path = path + (size_t)q0 * x.n_max_extend * 5;
+        r.n_steps = n_steps + q0; r.status = status + q0; r.node_step = node_step + (size_t)q0 * per;
+        r.n_nodes = n_nodes + q0;
+        r.actions = actions ? actions + (size_t)q0 * x.n_max_extend * 2 : nullptr;
+        r.flags = flags ? flags + q0 : nullptr;
+        r.obs32 = tc ? nullptr : w.obs; r.ld32 = 736;
+        r.planes_v = h[i].planes; r.Mpad = h[i].Mpad; r.Kp = h[i].Kp;
+        r.k = 0; r.n = h[i].n;
+        rc = crlk_rl_advance(env, &x, &r, 1, (void *)h[i].s);            // observation of the start states (rrt_rl.py:34)
+        if (rc) return rc;
+    }
     for (int k = 1; k <= x.n_max_extend; k++) {
         for (int i = 0; i < ns; i++) {
-            const int q0 = h[i].q0, n = h[i].n;
+            if (h[i].n <= 0) continue;
             RlWs &w = h[i].w;
-            const int *list = w.list[(k - 1) & 1], *cnt = w.count + (k - 1);
-            const double *tg = targets + 5 * (size_t)q0;
-            // observation of the current state (rrt_rl.py:34 / differential_gym.py:141): straight
-            // into the bf16 operand planes of the first layer on the tensor-core path
-            rc = crlk_local_obs_compact(env, w.state, tg, 5, n, list, cnt, tc ? nullptr : w.obs, 736,
-                                        h[i].planes, h[i].Mpad, h[i].Kp, (void *)h[i].s);
-            if (rc) return rc;
+            RlAdvP &r = a[i];
+            const int *cnt = w.count + (k - 1);
             // action = policy(obs) (rrt_rl.py:41); only the four goal / velocity inputs have low planes
-            rc = policy_forward_impl(p, tc ? nullptr : w.obs, 736,
-                                     noise ? noise + (size_t)q0 * noise_rows * 2 : nullptr,
-                                     (long long)noise_rows * 2, noise_cursor ? noise_cursor + q0 : nullptr,
-                                     k - 1, noise_rows, eps, n, w.act, w.mlp, h[i].s, cnt, list, 1);
+            rc = policy_hidden_impl(p, tc ? nullptr : w.obs, 736, h[i].n, w.mlp, h[i].s, cnt, 1, &r.h, &r.ld_h);
             if (rc) return rc;
-            k_rl_step<<<(n + 7) / 8, 256, 0, h[i].s>>>(env->p, x, env->os, tg, w.act, k, n, list, cnt,
-                                                      w.list[k & 1], w.count + k, w.state, w.nn,
-                                                      path + (size_t)q0 * x.n_max_extend * 5, n_steps + q0,
-                                                      status + q0, node_step + (size_t)q0 * per, n_nodes + q0,
-                                                      actions ? actions + (size_t)q0 * x.n_max_extend * 2 : nullptr,
-                                                      flags ? flags + q0 : nullptr);
-            CRLK_LAUNCH_CHECK();
+            r.k = k; r.noise_off = k - 1;
+            r.list_in = w.list[(k - 1) & 1]; r.count_in = cnt;
+            r.list_out = w.list[k & 1]; r.count_out = w.count + k;
+            rc = crlk_rl_advance(env, &x, &r, 0, (void *)h[i].s);
+            if (rc) return rc;
         }
     }
-    if (ns == 2) {
-        CRLK_CUDA(cudaEventRecord(side->join, side->stream));
-        CRLK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    for (int i = 1; i < ns; i++) {
+        CRLK_CUDA(cudaEventRecord(side->join[i - 1], side->stream[i - 1]));
+        CRLK_CUDA(cudaStreamWaitEvent(st, side->join[i - 1], 0));
     }
     if (noise && noise_cursor) {
         k_advance_cursor<<<(Q + 127) / 128, 128, 0, st>>>(noise_cursor, n_steps, active, Q);
