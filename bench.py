@@ -36,9 +36,9 @@ sys.path.insert(0, ROOT)
 M_FLOP_ROLLOUT = 406.0      # FP ops per DWA rollout as the reference evaluates it
 M_FLOP_PAIR = 860.0         # FP ops per (pose, obstacle) pair, brute force
 FP64_LANES_PER_SM = 64      # B200: 64 FP64 FMA lanes per SM
-# float64 operations the kernels execute per counted unit (FMA = 2), from the SASS of k_extend_dwa
-# (tools/count_fp64.py prints them; DESIGN.md section 4 has the table)
-X_FLOP = dict(rollout=118.0, sincos_task=330.0, vel_substep=14.0, pair_test=420.0, step_fixed=900.0)
+# float64 operations k_extend_dwa executes per counted unit (FMA = 2; DESIGN.md section 4 derives them from
+# the source and checks the total against ncu's dadd + dmul + 2 dfma count of one launch: within 8 %)
+X_FLOP = dict(rollout=99.0, sincos_task=130.0, velocity_chain=100.0, pair_test=400.0, step_fixed=300.0)
 WORKLOAD_SEED = 100
 POLICY_FLOP = 3600384.0     # 2 * MACs of the 733-1024-512-512-512-2 actor
 
@@ -840,15 +840,16 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
     achieved = flop / (t_ext * 1e-3) / 1e12
     executed = None
     if len(stats) >= 8 and stats[5] > 0:
-        xf = (X_FLOP["rollout"] * n_roll + X_FLOP["sincos_task"] * stats[5] + X_FLOP["vel_substep"] * stats[6] +
+        xf = (X_FLOP["rollout"] * n_roll + X_FLOP["sincos_task"] * stats[5] + X_FLOP["velocity_chain"] * stats[6] +
               X_FLOP["pair_test"] * stats[3] + X_FLOP["step_fixed"] * n_ctrl)
         executed = {"fp64_flop_per_launch": xf / K, "tflops": xf / (t_ext * 1e-3) / 1e12,
                     "counters_per_launch": {"control_steps": n_ctrl / K, "rollouts": n_roll / K,
-                                            "exact_pair_tests": stats[3] / K, "grid_cells_visited": stats[4] / K,
-                                            "sincos_chain_tasks": stats[5] / K, "velocity_substeps": stats[6] / K},
+                                            "exact_pair_tests": stats[3] / K, "rectangles_screened_fp32": stats[4] / K,
+                                            "sincos_chain_tasks": stats[5] / K, "velocity_chains": stats[6] / K},
                     "per_unit_fp64_flop": X_FLOP,
-                    "source": "counters maintained by k_extend_dwa (crlk_extend_dwa `stats`), per-unit FP64 operation "
-                              "counts from the kernel's SASS (DESIGN.md section 4)"}
+                    "source": "counters maintained by k_extend_dwa (crlk_extend_dwa `stats`) x per-unit FP64 operation "
+                              "counts (DESIGN.md section 4); frac_executed counts an FMA as 2 against the FMA peak, the "
+                              "pipe's busy share is in roofline.ncu (fp64_pipe_pct_while_active)"}
     ncu = load_ncu("r2_extend_ncu.json")
     value = tot_ext / (t_total_max * 1e-3)
     line = {

@@ -1513,7 +1513,7 @@ static __device__ __noinline__ double dis2obs_exact_cold(const EnvP &e, const Ro
 }
 
 template <class G>
-__device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, const RobotPose *gp)
+__device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, const RobotPose *gp, int *work = nullptr)
 {
     const int tid = grp.tid(), T = grp.size();
     const RobotPose g = *gp;
@@ -1526,13 +1526,17 @@ __device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, co
     bool coll = false, definite = false, marginal = false;
     // each thread screens its share of the cell lists and tests its survivors at once
     // (a pose touches a few hundred listed obstacles at most: <= 1-2 per thread)
+    int n_screened = 0;
     grid_visit_rows(os, px, py, thr, tid, T, [&](float4 r) {
+        n_screened++;
         if (aabb_center_d2(r, px, py) <= thr2 && footprint_lb(e, cf, sf, px, py, r) <= cthr) {
             bool d, m;
             coll |= dis2obs_exact_cold(e, g, r, d, m) < 0.0;
             definite |= d; marginal |= m;
+            if (work) atomicAdd(&work[0], 1);                 // exact FP64 footprint tests (rare)
         }
     });
+    if (work && n_screened) atomicAdd(&work[1], n_screened);  // rectangles through the FP32 screens
     // barrier-fused reductions; most poses are not within the threshold band of any obstacle's
     // bounding circle, so no thread ran an exact test and one barrier settles it
     if (!grp.sync_or(coll | definite | marginal)) return 0;
@@ -1545,6 +1549,7 @@ __device__ int collision_block(const G &grp, const EnvP &e, const ObsSet &os, co
 struct ExtResult {
     int nn, status, steps, flags;
     unsigned long long rolls;
+    unsigned tasks, chains;       // sincos chain tasks (nw x positions) and velocity chains (nv) over the steps
 };
 
 // RRT.steer (rrt.py:99-135) by one CTA: up to n_max_extend closed-loop control
@@ -1560,7 +1565,7 @@ __device__ ExtResult extend_dwa_block(const G &g, const EnvP &e, const DwaP &d, 
                                       double gy, double *path, int *ctrl_idx, OnNode on_node)
 {
     ExtResult res;
-    res.nn = 0; res.status = CRLK_EXT_TIMEOUT; res.steps = 0; res.flags = 0; res.rolls = 0;
+    res.nn = 0; res.status = CRLK_EXT_TIMEOUT; res.steps = 0; res.flags = 0; res.rolls = 0; res.tasks = 0; res.chains = 0;
     for (int k = 1; k <= x.n_max_extend; k++) {
         // rrt.py:116-118: control, then thread 0 advances the state inside the control block's
         // closing section: s_state (nobody reads it any more) and the footprint of the new state
@@ -1588,10 +1593,12 @@ __device__ ExtResult extend_dwa_block(const G &g, const EnvP &e, const DwaP &d, 
         }
         res.flags |= r.near_tie ? 2 : 0;
         res.rolls += (unsigned long long)r.R;
+        res.tasks += (unsigned)(sm.ihdr[1] * sm.spos);
+        res.chains += (unsigned)sm.ihdr[0];
         res.steps = k;
         // rrt.py:121: valid_state_check on the new state
         PHASE_START();
-        int col = collision_block(g, e, os, sm.pose);
+        int col = collision_block(g, e, os, sm.pose, sm.cl_n + 2);
         PHASE_MARK(8);
         if (col & 2) res.flags |= 1;
         col &= 1;
@@ -1646,6 +1653,7 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
             continue;
         }
         if (tid < 5) s_state[tid] = from_states[5 * (size_t)q + tid];
+        if (tid == 0) { sm.cl_n[2] = 0; sm.cl_n[3] = 0; }
         __syncthreads();
         const double gx = targets[5 * (size_t)q], gy = targets[5 * (size_t)q + 1];
         ExtResult r = extend_dwa_block<GrpCta<T>, CLR>(GrpCta<T>(), e, d, x, os, sm, s_state, gx, gy,
@@ -1662,6 +1670,10 @@ k_extend_dwa(EnvP e, DwaP d, ExtP x, ObsSet os,
                 atomicAdd(&stats[0], 1ull);                            // extensions
                 atomicAdd(&stats[1], (unsigned long long)r.steps);     // control steps
                 atomicAdd(&stats[2], r.rolls);                         // rollouts scored
+                atomicAdd(&stats[3], (unsigned long long)sm.cl_n[2]);  // exact FP64 footprint tests
+                atomicAdd(&stats[4], (unsigned long long)sm.cl_n[3]);  // rectangles through the FP32 screens
+                atomicAdd(&stats[5], (unsigned long long)r.tasks);     // sincos chain tasks
+                atomicAdd(&stats[6], (unsigned long long)r.chains);    // velocity chains
             }
         }
     }

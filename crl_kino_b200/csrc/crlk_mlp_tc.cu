@@ -549,9 +549,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16x3_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                    int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
                    __nv_bfloat16 *__restrict__ planes_out, int ld_out, float *__restrict__ c32, int ldc,
-                   const int *__restrict__ n_rows_dev, int a_lo_kb)
+                   const int *__restrict__ n_rows_dev, int a_lo_kb, int nprod)
 {
     if (n_rows_dev) B = min(B, *n_rows_dev);
+    const int npl = nprod == 6 ? 3 : 2;              // planes in use (k_gemm_bf16x3_persist)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + PairCfg<PBN>::stages * PairCfg<PBN>::stage;
@@ -593,9 +594,10 @@ k_gemm_bf16x3_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 const bool lo = kb < a_lo_kb;
                 if (rank == 0)                  // the leader's barrier counts the bytes of both CTAs
-                    mbar_expect_tx(full0 + 8 * s, 2 * ((lo ? TCP_A_BYTES : TC_STAGE_BYTES) + PairCfg<PBN>::b_bytes));
+                    mbar_expect_tx(full0 + 8 * s, 2 * ((lo ? npl : 1) * TC_STAGE_BYTES + npl * PairCfg<PBN>::b_plane));
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++) {
+                    if (pl >= npl) continue;
                     if (pl == 0 || lo)
                         tma_load_2d_pair(st + pl * TC_STAGE_BYTES, &tmA, kb * TC_BK, pl * Mpad + m0, full0 + 8 * s);
                     tma_load_2d_pair(st + TCP_A_BYTES + pl * PairCfg<PBN>::b_plane, &tmWh, kb * TC_BK, pl * N + n0,
@@ -621,6 +623,7 @@ k_gemm_bf16x3_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int pr = 0; pr < TC_NPAIR; pr++) {
                     if (!lo && c_pair_a[pr] != 0) continue;
+                    if (pr >= nprod) continue;
                     uint64_t da = umma_desc_sw128(st + c_pair_a[pr] * TC_STAGE_BYTES);
                     uint64_t db = umma_desc_sw128(st + TCP_A_BYTES + c_pair_w[pr] * PairCfg<PBN>::b_plane);
 #pragma unroll
@@ -855,21 +858,21 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
         // every pair has several tiles to work through (measured: 203 vs 177 algorithmic TFLOP/s at 65,536
         // rows), slower below that (fewer, larger tiles per wave).  CRLK_MLP_PAIR=0 / 128 / 256 forces.
         static const int pair_env = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
-        const int pair = t->nprod != 6 ? 0 : pair_env >= 0 ? pair_env : (B >= 24576 ? 256 : 0);
+        const int pair = pair_env >= 0 ? pair_env : (B >= 24576 ? 256 : 0);
         if (pair == 256 && Mpad % (2 * TC_BM) == 0 && L.N % 256 == 0) {
             int tiles = (L.N / 256) * (Mpad / (2 * TC_BM));
             int pairs = tiles < n_sms / 2 ? tiles : n_sms / 2;
             k_gemm_bf16x3_pair<256><<<2 * pairs, TC_THREADS, PairCfg<256>::smem, st>>>(
                 mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
                 is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N, n_rows_dev,
-                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks);
+                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks, t->nprod);
         } else if (pair && Mpad % (2 * TC_BM) == 0) {
             int tiles = (L.N / TC_BN) * (Mpad / (2 * TC_BM));
             int pairs = tiles < n_sms / 2 ? tiles : n_sms / 2;
             k_gemm_bf16x3_pair<128><<<2 * pairs, TC_THREADS, PairCfg<128>::smem, st>>>(
                 mapA, L.map_wh, Mpad, L.N, kblocks, d_bias[i], B,
                 is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N, n_rows_dev,
-                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks);
+                (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks, t->nprod);
         } else if (unfused && !need_persist)
             k_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(
                 mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,

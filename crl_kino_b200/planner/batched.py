@@ -260,7 +260,7 @@ class BatchedRRT:
         self.cursor = torch.zeros(Q, **i32)
         self.sample = torch.zeros(Q, 5, dtype=torch.float64, device=d)
         self.from_states = torch.zeros(Q, 5, dtype=torch.float64, device=d)
-        self.stats = torch.zeros(4, dtype=torch.int64, device=d)
+        self.stats = torch.zeros(8, dtype=torch.int64, device=d)
         self.out = [None, None]
         self.rounds = 0
         self.coord_bound = env.coord_bound()

@@ -189,8 +189,10 @@ int64_t crlk_nearest_scratch_bytes(int32_t Q, int32_t max_nodes);
  *   flags      dev u8[Q] (nullable) bit0 near-boundary collision test, bit1 near-tie argmin (see
  *              crlk_dwa_control), bit3 empty DWA grid (status CRLK_EXT_INVALID, nothing executed)
  *   active     dev u8[Q] (nullable) 0 => skip this pair (n_steps = 0, n_nodes = 0)
- *   stats      dev u64[3] (nullable) ACCUMULATED (+=): extensions run, control steps
- *              executed, rollouts scored -- the work counters behind bench.py's roofline. */
+ *   stats      dev u64[8] (nullable) ACCUMULATED (+=): [0] extensions run, [1] control steps executed,
+ *              [2] rollouts scored, [3] exact FP64 footprint tests, [4] obstacle rectangles that went
+ *              through the FP32 screens of the validity tests, [5] sincos chain tasks, [6] velocity
+ *              chains, [7] reserved -- the executed-work counters behind bench.py's roofline. */
 int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const CrlkExtendParams *ext,
                     const double *from_states, const double *targets, int32_t Q, double *path,
                     int32_t *n_steps, int32_t *status, int32_t *node_step, int32_t *n_nodes,

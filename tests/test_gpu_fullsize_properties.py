@@ -58,7 +58,7 @@ def test_extend_full_cfg4_batch_properties():
     d = DWA(env)
     d.set_dwa(**DENSE_DWA)
     xp = ops.extend_params()
-    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
     out = ops.extend_dwa(env.handle, d.params(), xp, froms, targets, want_ctrl=True, stats=stats)
     ns, status, nn = np_(out["n_steps"]), np_(out["status"]), np_(out["n_nodes"])
     path, node_step = np_(out["path"]), np_(out["node_step"])
