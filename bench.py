@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--plan-iters", type=int, default=100, help="max_iter of the planning-queries/s leg")
     ap.add_argument("--plan-queries", type=int, default=0, help="queries per GPU of the planning leg (0 = --queries)")
     ap.add_argument("--plan-lockstep", action="store_true", help="also time the lock-step planner (BatchedRRT)")
+    ap.add_argument("--plan-rl-queries", type=int, default=1024, help="queries of the learned-steering planning leg")
+    ap.add_argument("--plan-rl-iters", type=int, default=6, help="max_iter of the learned-steering planning leg")
     ap.add_argument("--cfg5-steps", type=int, default=4)
     ap.add_argument("--cfg5-warmup", type=int, default=2)
     ap.add_argument("--cfg5-total", type=int, default=65536, help="queries of the cfg5 leg over all GPUs")
@@ -401,6 +403,102 @@ def planning_leg(args, env, dwa, rank):
         out["lockstep_seconds"] = time.perf_counter() - t0
         out["lockstep_rounds"] = p.samples_used
         out["lockstep_identical"] = bool(np.array_equal(r2, r_streams) and torch.equal(p.forest.n_nodes, nodes_from_streams))
+    return out
+
+
+def _one_thread():
+    """Pool initializer: one BLAS / OpenMP thread per worker process (the pool already uses every core)."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+
+
+def _cpu_plan_rl_one(a):
+    rects, start, goal, stream, iters, aw, ab, est, cls = a
+    from oracle import oracle as orc
+    o = orc.Env()
+    o.set_obs(rects)
+    p = orc.PlannerPort(o, steering="rl", actor=(aw, ab), estimator=est, classifier=cls, max_iter=iters, eps=0.0)
+    p.set_start_and_goal(start, goal)
+    try:
+        p.planning(iter(stream))
+    except StopIteration:
+        return p.n_extend_calls, False, -1
+    return p.n_extend_calls, bool(p.reach_exactly), len(p.node_list)
+
+
+def planning_rl_leg(args, env, rects, no_cpu):
+    """Planning queries/s with the learned steering function (examples/benchmark.py runs RRT_RL_Estimator
+    only, benchmark.py:48-51): Q queries advanced in lock step by BatchedRRT -- per round one nearest-node
+    (RRT_RL) or estimator choose_parent (RRT_RL_Estimator) pass, one batched policy extension toward the
+    sample and one toward the goal (rrt.py:72-83) -- from pre-drawn host sample streams, wall clock.  The
+    CPU port (oracle.PlannerPort, numpy actor / CNN) runs the first queries from the same streams."""
+    import multiprocessing as mp
+    import torch
+    from crl_kino_b200.env import DifferentialDriveGym
+    from crl_kino_b200.estimator import load_estimator
+    from crl_kino_b200.planner.batched import BatchedRRT
+    from crl_kino_b200.policy.rl_policy import load_policy
+    from crl_kino_b200.workloads import query_pairs
+    Q, iters = args.plan_rl_queries, args.plan_rl_iters
+    pol = load_policy(DifferentialDriveGym(), [1024, 512, 512, 512], None, seed=0)
+    w = np.load(os.path.join(ROOT, "data", "estimator_weights.npz"))
+    est_sd = {k[4:]: w[k] for k in w.files if k.startswith("est.")}
+    cls_sd = {k[4:]: w[k] for k in w.files if k.startswith("cls.")}
+    est = load_estimator(est_sd, cls_sd)
+
+    def clearance(c):
+        return env.valid_state_batch(c, want_clearance=True)[1].cpu().numpy()
+    starts, goals = query_pairs(clearance, Q, seed=11)
+    sb = env.get_bounds()["state_bounds"]
+    S = iters * 6 + 32
+    rng = np.random.default_rng(411)
+    streams = rng.uniform(sb[:, 0], sb[:, 1], (Q, S, 5))
+    pick = rng.integers(0, 101, (Q, S)) <= 5                      # goal bias of rrt.py:147
+    streams[pick] = np.repeat(goals[:, None, :], S, 1)[pick]
+    h_streams = torch.as_tensor(streams).pin_memory()
+    out = {"queries": Q, "max_iter": iters, "unit": "queries/s",
+           "policy": "seeded random-init actor 733-1024-512-512-512-2, eps 0 (the trained policy.pth is missing upstream)",
+           "estimator": "data/estimator_weights.npz (the reference's dist_est / classifier state dicts)"}
+    res = {}
+    for name, e in (("rrt_rl", None), ("rrt_rl_estimator", est)):
+        best = None
+        for rep in range(2):                                    # first pass = warm-up
+            p = BatchedRRT(env, starts, goals, max_iter=iters, policy=pol, eps=0.0, keep_paths=False, estimator=e)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            d = h_streams.cuda(non_blocking=True)                # the streams are the step's host inputs
+            reached = p.plan(d, check_every=8)
+            nodes = p.forest.n_nodes.cpu().numpy()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        res[name] = dict(reached=reached, nodes=nodes)
+        out[name] = {"queries_per_sec": Q / best, "seconds": best, "rounds": int(p.samples_used),
+                     "reached_frac": float(np.mean(reached)), "mean_nodes": float(nodes.mean()),
+                     "h2d_bytes": int(h_streams.numel() * 8), "d2h_bytes": int(nodes.nbytes + Q),
+                     "planner": "BatchedRRT(policy" + (", estimator)" if e is not None else ")") + ": lock-step rounds, wall clock incl. H2D / D2H"}
+    if not no_cpu:
+        from oracle import oracle as orc
+        cores = orc.cpu_count()
+        n = min(Q, cores, 16)
+        aw, ab = pol.actor.weights, pol.actor.biases
+        for name, es, cs in (("rrt_rl", None, None), ("rrt_rl_estimator", est_sd, cls_sd)):
+            t0 = time.perf_counter()
+            with mp.get_context("fork").Pool(n, initializer=_one_thread) as pool:
+                r = pool.map(_cpu_plan_rl_one, [(rects, starts[q], goals[q], streams[q], iters, aw, ab, es, cs) for q in range(n)])
+            dt = time.perf_counter() - t0
+            g = res[name]
+            out[name]["cpu_baseline"] = {"queries_per_sec": n / dt, "queries": n, "seconds": dt, "cores": cores, "kind": "port",
+                                         "extensions": int(sum(x[0] for x in r)),
+                                         "same_reach_and_node_count_as_gpu": int(sum(1 for q in range(n) if r[q][1] == bool(g["reached"][q]) and
+                                                                                     r[q][2] == int(g["nodes"][q])))}
     return out
 
 
@@ -915,6 +1013,7 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
                                             "note": "BatchedRRT: five launches per round, wall clock"}
         line["rooflines_other_kernels"] = [nearest_roofline(peaks), mlp_roofline(peaks)]
         line["sub_rates"] = sub_rates(env, dwa, peaks)
+        line["planning_rl"] = planning_rl_leg(args, env, rects, args.no_cpu)
     h2d, d2h = ext.h2d_bytes(), ext.d2h_bytes()
     del ext, forest, dev_batches, flush
     torch.cuda.empty_cache()
