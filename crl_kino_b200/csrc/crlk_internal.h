@@ -108,6 +108,10 @@ int crlk_make_ext(const CrlkEnv *env, const CrlkExtendParams *in, ExtP *x);
         }                                                                                 \
     } while (0)
 
+// an environment whose last crlk_env_set_obs failed holds no obstacle set: every entry point refuses it
+#define CRLK_ENV_OK(env) CRLK_REQUIRE((env) != nullptr && (env)->os.rects != nullptr, \
+                                      "env is NULL or holds no obstacle set (crlk_env_set_obs failed)")
+
 int crlk_require_device(void);
 int crlk_local_obs_compact(const CrlkEnv *env, const double *states, const double *goals,
                            int32_t goal_stride, int32_t Bmax, const int *list, const int *count,

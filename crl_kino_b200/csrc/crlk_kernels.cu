@@ -221,6 +221,7 @@ extern "C" int crlk_env_set_obs(CrlkEnv *env, const float *rects_host, int32_t M
     CRLK_REQUIRE(env != nullptr, "env is NULL");
     CRLK_REQUIRE(M >= 0 && (M == 0 || rects_host != nullptr), "rects");
     CRLK_CUDA(cudaSetDevice(env->device));
+    memset(&env->os, 0, sizeof env->os);          // nothing published until every upload has succeeded
     if (env->d_rects) { CRLK_CUDA(cudaFree(env->d_rects)); env->d_rects = nullptr; }
     env->M = M;
     // one spare element so that a zero-obstacle env still has a valid pointer
@@ -230,6 +231,8 @@ extern "C" int crlk_env_set_obs(CrlkEnv *env, const float *rects_host, int32_t M
                              cudaMemcpyHostToDevice));
     return build_grid(env, rects_host, M);
 }
+
+extern "C" int crlk_env_destroy(CrlkEnv *env);
 
 extern "C" int crlk_env_create(const CrlkEnvParams *params, const float *rects_host, int32_t M,
                                CrlkEnv **out)
@@ -244,7 +247,7 @@ extern "C" int crlk_env_create(const CrlkEnvParams *params, const float *rects_h
     e->host = *params;
     fill_envp(params, &e->p);
     rc = crlk_env_set_obs(e, rects_host, M);
-    if (rc) { delete e; return rc; }
+    if (rc) { crlk_env_destroy(e); return rc; }
     *out = e;
     return CRLK_OK;
 }
@@ -351,7 +354,7 @@ k_clearance(EnvP e, ObsSet os, const double *__restrict__ states, int B, uint8_t
 extern "C" int crlk_valid_state(const CrlkEnv *env, const double *states, int32_t B, uint8_t *valid,
                                 double *clearance, uint8_t *near_boundary, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     CRLK_REQUIRE(B >= 0 && (B == 0 || states != nullptr), "states");
     if (B == 0) return CRLK_OK;
     if (clearance)
@@ -419,7 +422,7 @@ __global__ void k_motion(EnvP e, const double *__restrict__ sin_, const double *
 static int launch_motion(const CrlkEnv *env, const double *sin_, const double *cmd, double duration,
                          int B, int accel, double *sout, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     CRLK_REQUIRE(B >= 0 && (B == 0 || (sin_ && cmd && sout)), "NULL array");
     if (B == 0) return CRLK_OK;
     int n_sub = crlk_count_loop_lt(duration, env->p.base_dt);
@@ -456,7 +459,7 @@ __global__ void k_dynamic_window(EnvP e, const double *__restrict__ states, doub
 extern "C" int crlk_dynamic_window(const CrlkEnv *env, const double *states, double dt, int32_t B,
                                    double *out, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     CRLK_REQUIRE(B >= 0 && (B == 0 || (states && out)), "NULL array");
     if (B == 0) return CRLK_OK;
     k_dynamic_window<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, states, dt, B, out);
@@ -560,7 +563,7 @@ extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const do
                               int32_t goal_stride, int32_t B, double *obs64, float *obs32,
                               int32_t ld32, uint8_t *near_boundary, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     CRLK_REQUIRE(B >= 0 && (B == 0 || (states && goals)), "NULL array");
     CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
     CRLK_REQUIRE(obs32 == nullptr || ld32 >= 4 + OBS_NPTS, "ld32 < 733");
@@ -642,7 +645,7 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
                              int32_t B, double *info, double *reward, double *obs64, float *obs32,
                              int32_t ld32, uint8_t *near_boundary, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     CRLK_REQUIRE(B >= 0 && (B == 0 || (states && goals)), "NULL array");
     CRLK_REQUIRE(goal_stride >= 2, "goal_stride < 2");
     CRLK_REQUIRE(!reward || reward_param_host, "reward_param required with reward");
@@ -681,13 +684,14 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
 #define DWA_MIN_BLOCKS 2
 #endif
 #define DWA_WIDE_THREADS 768
-// The whole-query planner kernel interleaves many short serial sections (sample test, tree scan,
-// node append) with the control steps, so it prefers more, smaller CTAs per SM (measured).
+// The whole-query planner kernel: the same shape as the extend kernel since the control step's cost
+// and summation passes became exact (round 2: 256 x 2 measured 22.1 k queries/s against 20.3 k for
+// the 128 x 4 shape that was best with the cheaper round-1 control step).
 #ifndef PLAN_THREADS
-#define PLAN_THREADS 128
+#define PLAN_THREADS 256
 #endif
 #ifndef PLAN_MIN_BLOCKS
-#define PLAN_MIN_BLOCKS 4
+#define PLAN_MIN_BLOCKS 2
 #endif
 
 __global__ void k_debug_atan2(const double *__restrict__ y, const double *__restrict__ x, int n, double *out)
@@ -1478,7 +1482,7 @@ extern "C" int crlk_dwa_control(const CrlkEnv *env, const CrlkDwaParams *dwa, co
                                 int32_t *opt_idx, double *opt_cost, double *opt_traj,
                                 int32_t *n_rollouts, uint8_t *near_tie, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     DwaP d;
     int rc = crlk_make_dwa(env, dwa, &d);
     if (rc) return rc;
@@ -2227,7 +2231,7 @@ extern "C" int crlk_extend_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, con
                                int32_t *n_nodes, int32_t *ctrl_idx, uint8_t *flags,
                                const uint8_t *active, uint64_t *stats, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr, "env is NULL");
+    CRLK_ENV_OK(env);
     DwaP d;
     ExtP x;
     int rc = crlk_make_dwa(env, dwa, &d);
@@ -2521,7 +2525,8 @@ extern "C" int crlk_plan_dwa(const CrlkEnv *env, const CrlkDwaParams *dwa, const
                              uint8_t *reached, uint8_t *flags, int32_t *overflow, uint64_t *stats,
                              const int32_t *order, void *stream)
 {
-    CRLK_REQUIRE(env != nullptr && plan != nullptr && forest != nullptr, "env/plan/forest is NULL");
+    CRLK_ENV_OK(env);
+    CRLK_REQUIRE(plan != nullptr && forest != nullptr, "plan/forest is NULL");
     DwaP d;
     ExtP x;
     int rc = crlk_make_dwa(env, dwa, &d);

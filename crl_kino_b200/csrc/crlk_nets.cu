@@ -12,6 +12,8 @@
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+extern "C" int crlk_policy_destroy(CrlkPolicy *p);
+
 extern "C" int crlk_policy_create(int32_t n_layers, const int32_t *dims,
                                   const float *const *weights_host, const float *const *biases_host,
                                   const float *low, const float *high, CrlkPolicy **out)
@@ -23,36 +25,48 @@ extern "C" int crlk_policy_create(int32_t n_layers, const int32_t *dims,
     if (rc) return rc;
     CrlkPolicy *p = new CrlkPolicy();
     memset(p, 0, sizeof *p);
-    CRLK_CUDA(cudaGetDevice(&p->device));
-    p->n_layers = n_layers;
-    p->max_dim = 0;
-    for (int i = 0; i <= n_layers; i++) {
-        CRLK_REQUIRE(dims[i] >= 1, "layer width < 1");
-        p->dims[i] = dims[i];
-    }
-    for (int i = 0; i < n_layers; i++) {
-        int K = dims[i], N = dims[i + 1];
-        int kp = round_up(K, 16);
-        p->kpad[i] = kp;
-        if (i > 0 && kp > p->max_dim) p->max_dim = kp;
-        float *hw = (float *)calloc((size_t)N * kp, sizeof(float));
-        for (int n = 0; n < N; n++) memcpy(hw + (size_t)n * kp, weights_host[i] + (size_t)n * K, sizeof(float) * K);
-        CRLK_CUDA(cudaMalloc(&p->d_w[i], sizeof(float) * (size_t)N * kp));
-        CRLK_CUDA(cudaMemcpy(p->d_w[i], hw, sizeof(float) * (size_t)N * kp, cudaMemcpyHostToDevice));
-        free(hw);
-        CRLK_CUDA(cudaMalloc(&p->d_b[i], sizeof(float) * N));
-        CRLK_CUDA(cudaMemcpy(p->d_b[i], biases_host[i], sizeof(float) * N, cudaMemcpyHostToDevice));
-    }
-    for (int k = 0; k < 2; k++) {
-        // net.py:134-138 in float32
-        p->low[k] = low[k]; p->high[k] = high[k];
-        p->bias[k] = (low[k] + high[k]) / 2.0f;
-        p->scale[k] = (high[k] - low[k]) / 2.0f;
-    }
-    p->tc = nullptr;
-    if (crlk_tc_supported(p->dims, n_layers)) {
-        int rc2 = crlk_tc_create(p->dims, n_layers, weights_host, &p->tc);
-        if (rc2) return rc2;
+    // built inside a lambda: on any failure the partly built handle is destroyed, not leaked
+    auto build = [&]() -> int {
+        CRLK_CUDA(cudaGetDevice(&p->device));
+        p->n_layers = n_layers;
+        p->max_dim = 0;
+        for (int i = 0; i <= n_layers; i++) {
+            CRLK_REQUIRE(dims[i] >= 1, "layer width < 1");
+            p->dims[i] = dims[i];
+        }
+        for (int i = 0; i < n_layers; i++) {
+            int K = dims[i], N = dims[i + 1];
+            int kp = round_up(K, 16);
+            p->kpad[i] = kp;
+            if (i > 0 && kp > p->max_dim) p->max_dim = kp;
+            float *hw = (float *)calloc((size_t)N * kp, sizeof(float));
+            CRLK_REQUIRE(hw != nullptr, "out of host memory");
+            for (int n = 0; n < N; n++) memcpy(hw + (size_t)n * kp, weights_host[i] + (size_t)n * K, sizeof(float) * K);
+            cudaError_t e1 = cudaMalloc(&p->d_w[i], sizeof(float) * (size_t)N * kp);
+            cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpy(p->d_w[i], hw, sizeof(float) * (size_t)N * kp, cudaMemcpyHostToDevice) : e1;
+            free(hw);
+            CRLK_CUDA(e2);
+            CRLK_CUDA(cudaMalloc(&p->d_b[i], sizeof(float) * N));
+            CRLK_CUDA(cudaMemcpy(p->d_b[i], biases_host[i], sizeof(float) * N, cudaMemcpyHostToDevice));
+        }
+        for (int k = 0; k < 2; k++) {
+            // net.py:134-138 in float32
+            p->low[k] = low[k]; p->high[k] = high[k];
+            p->bias[k] = (low[k] + high[k]) / 2.0f;
+            p->scale[k] = (high[k] - low[k]) / 2.0f;
+        }
+        p->tc = nullptr;
+        if (crlk_tc_supported(p->dims, n_layers)) {
+            int rc2 = crlk_tc_create(p->dims, n_layers, weights_host, &p->tc);
+            if (rc2) return rc2;
+        }
+        return CRLK_OK;
+    };
+    rc = build();
+    if (rc) {
+        p->n_layers = n_layers;          // destroy walks every layer slot (unset ones are NULL)
+        crlk_policy_destroy(p);
+        return rc;
     }
     *out = p;
     return CRLK_OK;
@@ -613,7 +627,8 @@ extern "C" int crlk_estimator_choose_parent(const CrlkEnv *env, const CrlkEstima
                                             int32_t max_nodes, const double *targets, int32_t Q, int32_t *idx,
                                             double *cost, void *workspace, void *stream)
 {
-    CRLK_REQUIRE(env && e, "env/estimator is NULL");
+    CRLK_ENV_OK(env);
+    CRLK_REQUIRE(e != nullptr, "estimator is NULL");
     CRLK_REQUIRE(Q >= 0 && max_nodes >= 1 && stride >= max_nodes, "shape");
     if (Q == 0) return CRLK_OK;
     CRLK_REQUIRE(states && n_nodes && targets && idx && cost && workspace, "NULL array");
@@ -762,7 +777,8 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
                               int32_t *n_nodes, float *actions, uint8_t *flags, const uint8_t *active,
                               void *workspace, void *stream)
 {
-    CRLK_REQUIRE(env && p, "env/policy is NULL");
+    CRLK_ENV_OK(env);
+    CRLK_REQUIRE(p != nullptr, "policy is NULL");
     CRLK_REQUIRE(p->dims[0] == 733, "the actor must take the 733-vector observation");
     ExtP x;
     int rc = crlk_make_ext(env, ext, &x);
@@ -795,6 +811,9 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
         CRLK_CUDA(cudaEventRecord(side->fork, st));
         for (int i = 1; i < ns; i++) CRLK_CUDA(cudaStreamWaitEvent(side->stream[i - 1], side->fork, 0));
     }
+    // Everything between the fork above and the join below runs inside `body`, so that an error on
+    // any launch still joins the side streams back into the caller's stream before returning.
+    auto body = [&]() -> int {
     struct Half { int q0, n; cudaStream_t s; RlWs w; void *planes; int Mpad, Kp; } h[RL_MAX_SPLIT];
     const bool tc = policy_uses_tc(p);
     unsigned char *wsb = (unsigned char *)workspace;
@@ -861,10 +880,16 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
             if (rc) return rc;
         }
     }
+    return CRLK_OK;
+    };
+    rc = body();
     for (int i = 1; i < ns; i++) {
-        CRLK_CUDA(cudaEventRecord(side->join[i - 1], side->stream[i - 1]));
-        CRLK_CUDA(cudaStreamWaitEvent(st, side->join[i - 1], 0));
+        if (cudaEventRecord(side->join[i - 1], side->stream[i - 1]) != cudaSuccess ||
+            cudaStreamWaitEvent(st, side->join[i - 1], 0) != cudaSuccess) {
+            if (!rc) { crlk_set_error("joining the side streams of crlk_extend_rl failed"); rc = CRLK_E_CUDA; }
+        }
     }
+    if (rc) return rc;
     if (noise && noise_cursor) {
         k_advance_cursor<<<(Q + 127) / 128, 128, 0, st>>>(noise_cursor, n_steps, active, Q);
         CRLK_LAUNCH_CHECK();

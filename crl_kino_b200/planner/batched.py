@@ -369,6 +369,13 @@ class BatchedRRT:
         torch.cuda.synchronize()
         if int(self.overflow.item()):
             raise RuntimeError(f"{int(self.overflow.item())} trees ran out of node/path capacity")
+        if self.noise is not None and self.eps != 0.0:
+            # one draw per executed policy step (net.py:147-150); the kernel treats draws past the end of
+            # a query's stream as zero, which would silently change the exploration: refuse that
+            used = int(self.noise_cursor.max().item())
+            if used > self.noise.shape[1]:
+                raise RuntimeError(f"a query consumed {used} exploration draws but its noise stream holds "
+                                   f"{self.noise.shape[1]}: pass at least 2 * max_iter * n_max_extend rows")
         self.samples_used = r + 1
         return self.reached.cpu().numpy().astype(bool)
 

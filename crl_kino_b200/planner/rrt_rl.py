@@ -32,6 +32,9 @@ class RRT_RL(RRT):
         if self.eps != 0.0:
             if self._noise is not None:
                 noise, cursor = self._noise, self._cursor
+                if self.n_control_steps + xp.n_max_extend > self._noise.shape[1]:
+                    raise RuntimeError("the exploration noise stream is too short for another extension: "
+                                       f"{self.n_control_steps} draws used of {self._noise.shape[1]}")
             else:
                 noise = torch.randn(size=(1, xp.n_max_extend, 2)).numpy()
         out = ops.extend_rl(self.robot_env.handle, self.policy.actor.handle, xp, from_node.state[None],

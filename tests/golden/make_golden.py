@@ -920,11 +920,82 @@ def g_plan_cfg3():
     save("plan_cfg3", **out)
 
 
+def _steer_rl_dense_one(a):
+    """One RRT_RL.steer of the unmodified reference on the cfg4 map (worker of a process pool)."""
+    rects, f, t, seed = a
+    import crl_kino.planner.rrt_rl as rl_mod
+    env = make_env([RectObs(r.reshape(2, 2)) for r in rects])
+    pol, actor = make_policy(seed)
+    planner = RRT_RL(env, pol)
+    rec, arec = [], []
+    orig_pf = rl_mod.policy_forward
+
+    def pf(policy, obs, info=None, eps=0.0):
+        a_ = orig_pf(policy, obs, info=info, eps=0.0)
+        arec.append(a_[0].copy())
+        return a_
+    rl_mod.policy_forward = pf
+    orig_valid = env.valid_state_check
+
+    def tap(state, _rec=rec, _o=orig_valid):
+        r = _o(state)
+        _rec.append((np.array(state), r))
+        return r
+    env.valid_state_check = tap
+    planner.node_list = []
+    tic = time.time()
+    new = planner.steer(planner.Node(np.array(f)), planner.Node(np.array(t)))
+    el = time.time() - tic
+    rec = rec[1::2]          # _info() inside gym.step also calls valid_state_check (differential_gym.py:163)
+    p = np.zeros((50, 5)); ac = np.zeros((50, 2))
+    for k, (st, _) in enumerate(rec):
+        p[k] = st
+    for k, a_ in enumerate(arec):
+        ac[k] = a_
+    code = 0
+    if not rec[-1][1]:
+        code = 1
+    elif np.linalg.norm(rec[-1][0][:2] - np.array(t)[:2]) <= 1.0:
+        code = 2
+    return dict(path=p, act=ac, nsteps=len(rec), status=code, nnodes=len(new), seconds=el)
+
+
+def g_steer_rl_dense():
+    """RRT_RL.steer (rrt_rl.py:22-63) of the unmodified reference on BASELINE config 4's map (10,004
+    obstacles, crl_kino_b200.workloads.dense_map), seeded random-init policy, eps = 0: start states with
+    no obstacle within 1.5 m (conservative raster), targets 3-20 m away.  ~1.5 s of reference time per
+    policy step (valid_state_check and get_clearance over every obstacle in Python)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from crl_kino_b200.workloads import clearance_raster, dense_map, raster_free
+    import multiprocessing as mp
+    rects = dense_map()
+    rng = np.random.default_rng(21)
+    gx, occ = clearance_raster(rects, 1.5)
+    froms, targets = [], []
+    while len(froms) < 8:
+        f = random_states(rng, 1)[0]
+        f[3:] = 0
+        if not raster_free(gx, occ, f[None])[0]:
+            continue
+        t = random_states(rng, 1)[0]
+        if not (3.0 <= np.linalg.norm(f[:2] - t[:2]) < 20):
+            continue
+        froms.append(f); targets.append(t)
+    with mp.get_context("fork").Pool(int(os.environ.get("GOLDEN_WORKERS", "4"))) as pool:
+        res = pool.map(_steer_rl_dense_one, [(rects, froms[i], targets[i], 0) for i in range(len(froms))], chunksize=1)
+    out = {"seed": np.array(0), "n_cells": np.array(10000), "from": np.array(froms), "target": np.array(targets)}
+    for key in ("path", "act", "nsteps", "status", "nnodes", "seconds"):
+        out[key] = np.array([r[key] for r in res])
+    for i, r in enumerate(res):
+        print(f"steer_rl_dense {i}: {r['nsteps']} steps, status {r['status']}, {r['nnodes']} nodes, {r['seconds']:.0f}s")
+    save("steer_rl_dense", **out)
+
+
 ALL = dict(fixtures=g_fixtures, numerics=g_numerics, motion=g_motion, dwa=g_dwa,
            dwa_clearance=g_dwa_clearance, geometry=g_geometry, obs=g_obs, nearest=g_nearest,
            steer_dwa=g_steer_dwa, plan_dwa=g_plan_dwa, policy=g_policy, estimator=g_estimator,
            steer_rl=g_steer_rl, plan_rl=g_plan_rl, gym=g_gym, circle=g_circle, formats=g_formats,
-           plan_dwa_full=g_plan_dwa_full, plan_cfg3=g_plan_cfg3)
+           plan_dwa_full=g_plan_dwa_full, plan_cfg3=g_plan_cfg3, steer_rl_dense=g_steer_rl_dense)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

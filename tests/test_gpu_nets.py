@@ -100,6 +100,35 @@ def test_steer_rl_golden(tag, eps):
             assert np_(out["n_nodes"])[q] == g[tag + "_nnodes"][q]
 
 
+def test_steer_rl_dense_map_golden():
+    """RRT_RL.steer of the unmodified reference on BASELINE config 4's map (10,004 obstacles, golden
+    steer_rl_dense): closed loop with the float32 policy, states to 1e-4, verdicts exact unless the
+    kernel reported a near-boundary decision."""
+    import os
+    from crl_kino_b200 import ops
+    from crl_kino_b200.env import DifferentialDriveEnv
+    from crl_kino_b200.workloads import dense_map
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "steer_rl_dense.npz")):
+        pytest.skip("tests/golden/steer_rl_dense.npz not generated")
+    g = golden("steer_rl_dense")
+    env = DifferentialDriveEnv(1.0, -0.1, np.pi, 1.0, np.pi)
+    env.set_obs(dense_map(n_cells=int(g["n_cells"])))
+    pol = _policy(int(g["seed"]))
+    out = ops.extend_rl(env.handle, pol.actor.handle, ops.extend_params(), g["from"], g["target"], None, 0.0,
+                        want_actions=True)
+    fl, ns = np_(out["flags"]), np_(out["n_steps"])
+    for q in range(len(ns)):
+        n_ref = int(g["nsteps"][q])
+        n = min(n_ref, ns[q])
+        np.testing.assert_allclose(np_(out["actions"])[q, :n], g["act"][q, :n], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(np_(out["path"])[q, :n], g["path"][q, :n], rtol=1e-4, atol=1e-4)
+        if fl[q] == 0:
+            assert ns[q] == n_ref
+            assert np_(out["status"])[q] == g["status"][q]
+            assert np_(out["n_nodes"])[q] == g["nnodes"][q]
+
+
 def test_extend_rl_vs_oracle_teacher_forced():
     """Per-step parity with teacher forcing: feed the kernel's own actions to the oracle dynamics."""
     from crl_kino_b200 import ops
