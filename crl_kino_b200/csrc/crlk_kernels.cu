@@ -1307,71 +1307,38 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
             else if (c < second) { second = c; si = r | (i << 16); }
         }
     }
-    auto merge = [&](double ob, int oi, double os2, int osi) {
-        // loser of the two minima, then the smallest of {loser, both runner-ups}
-        const bool owins = ob < best || (ob == best && (oi & 0xffff) < (bi & 0xffff));
-        double lv = owins ? best : ob;
-        int li = owins ? bi : oi;
-        if (owins) { best = ob; bi = oi; }
-        if (os2 < second) { second = os2; si = osi; }
-        if (lv < second) { second = lv; si = li; }
-    };
+    // The winner: (minimum, first index) across the warp by shuffles, across the block through shared
+    // memory -- every thread then reads the per-warp results itself (no serial merge by one thread).
+    double wb = best;
+    int wi = bi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const double os2 = __shfl_xor_sync(0xffffffffu, second, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const int osi = __shfl_xor_sync(0xffffffffu, si, o);
-        merge(ob, oi, os2, osi);
+        const double ob = __shfl_xor_sync(0xffffffffu, wb, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (ob < wb || (ob == wb && (oi & 0xffff) < (wi & 0xffff))) { wb = ob; wi = oi; }
     }
-    if (lane == 0) { sm.red3_v[warp] = best; sm.red3_s[warp] = second; sm.red_i[warp] = bi; sm.red_i[32 + warp] = si; }
+    if (lane == 0) { sm.red3_v[warp] = wb; sm.red_i[warp] = wi; }
     g.sync();
     PHASE_MARK(3);
+    wb = sm.red3_v[0]; wi = sm.red_i[0];
+    for (int w = 1; w < (T >> 5); w++) {
+        const double ob = sm.red3_v[w];
+        const int oi = sm.red_i[w];
+        if (ob < wb || (ob == wb && (oi & 0xffff) < (wi & 0xffff))) { wb = ob; wi = oi; }
+    }
+    // This thread's candidate for the runner-up (its best, or its second if its best is the winner), and
+    // whether it lies within 8 ulp of the winner: only then can the decision be a near tie (below).
+    const double cand = (bi == wi) ? second : best;
+    const int candi = (bi == wi) ? si : bi;
+    const int close = (candi != 0x7fffffff && cand - wb <= 8.0 * 2.220446049250313e-16 * fabs(wb)) ? 1 : 0;
+    const int ix = wi & 0xffff;
+    const int wrow = wi >> 16;
     if (tid == 0) {
-        best = sm.red3_v[0]; second = sm.red3_s[0]; bi = sm.red_i[0]; si = sm.red_i[32];
-        for (int w = 1; w < T / 32; w++) merge(sm.red3_v[w], sm.red_i[w], sm.red3_s[w], sm.red_i[32 + w]);
-        const int ix = bi & 0xffff;
-        const int i = bi >> 16, j = ix - i * nw;
+        const int i = wrow, j = ix - i * nw;
         sm.scal[4] = arange_at(v_lo, v1, vd, i);
         sm.scal[5] = arange_at(w_lo, w1, wd, j);
-        sm.scal[6] = best;
+        sm.scal[6] = wb;
         sm.iscal[1] = ix;
-        // Near-tie report.  The costs above are the reference's arithmetic applied to this build's
-        // heading costs, which are the C library's bits except where the library itself misrounds
-        // (7.5e-4 of its atan2 results, one ulp; crlk_crmath.h).  Such a last bit moves the heading
-        // column's sum by an ulp in about one control step in a hundred, and with it every cost.  A
-        // decision is reported when that could change it:
-        //   * winner and runner-up have DIFFERENT heading costs and lie within 8 ulp of each other
-        //     (their own last bits could decide); or
-        //   * they share the heading cost bit for bit (the rollout grid's last velocity row repeats
-        //     the one before it whenever the window ends at max_v: same first step, same atan2
-        //     arguments, speed terms one ulp apart) and the winner changes when the column sum moves
-        //     by one ulp either way (a rounding that merges the two costs, or stops merging them,
-        //     hands the decision to the first index).
-        // Identical rollouts (same heading AND speed cost: commands clamped to the same value) are
-        // never near ties: np.argmin and this kernel both keep the first.
-        int tie = 0;
-        if (si != 0x7fffffff && second - best <= 8.0 * 2.220446049250313e-16 * fabs(best)) {
-            const int sx = si & 0xffff, s_i = si >> 16;
-            const bool same_c0 = sm.c0[sx] == sm.c0[ix] && (!CLR || sm.c1[sx] == sm.c1[ix]);
-            if (!same_c0) tie = 1;
-            else if (sm.c2[s_i] != sm.c2[i]) {
-                // same heading (and obstacle) cost: only the common first part of the two costs moves
-                const double c0 = sm.c0[ix];
-                const double c1n = CLR ? (z1 ? div_rn_y(sm.c1[ix], S1, y1) : sm.c1[ix]) : c1n_const;
-                const double k2w = d.g_speed * (z2 ? div_rn_y(sm.c2[i], S2, y2) : sm.c2[i]);
-                const double k2r = d.g_speed * (z2 ? div_rn_y(sm.c2[s_i], S2, y2) : sm.c2[s_i]);
-                for (int dir = -1; dir <= 1 && !tie; dir += 2) {
-                    const double S0p = __longlong_as_double(__double_as_longlong(S0) + dir);
-                    const double c0n = (S0p != 0.0) ? div_rn_y(c0, S0p, 1.0 / S0p) : c0;
-                    const double head = d.g_goal * c0n + d.g_ob * c1n;
-                    const double cw = head + k2w, cr = head + k2r;
-                    const bool winner_stays = cw < cr || (cw == cr && ix < sx);
-                    if (!winner_stays) tie = 1;
-                }
-            }
-        }
-        sm.iscal[2] = tie;
         PHASE_MARK(4);
         // trajectory row 1 of the winner (= motion_velocity(state, opt_v, d.dt), same operations)
         double row1[5];
@@ -1393,11 +1360,68 @@ __device__ DwaResult dwa_control_block(const G &g, const EnvP &e, const DwaP &d,
                  sm.wsin[(d.n_sub - 1) * d.nw_max + j]);
     }
     PHASE_MARK(9);
-    g.sync();
+    // closing barrier, fused with the vote "is any other rollout within 8 ulp of the winner?"
+    int tie = 0;
+    if (g.sync_or(close)) {
+        // Near-tie report.  The costs above are the reference's arithmetic applied to this build's
+        // heading costs, which are the C library's bits except where the library itself misrounds
+        // (7.5e-4 of its atan2 results, one ulp; crlk_crmath.h).  Such a last bit moves the heading
+        // column's sum by an ulp in about one control step in a hundred, and with it every cost.  A
+        // decision is reported when that could change it:
+        //   * winner and runner-up have DIFFERENT heading costs and lie within 8 ulp of each other
+        //     (their own last bits could decide); or
+        //   * they share the heading cost bit for bit (the rollout grid's last velocity row repeats
+        //     the one before it whenever the window ends at max_v: same first step, same atan2
+        //     arguments, speed terms one ulp apart) and the winner changes when the column sum moves
+        //     by one ulp either way (a rounding that merges the two costs, or stops merging them,
+        //     hands the decision to the first index).
+        // Identical rollouts (same heading AND speed cost: commands clamped to the same value) are
+        // never near ties: np.argmin and this kernel both keep the first.
+        // (rare path) the runner-up: lexicographic (cost, index) minimum of the candidates
+        double rb = cand;
+        int rix = candi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, rb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, rix, o);
+            if (ob < rb || (ob == rb && (oi & 0xffff) < (rix & 0xffff))) { rb = ob; rix = oi; }
+        }
+        if (lane == 0) { sm.red3_s[warp] = rb; sm.red_i[32 + warp] = rix; }
+        g.sync();
+        if (tid == 0) {
+            for (int w = 0; w < (T >> 5); w++) {
+                const double ob = sm.red3_s[w];
+                const int oi = sm.red_i[32 + w];
+                if (w == 0 || ob < rb || (ob == rb && (oi & 0xffff) < (rix & 0xffff))) { rb = ob; rix = oi; }
+            }
+            const int i = wrow;
+            const int sx = rix & 0xffff, s_i = rix >> 16;
+            const bool same_c0 = sm.c0[sx] == sm.c0[ix] && (!CLR || sm.c1[sx] == sm.c1[ix]);
+            if (!same_c0) tie = 1;
+            else if (sm.c2[s_i] != sm.c2[i]) {
+                // same heading (and obstacle) cost: only the common first part of the two costs moves
+                const double c0 = sm.c0[ix];
+                const double c1n = CLR ? (z1 ? div_rn_y(sm.c1[ix], S1, y1) : sm.c1[ix]) : c1n_const;
+                const double k2w = d.g_speed * (z2 ? div_rn_y(sm.c2[i], S2, y2) : sm.c2[i]);
+                const double k2r = d.g_speed * (z2 ? div_rn_y(sm.c2[s_i], S2, y2) : sm.c2[s_i]);
+                for (int dir = -1; dir <= 1 && !tie; dir += 2) {
+                    const double S0p = __longlong_as_double(__double_as_longlong(S0) + dir);
+                    const double c0n = (S0p != 0.0) ? div_rn_y(c0, S0p, 1.0 / S0p) : c0;
+                    const double head = d.g_goal * c0n + d.g_ob * c1n;
+                    const double cw = head + k2w, cr = head + k2r;
+                    const bool winner_stays = cw < cr || (cw == cr && ix < sx);
+                    if (!winner_stays) tie = 1;
+                }
+            }
+            sm.iscal[2] = tie;
+        }
+        g.sync();
+        tie = sm.iscal[2];
+    }
     PHASE_MARK(7);
     DwaResult res;
     res.v = sm.scal[4]; res.w = sm.scal[5]; res.cost = sm.scal[6];
-    res.idx = sm.iscal[1]; res.near_tie = sm.iscal[2]; res.R = R;
+    res.idx = sm.iscal[1]; res.near_tie = tie; res.R = R;
     return res;
 }
 

@@ -275,13 +275,13 @@ def _check_against_reference_runs(planner_cls, g, runs, env, **kw):
     for i, r in enumerate(runs):
         states, parents = p.tree(i)
         ref = g[f"run{r}_node_states"]
-        ok = len(states) == len(ref) and np.allclose(states, ref, rtol=1e-9, atol=1e-11)
+        ok = len(states) == len(ref) and np.allclose(states, ref, rtol=1e-12, atol=1e-13)
         if not ok:
             assert flags[i] & 3, f"run {r} differs from the reference without a near-tie / near-boundary report"
             continue
         assert np.array_equal(parents, g[f"run{r}_parents"])
         assert reached[i] == bool(g[f"run{r}_reach"])
-        np.testing.assert_allclose(np.array(p.final_course(i)), g[f"run{r}_path"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(np.array(p.final_course(i)), g[f"run{r}_path"], rtol=1e-12, atol=1e-13)
         if planner_cls.__name__ == "FusedRRT":
             assert int(np_(p.cursor)[i]) == len(g[f"run{r}_samples"])       # same number of draws consumed
         same += 1

@@ -19,35 +19,34 @@ def _extend(env, froms, targets, **dwa_kw):
     return ops.extend_dwa(env.handle, d.params(), ops.extend_params(), froms, targets, want_ctrl=True)
 
 
-def _compare(out, ref, what, min_clean=0.0):
-    """flags bit0 (collision decision within 1e-6 of the threshold) exempts an
-    extension; bit1 (near-tie argmin somewhere along it) only exempts the chosen
-    rollout indices -- the executed states must still agree (tied rollouts that
-    differ only by the clamped grid overshoot give the same motion)."""
+def _compare(out, ref, what, max_flagged=0.15, max_diverged=0):
+    """The contract of include/crlk.h: step counts, status, emitted nodes and the chosen rollout of every
+    control step exactly the oracle's, executed states to 1e-12 (contract: 1e-4) -- unless the kernel itself
+    reported the extension: flags bit 0 (a collision decision within 1e-6 of the threshold) or bit 1 (an
+    argmin decision that one misrounded last bit of the C library's atan2 could change).  Reported
+    extensions may differ, at most `max_diverged` of them do, and at most `max_flagged` of the batch is
+    reported at all.  Executed states are the oracle's BITS except where the C library misrounds a sin /
+    cos (6e-4 of its results, one ulp, which survives into a coordinate about once in 10^4 steps): at
+    least 98 % of the extensions must be bit-identical."""
     fl = np_(out["flags"])
-    ok = (fl & 1) == 0
-    clean = fl == 0
-    assert ok.mean() > 0.9, f"{what}: too many near-boundary extensions"
-    assert clean.mean() >= min_clean, f"{what}: too many near-tie extensions ({clean.mean():.2f} clean)"
+    assert (fl != 0).mean() <= max_flagged, f"{what}: {(fl != 0).sum()} of {len(fl)} extensions reported"
     path, rpath = np_(out["path"]), ref["path"]
-    diverged = 0
-    for q in np.where(ok)[0]:
-        n = ref["n_steps"][q]
+    diverged, bitwise = 0, 0
+    for q in range(len(fl)):
+        n = int(ref["n_steps"][q])
+        bitwise += int(np_(out["n_steps"])[q] == n and np.array_equal(path[q, :n], rpath[q, :n]))
         same = (np_(out["n_steps"])[q] == n and np_(out["status"])[q] == ref["status"][q]
                 and np_(out["n_nodes"])[q] == ref["n_nodes"][q]
-                and np.allclose(path[q, :n], rpath[q, :n], rtol=1e-7, atol=1e-9))
+                and np.allclose(path[q, :n], rpath[q, :n], rtol=1e-12, atol=1e-13)
+                and np.array_equal(np_(out["node_step"])[q, :ref["n_nodes"][q]],
+                                   np.asarray(ref["node_step"])[q, :ref["n_nodes"][q]])
+                and (ref.get("ctrl_idx") is None or np.array_equal(np_(out["ctrl_idx"])[q, :n], ref["ctrl_idx"][q, :n])))
         if not same:
-            assert fl[q] & 2, f"{what}: extension {q} differs without a near-tie report"
+            assert fl[q] != 0, f"{what}: extension {q} differs from the oracle without a report"
             diverged += 1
-            continue
-        k = ref["n_nodes"][q]
-        assert np.array_equal(np_(out["node_step"])[q, :k], np.asarray(ref["node_step"])[q, :k])
-        if fl[q] == 0:
-            np.testing.assert_allclose(path[q, :n], rpath[q, :n], rtol=1e-9, atol=1e-11)
-            if ref.get("ctrl_idx") is not None:
-                assert np.array_equal(np_(out["ctrl_idx"])[q, :n], ref["ctrl_idx"][q, :n])
-    assert diverged <= max(1, int(0.05 * len(fl))), f"{what}: {diverged} near-tie extensions diverged"
-    return dict(clean=int(clean.sum()), tie=int(((fl & 2) != 0).sum()), diverged=diverged)
+    assert diverged <= max_diverged, f"{what}: {diverged} reported extensions differ from the oracle"
+    assert bitwise >= 0.98 * len(fl), f"{what}: only {bitwise} of {len(fl)} extensions bit-identical"
+    return dict(clean=int((fl == 0).sum()), tie=int(((fl & 2) != 0).sum()), diverged=diverged)
 
 
 @pytest.mark.parametrize("mname", ("test_env1", "test_env2"))
@@ -60,9 +59,10 @@ def test_steer_dwa_golden(mname):
     assert np.array_equal(np_(out["n_steps"])[clean], g[mname + "_nsteps"][clean])
     assert np.array_equal(np_(out["status"])[clean], g[mname + "_status"][clean])
     assert np.array_equal(np_(out["n_nodes"])[clean], g[mname + "_nnodes"][clean])
+    assert clean.mean() >= 0.9
     for q in np.where(clean)[0]:
         n = g[mname + "_nsteps"][q]
-        np.testing.assert_allclose(np_(out["path"])[q, :n], g[mname + "_path"][q, :n], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(np_(out["path"])[q, :n], g[mname + "_path"][q, :n], rtol=1e-12, atol=1e-13)
 
 
 def test_extend_vs_oracle_many():
@@ -73,19 +73,28 @@ def test_extend_vs_oracle_many():
     targets = random_states(rng, 300)
     out = _extend(env, froms, targets)
     ref = orc.Dwa(o, dt=0.2, v_res=0.02).extend_batch(froms, targets, want_ctrl=True)
-    _compare(out, ref, "test_env1", min_clean=0.8)
+    _compare(out, ref, "test_env1", max_flagged=0.05, max_diverged=1)
     assert set(np.unique(ref["status"])) == {0, 1, 2}
 
 
 def test_extend_dense_map_vs_oracle():
-    """cfg4 shape: 10,004 obstacles, ~4096-rollout windows."""
-    from crl_kino_b200.workloads import DENSE_DWA, dense_map, query_pairs
-    rects = dense_map()
-    env, o = make_envs(rects)
-    s, g = query_pairs(lambda c: o.valid_state_batch(c)[1], 24)
-    out = _extend(env, s, g, **DENSE_DWA)
-    ref = orc.Dwa(o, **DENSE_DWA).extend_batch(s, g, want_ctrl=True)
-    _compare(out, ref, "dense")
+    """BASELINE config 4's shape at half its batch: 10,004 obstacles, ~4096-rollout windows, 512 extensions
+    of the shared bench workload (workloads.cfg4_workload: nearest tree node -> accepted sample) against
+    the threaded oracle: every unreported extension identical down to the chosen rollout of every control
+    step and the last bit of every executed state."""
+    from crl_kino_b200.workloads import DENSE_DWA, cfg4_workload
+    Q = 512
+    w = cfg4_workload(Q=Q, tree_nodes=1024, n_batches=1, seed=100)
+    env, o = make_envs(w["rects"])
+    tr, smp = w["trees"], w["batches"][0]
+    idx, _ = orc.nearest_batch(np.ascontiguousarray(tr[:, :, 0]), np.ascontiguousarray(tr[:, :, 1]),
+                               np.full(Q, tr.shape[1], dtype=np.int32), smp)
+    froms = tr[np.arange(Q), idx]
+    out = _extend(env, froms, smp, **DENSE_DWA)
+    ref = orc.Dwa(o, **DENSE_DWA).extend_batch(froms, smp, want_ctrl=True)
+    r = _compare(out, ref, "dense", max_flagged=0.15, max_diverged=2)
+    assert r["clean"] >= 0.85 * Q
+    assert int(ref["n_steps"].max()) >= 40 and set(np.unique(ref["status"])) >= {1, 2}
 
 
 def test_extend_inactive_and_empty():
@@ -123,8 +132,8 @@ def test_rrt_class_reproduces_reference_run(run, seed):
     assert p.n_control_steps == int(g[f"run{run}_ctrl_steps"])
     assert np.array_equal(parents, g[f"run{run}_parents"])
     assert np.array_equal(np.array([len(n.path) for n in p.node_list]), g[f"run{run}_plen"])
-    np.testing.assert_allclose(states, g[f"run{run}_node_states"], rtol=1e-9, atol=1e-11)
-    np.testing.assert_allclose(np.array(path), g[f"run{run}_path"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(states, g[f"run{run}_node_states"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(np.array(path), g[f"run{run}_path"], rtol=1e-12, atol=1e-13)
     assert p.reach_exactly == bool(g[f"run{run}_reach"])
 
 
@@ -194,6 +203,6 @@ def test_rrt_class_contract_size(seed):
         pytest.skip("a reported near-tie / near-boundary decision went the other way")
     assert p.n_extend_calls == int(g[f"run{seed}_extensions"])
     assert p.n_control_steps == int(g[f"run{seed}_ctrl_steps"])
-    np.testing.assert_allclose(states, g[f"run{seed}_node_states"], rtol=1e-9, atol=1e-11)
-    np.testing.assert_allclose(np.array(path), g[f"run{seed}_path"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(states, g[f"run{seed}_node_states"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(np.array(path), g[f"run{seed}_path"], rtol=1e-12, atol=1e-13)
     assert p.reach_exactly == bool(g[f"run{seed}_reach"])
