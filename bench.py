@@ -61,6 +61,7 @@ def parse():
                     help="enable the per-rollout clearance term (dwa.py:64-69); GPU legs only")
     ap.add_argument("--no-extra", action="store_true", help="skip the planning / nearest / MLP side measurements")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained step loop (0 = skip)")
+    ap.add_argument("--pipe-depth", type=int, default=3, help="independent steps in flight of the end-to-end arm")
     ap.add_argument("--plan-iters", type=int, default=100, help="max_iter of the planning-queries/s leg")
     ap.add_argument("--plan-queries", type=int, default=0, help="queries per GPU of the planning leg (0 = --queries)")
     ap.add_argument("--plan-lockstep", action="store_true", help="also time the lock-step planner (BatchedRRT)")
@@ -818,7 +819,7 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
     batches = wl["batches"]
     forest = Forest(Q, args.tree_nodes)
     forest.fill(wl["trees"])
-    ext = BatchedExtender(env, forest, dwa=dwa)
+    ext = BatchedExtender(env, forest, dwa=dwa, pipe_depth=args.pipe_depth)
     dev_batches = ops.as_dev(batches)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -870,22 +871,24 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
 
     # ---- end-to-end arm: host buffers through the public API -------------------
     # submit_host / collect: every step stages its samples in pinned memory, copies them to the
-    # device, runs nearest + gather + extension and copies path / status / nodes back; two steps are
-    # in flight so that the D2H of step k overlaps the kernels of step k + 1.
+    # device, runs nearest + gather + extension and copies path / status / nodes back; up to three
+    # steps are in flight, each on its own stream, so that the D2H of a step overlaps the kernels of the
+    # next and the next step's extensions fill the SMs that the tail of a step leaves idle.
+    from collections import deque
     for w in range(W):
         ext.collect(ext.submit_host(batches[w]))
     barrier()
     t0 = time.perf_counter()
-    pending = None
+    pending = deque()
     n_checked = 0
     for k in range(K):
-        t = ext.submit_host(batches[W + k])
-        if pending is not None:
-            res = ext.collect(pending)
+        pending.append(ext.submit_host(batches[W + k]))
+        if len(pending) == ext.pipe_depth:             # oldest step's results (pinned host memory)
+            res = ext.collect(pending.popleft())
             n_checked += int(res["n_steps"].shape[0])
-        pending = t
-    res = ext.collect(pending)
-    n_checked += int(res["n_steps"].shape[0])
+    while pending:
+        res = ext.collect(pending.popleft())
+        n_checked += int(res["n_steps"].shape[0])
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     assert n_checked == K * Q
@@ -964,7 +967,7 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
                                                       "reached": int((status == 2).sum())}},
         "e2e": {"value": tot_ext / t_e2e_max, "unit": "extensions/s",
                 "h2d_bytes_per_step": ext.h2d_bytes(), "d2h_bytes_per_step": ext.d2h_bytes(),
-                "api": "BatchedExtender.submit_host / collect (two steps in flight)",
+                "api": f"BatchedExtender.submit_host / collect ({ext.pipe_depth} independent steps in flight, one stream each)",
                 "one_step_at_a_time_rank0": Q * K / t_e2e_sync},
         "gpu_launches": K * ext.launches_per_step,
         "kernel_ms_per_step": {"nearest": t_near / K, "gather": t_gath / K, "extend_dwa": t_ext / K},

@@ -63,8 +63,10 @@ class Forest:
 class BatchedExtender:
     """nearest -> gather -> extend for Q queries per call."""
 
-    def __init__(self, env, forest, dwa=None, policy=None, eps=0.0, t_max_extend=10.0, t_tree=5.0, rl_chunk=8192):
+    def __init__(self, env, forest, dwa=None, policy=None, eps=0.0, t_max_extend=10.0, t_tree=5.0, rl_chunk=8192,
+                 pipe_depth=3):
         self.env = env
+        self.pipe_depth = max(2, int(pipe_depth))   # steps in flight of submit_host / collect
         self.rl_chunk = rl_chunk      # policy steering: queries per crlk_extend_rl pass (bounds its workspace)
         self.forest = forest
         self.dwa = dwa
@@ -147,34 +149,41 @@ class BatchedExtender:
     def _pipe_init(self):
         d = self.forest.states.device
         self._pipe = []
-        for _ in range(2):
+        for _ in range(self.pipe_depth):
             self._pipe.append(dict(
                 h_in=torch.empty_like(self._h_samples).pin_memory(), d_in=torch.empty_like(self._d_samples),
                 h_out={k: torch.empty_like(v).pin_memory() for k, v in self._h_out.items()},
                 out=None, from_states=torch.empty_like(self.from_states),
+                stream=torch.cuda.Stream(device=d),
                 done=torch.cuda.Event(), copied=torch.cuda.Event(), busy=False))
         self._copy_stream = torch.cuda.Stream(device=d)
         self._slot = 0
 
     def submit_host(self, samples_np):
         """Asynchronous form of step_host: stages the samples (pinned) and enqueues H2D, the step and the
-        D2H of its results; returns a ticket for collect().  Two steps may be in flight, so the D2H of one
-        step overlaps the kernels of the next.  Every step still moves its own inputs and results."""
+        D2H of its results; returns a ticket for collect().  pipe_depth steps may be in flight, each on its
+        own stream: the D2H of one step overlaps the kernels of the next, and -- a batch of extensions ends
+        when its longest one does -- the next step's extensions fill the SMs that the tail of the
+        previous step leaves idle.  Steps are independent (a step reads the forest, it does not grow
+        it); every step still moves its own inputs and results."""
         if not hasattr(self, "_pipe"):
             self._pipe_init()
         i = self._slot
-        self._slot ^= 1
+        self._slot = (self._slot + 1) % self.pipe_depth
         s = self._pipe[i]
         if s["busy"]:
             s["copied"].synchronize()              # the slot's previous results must have been collected / copied
         s["h_in"].numpy()[...] = samples_np
-        s["d_in"].copy_(s["h_in"], non_blocking=True)
-        keep_out, keep_from = self.out, self.from_states
-        self.out, self.from_states = s["out"], s["from_states"]
-        out = self.step(s["d_in"])
-        s["out"] = out
-        self.out, self.from_states = keep_out, keep_from
-        s["done"].record()
+        cur = torch.cuda.current_stream()
+        s["stream"].wait_stream(cur)               # whatever the caller enqueued so far (forest updates) comes first
+        with torch.cuda.stream(s["stream"]):
+            s["d_in"].copy_(s["h_in"], non_blocking=True)
+            keep_out, keep_from = self.out, self.from_states
+            self.out, self.from_states = s["out"], s["from_states"]
+            out = self.step(s["d_in"])
+            s["out"] = out
+            self.out, self.from_states = keep_out, keep_from
+            s["done"].record()
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(s["done"])
             for k, h in s["h_out"].items():
@@ -185,7 +194,7 @@ class BatchedExtender:
 
     def collect(self, ticket):
         """Results of a submit_host() call as numpy views of pinned memory (valid until the slot is reused
-        two submissions later)."""
+        pipe_depth submissions later)."""
         s = self._pipe[ticket]
         s["copied"].synchronize()
         s["busy"] = False
