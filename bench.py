@@ -98,7 +98,9 @@ def load_ncu(name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons under load.  The sampler is started ahead of the load
+    (nvidia-smi needs a few hundred ms to print its first row); every row is stamped on arrival and
+    stop() keeps the rows that fall inside the given windows of time.perf_counter()."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
         "clocks_event_reasons.sw_power_cap"
@@ -117,16 +119,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        """Block until nvidia-smi has printed its first row (so the load that follows is sampled)."""
+        t0 = time.perf_counter()
+        while self.p is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, windows=None):
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            # a row printed up to one sampling period after a window still describes it
+            if windows is not None and not any(a <= t <= b + 0.03 for a, b in windows):
+                continue
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -658,18 +669,20 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
     goals = ops.as_dev(free_states(clearance, rng, Q, 0.5, batch=1 << 17))
     ext = BatchedExtender(env, forest, policy=pol, eps=0.0, rl_chunk=8192)
     ext.extend_targets = goals
+    sampler = ClockSampler(local_rank)
+    sampler.wait_first()
+    t_load0 = time.perf_counter()
     for w in range(W):
         ext.step(samples[w])
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    sampler = ClockSampler(local_rank)
     barrier()
     policy_evals = 0
     for k in range(K):
         out = ext.step(samples[W + k], events=evs[k])
         policy_evals += out["n_steps"].sum(dtype=torch.int64)
     barrier()
-    clocks = sampler.stop()
+    clock_windows = [(t_load0, time.perf_counter())]
     t_near = sum(e[0].elapsed_time(e[1]) for e in evs)
     t_ext = sum(e[2].elapsed_time(e[3]) for e in evs)
     step_ms = [e[0].elapsed_time(e[3]) for e in evs]
@@ -699,6 +712,7 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
             gather_bytes = int(sum(v.numel() * v.element_size() for v in res.values()))
     # ---- end to end: samples from pinned host memory, results back to the host, every step
     hs = [s.cpu().numpy() for s in samples]
+    t_load0 = time.perf_counter()
     ext.step_host(hs[0])
     barrier()
     t0 = time.perf_counter()
@@ -706,6 +720,9 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
         ext.step_host(hs[W + k])
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    clock_windows.append((t_load0, time.perf_counter()))
+    clocks = sampler.stop(clock_windows)
+    clocks["window"] = "warm-up + timed steps and the end-to-end loop of this leg (same step, same load)"
     red = torch.tensor([t_total, t_e2e, t_near, t_ext, gather_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([float(Q * K), policy_evals, float(Q)], dtype=torch.float64, device="cuda")
     per_rank = [t_total / K]
@@ -830,8 +847,10 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
     ext.stats.zero_()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     sampler = ClockSampler(local_rank)
+    sampler.wait_first()
     barrier()
     torch.cuda.profiler.start()          # ncu --profile-from-start off captures only the timed region
+    t_load0 = time.perf_counter()
     t_wall = time.time()
     for k in range(K):
         flush.fill_(k & 0xff)                      # L2 flush between timed iterations (untimed)
@@ -839,7 +858,6 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
     barrier()
     t_wall = time.time() - t_wall
     torch.cuda.profiler.stop()
-    clocks = sampler.stop()
     t_near = sum(e[0].elapsed_time(e[1]) for e in evs)
     t_gath = sum(e[1].elapsed_time(e[2]) for e in evs)
     t_ext = sum(e[2].elapsed_time(e[3]) for e in evs)
@@ -868,6 +886,9 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
                      "value_rank0": Q * n_done / (ms_sum * 1e-3),
                      "note": "same loop as the timed region over all K + W batches, cyclic, L2 flushed between steps; "
                              "per-step CUDA-event time summed"}
+
+    clocks = sampler.stop([(t_load0, time.perf_counter())])
+    clocks["window"] = "timed region + the sustained loop that follows it (same step loop)"
 
     # ---- end-to-end arm: host buffers through the public API -------------------
     # submit_host / collect: every step stages its samples in pinned memory, copies them to the
