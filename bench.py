@@ -442,8 +442,10 @@ def _cpu_plan_rl_one(a):
     try:
         p.planning(iter(stream))
     except StopIteration:
-        return p.n_extend_calls, False, -1
-    return p.n_extend_calls, bool(p.reach_exactly), len(p.node_list)
+        # the pre-drawn stream ran out inside the rejection loop (rrt.py:64-69 has no cap; the lock-step
+        # planner stops such a query with the tree it has): same stop, compare the tree built so far
+        return p.n_extend_calls, False, len(p.node_list), True
+    return p.n_extend_calls, bool(p.reach_exactly), len(p.node_list), False
 
 
 def planning_rl_leg(args, env, rects, no_cpu):
@@ -509,6 +511,7 @@ def planning_rl_leg(args, env, rects, no_cpu):
             g = res[name]
             out[name]["cpu_baseline"] = {"queries_per_sec": n / dt, "queries": n, "seconds": dt, "cores": cores, "kind": "port",
                                          "extensions": int(sum(x[0] for x in r)),
+                                         "stopped_on_exhausted_stream": int(sum(1 for x in r if x[3])),
                                          "same_reach_and_node_count_as_gpu": int(sum(1 for q in range(n) if r[q][1] == bool(g["reached"][q]) and
                                                                                      r[q][2] == int(g["nodes"][q])))}
     return out
