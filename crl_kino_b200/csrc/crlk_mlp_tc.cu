@@ -175,6 +175,71 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int m, i
     }
 }
 
+// The same epilogue with coalesced global stores (persistent and CTA-pair kernels).  A thread owns one
+// accumulator ROW (TMEM lane), so a direct store instruction touches 32 different cache lines with 16 B
+// each -- 192 such instructions per 128 x 128 tile made the epilogue, not the MMAs or the operand
+// traffic, the longest phase of a tile.  Here the warp's 32 rows x 32 columns pass through a per-warp
+// staging buffer in shared memory (XOR-swizzled 16 B pieces: conflict free both ways) and every
+// store instruction then writes whole row segments: 8 rows x 64 B of a bf16 plane or 4 rows x 128 B
+// of the float32 output.  nplanes = operand planes the next layer reads (2 in the three-product mode).
+#define TC_STG_WARP_BYTES 6144                      // 3 planes x 32 rows x 64 B (float32: 32 rows x 128 B)
+#define TC_STG_BYTES (4 * TC_STG_WARP_BYTES)
+__device__ __forceinline__ void epilogue_store_staged(const uint32_t (&r)[32], int m_base, int lane, int n,
+                                                      const float *__restrict__ bias, int B, int Mpad,
+                                                      __nv_bfloat16 *__restrict__ planes_out, int ld_out, int nplanes,
+                                                      float *__restrict__ c32, int ldc, uint4 *stg)
+{
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = fmaxf(__uint_as_float(r[j]) + __ldg(&bias[n + j]), 0.f);
+    if (c32) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            stg[lane * 8 + (j ^ (lane & 7))] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                          __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int row = 4 * i + (lane >> 3), j = lane & 7, m = m_base + row;
+            const uint4 x = stg[row * 8 + (j ^ (row & 7))];
+            if (m < B) *reinterpret_cast<uint4 *>(c32 + (size_t)m * ldc + n + 4 * j) = x;
+        }
+        __syncwarp();
+    }
+    if (planes_out) {
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t a[4], b[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                __nv_bfloat16 a0, b0, c0, a1, b1, c1;
+                split3(v[8 * j + 2 * u], a0, b0, c0);
+                split3(v[8 * j + 2 * u + 1], a1, b1, c1);
+                a[u] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
+                b[u] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                c[u] = (uint32_t)__bfloat16_as_ushort(c0) | ((uint32_t)__bfloat16_as_ushort(c1) << 16);
+            }
+            stg[lane * 4 + (j ^ sw)] = make_uint4(a[0], a[1], a[2], a[3]);
+            stg[128 + lane * 4 + (j ^ sw)] = make_uint4(b[0], b[1], b[2], b[3]);
+            if (nplanes > 2) stg[256 + lane * 4 + (j ^ sw)] = make_uint4(c[0], c[1], c[2], c[3]);
+        }
+        __syncwarp();
+        const size_t plane = (size_t)Mpad * ld_out;
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+            if (pl >= nplanes) continue;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int row = 8 * i + (lane >> 2), j = lane & 3, m = m_base + row;
+                const uint4 x = stg[pl * 128 + row * 4 + (j ^ ((row >> 1) & 3))];
+                if (m < B) *reinterpret_cast<uint4 *>(planes_out + pl * plane + (size_t)m * ld_out + n + 8 * j) = x;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ the GEMM
 
 // planes_out: [3][Mpad][ld_out] bf16 (nullable), c32: [B][ldc] float (nullable).
@@ -354,6 +419,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+#define TCP_SMEM_BYTES (TCF_SMEM_BYTES + TC_STG_BYTES)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                       int Mpad, int N, int kblocks, const float *__restrict__ bias, int B,
@@ -383,6 +449,8 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = N / TC_BN, tiles = tiles_n * ((B + TC_BM - 1) / TC_BM);     // Mpad is the plane pitch
+    // per-warp staging buffers of the epilogue, behind the 256 bytes of barriers
+    uint4 *stg = reinterpret_cast<uint4 *>(gen + TCF_STAGES * TCF_STAGE_BYTES + 256 + (warp & 3) * TC_STG_WARP_BYTES);
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < nst; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -451,7 +519,6 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ti++) {
             const int as = ti & 1, aph = (ti >> 1) & 1;
             const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * TC_BN;
-            const int m = m0 + 32 * q + lane;
             mbar_wait(tfull0 + 8 * as, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -464,7 +531,9 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty0 + 8 * as);
                 }
-                if (m < B) epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
+                if (m0 + 32 * q < B)       // warp-uniform: some row of this warp is live
+                    epilogue_store_staged(r, m0 + 32 * q, lane, n0 + 32 * c, bias, B, Mpad, planes_out, ld_out, npl,
+                                          c32, ldc, stg);
             }
         }
     }
@@ -495,7 +564,8 @@ template <int PBN> struct PairCfg {
     static constexpr int b_bytes = 3 * b_plane;
     static constexpr int stage = TCP_A_BYTES + b_bytes;           // 72 KB (PBN 128) / 96 KB (PBN 256)
     static constexpr int stages = (PBN == 128) ? 3 : 2;
-    static constexpr int smem = stages * stage + 1024 + 256;
+    static constexpr int stg = (PBN == 256) ? TC_STG_BYTES : 0;    // epilogue staging (the 128-column ring leaves no room)
+    static constexpr int smem = stages * stage + 1024 + 256 + stg;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -563,6 +633,7 @@ k_gemm_bf16x3_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + PairCfg<PBN>::stages * PairCfg<PBN>::stage + 16 * PairCfg<PBN>::stages + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *stg = reinterpret_cast<uint4 *>(gen + PairCfg<PBN>::stages * PairCfg<PBN>::stage + 256 + (warp & 3) * TC_STG_WARP_BYTES);
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int tiles_n = N / PBN, tiles = tiles_n * ((B + 2 * TC_BM - 1) / (2 * TC_BM));   // 256-row pair tiles
@@ -653,7 +724,12 @@ k_gemm_bf16x3_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(tempty0 + 8 * as);
                 }
-                if (m < B) epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
+                if (PairCfg<PBN>::stg) {
+                    if (m0 + 32 * q < B)
+                        epilogue_store_staged(r, m0 + 32 * q, lane, n0 + 32 * c, bias, B, Mpad, planes_out, ld_out, npl,
+                                              c32, ldc, stg);
+                } else if (m < B)
+                    epilogue_store(r, m, n0 + 32 * c, bias, Mpad, planes_out, ld_out, c32, ldc);
             }
         }
     }
@@ -798,7 +874,7 @@ int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_ho
     }
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
-    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::smem));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::smem));
     *out = t;
@@ -880,7 +956,7 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
         else if (persist || need_persist) {
             int tiles = (L.N / TC_BN) * (Mpad / TC_BM);
             int ctas = tiles < n_sms ? tiles : n_sms;
-            k_gemm_bf16x3_persist<<<ctas, TC_THREADS, TCF_SMEM_BYTES, st>>>(
+            k_gemm_bf16x3_persist<<<ctas, TC_THREADS, TCP_SMEM_BYTES, st>>>(
                 mapA, L.map_w, Mpad, L.N, kblocks, d_bias[i], B,
                 is_last ? nullptr : pl[(i + 1) & 1], L.N, is_last ? last : nullptr, L.N, n_rows_dev,
                 (i == 0 && a_lo_kb > 0) ? a_lo_kb : kblocks, t->nprod);
