@@ -546,6 +546,211 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 
+// ---------------------------------------------------------------- all hidden layers in ONE launch
+// Between the steps of the RL extension the batch is a few thousand rows: a layer is 90-360 tiles,
+// i.e. 0.6-2.4 waves of the 148 SMs, and each of the four per-layer launches pays its own prologue,
+// pipeline fill, partial last wave and drain (measured: 21-42 us per layer at 8192 rows against
+// 5-11 us of MMA time).  This kernel runs the whole chain of layers as one persistent grid with a
+// DATAFLOW schedule: the tiles of all layers form one global list (layer-major, row-tile-major inside a
+// layer) that the CTAs pull from with an atomic counter; a tile of layer l needs row tile m of layer
+// l - 1 complete (all its column tiles), which the epilogue warps publish with a release-add on
+// done[l - 1][m] and the TMA producer acquires before it loads the A operand (the W tiles of the first k
+// block are requested before the wait).  So the SMs that a layer's last wave leaves idle already run the
+// next layer's first row tiles, and nothing is launched or drained in between.
+// Deadlock freedom does not depend on all CTAs being resident: a tile only waits for tiles with smaller
+// indices, and those were pulled by CTAs that are running.
+// Activations live in two ping-pong plane buffers with ONE row pitch (ld_planes), so row tile m of layer
+// l + 1's output may overwrite row tile m of layer l's input: every reader of those rows (the tiles
+// (l, m, *)) has completed by then.  The first layer's input planes are a third buffer.
+#define TCC_MAX_LAYERS 4
+#define TCC_RING 8
+struct ChainP {
+    CUtensorMap tmA[TCC_MAX_LAYERS];
+    CUtensorMap tmW[TCC_MAX_LAYERS];
+    const float *bias[TCC_MAX_LAYERS];
+    __nv_bfloat16 *out_planes[TCC_MAX_LAYERS];      // null for the last layer (float32 output `last`)
+    float *last;
+    const int *n_rows_dev;
+    int *ctrl;                                       // [0] tile counter; [64 + l * row_tiles_max + m] epilogue warps done
+    int N[TCC_MAX_LAYERS], kblocks[TCC_MAX_LAYERS];
+    int n_layers, Mpad, B, ld_planes, ld_last, a_lo_kb, nprod, row_tiles_max;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void red_release_gpu_add(int *p, int v)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_mlp_chain(const __grid_constant__ ChainP p)
+{
+    int B = p.B;
+    if (p.n_rows_dev) B = min(B, *p.n_rows_dev);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int npl = p.nprod == 6 ? 3 : 2, nst = p.nprod == 6 ? 2 : 3;
+    const uint32_t stage_bytes = (uint32_t)(2 * npl) * TC_STAGE_BYTES;
+    const uint32_t bars = base + TCF_STAGES * TCF_STAGE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 24, tfull0 = bars + 48, tempty0 = bars + 64, tslot = bars + 80;
+    const uint32_t tq0 = bars + 96;                                    // TCC_RING tile-queue barriers, then the tile ids
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tslot_ptr = (volatile uint32_t *)(gen + TCF_STAGES * TCF_STAGE_BYTES + 80);
+    volatile int *tile_ids = (volatile int *)(gen + TCF_STAGES * TCF_STAGE_BYTES + 96 + 8 * TCC_RING);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *stg = reinterpret_cast<uint4 *>(gen + TCF_STAGES * TCF_STAGE_BYTES + 256 + (warp & 3) * TC_STG_WARP_BYTES);
+
+    const int row_tiles = (B + TC_BM - 1) / TC_BM;
+    int total = 0;
+    for (int l = 0; l < p.n_layers; l++) total += row_tiles * (p.N[l] / TC_BN);
+    auto decode = [&](int t, int &l, int &m0, int &n0) {
+        l = 0;
+        while (t >= row_tiles * (p.N[l] / TC_BN)) { t -= row_tiles * (p.N[l] / TC_BN); l++; }
+        const int tn = p.N[l] / TC_BN;
+        m0 = (t / tn) * TC_BM; n0 = (t % tn) * TC_BN;
+    };
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 3; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int i = 0; i < TCC_RING; i++) mbar_init(tq0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(2 * TC_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ---- tile scheduler + TMA producer
+        int git = 0;
+        for (int ti = 0;; ti++) {
+            int t = atomicAdd(&p.ctrl[0], 1);
+            if (t >= total) t = -1;
+            // the ring slot's previous tile (ti - TCC_RING) was read by every consumer long ago: the MMA thread
+            // is at most one tile behind (3-stage ring, >= 8 k blocks per tile) and it cannot start tile j
+            // before all epilogue warps have taken up tile j - 2
+            tile_ids[ti & (TCC_RING - 1)] = t;
+            mbar_arrive(tq0 + 8 * (ti & (TCC_RING - 1)));
+            if (t < 0) break;
+            int l, m0, n0;
+            decode(t, l, m0, n0);
+            const int kblocks = p.kblocks[l], a_lo = (l == 0 && p.a_lo_kb > 0) ? p.a_lo_kb : kblocks;
+            const CUtensorMap *mA = &p.tmA[l], *mW = &p.tmW[l];
+            const int N = p.N[l];
+            for (int kb = 0; kb < kblocks; kb++, git++) {
+                int s = git % nst, ph = (git / nst) & 1;
+                uint32_t st = base + s * stage_bytes;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const bool lo = kb < a_lo;
+                mbar_expect_tx(full0 + 8 * s, ((lo ? npl : 1) + npl) * TC_STAGE_BYTES);
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++)
+                    if (pl < npl) tma_load_2d(st + (npl + pl) * TC_STAGE_BYTES, mW, kb * TC_BK, pl * N + n0, full0 + 8 * s);
+                if (kb == 0 && l > 0) {
+                    // row tile m of the previous layer: all column tiles stored by all four epilogue warps
+                    const int *flag = p.ctrl + 64 + (l - 1) * p.row_tiles_max + m0 / TC_BM;
+                    const int need = 4 * (p.N[l - 1] / TC_BN);
+                    for (uint32_t spin = 0; ld_acquire_gpu(flag) < need; spin++)
+                        if (spin > (1u << 24)) __trap();
+                    asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> this thread's TMA reads
+                }
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++)
+                    if (pl < npl && (pl == 0 || lo))
+                        tma_load_2d(st + pl * TC_STAGE_BYTES, mA, kb * TC_BK, pl * p.Mpad + m0, full0 + 8 * s);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+        int git = 0;
+        for (int ti = 0;; ti++) {
+            mbar_wait(tq0 + 8 * (ti & (TCC_RING - 1)), (ti / TCC_RING) & 1);
+            const int t = tile_ids[ti & (TCC_RING - 1)];
+            if (t < 0) break;
+            int l, m0, n0;
+            decode(t, l, m0, n0);
+            const int kblocks = p.kblocks[l], a_lo = (l == 0 && p.a_lo_kb > 0) ? p.a_lo_kb : kblocks;
+            const int as = ti & 1, aph = (ti >> 1) & 1;
+            mbar_wait(tempty0 + 8 * as, aph ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + (uint32_t)(as * TC_BN);
+            for (int kb = 0; kb < kblocks; kb++, git++) {
+                int s = git % nst, ph = (git / nst) & 1;
+                uint32_t st = base + s * stage_bytes;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool lo = kb < a_lo;
+#pragma unroll
+                for (int pair = 0; pair < TC_NPAIR; pair++) {
+                    if (!lo && c_pair_a[pair] != 0) continue;
+                    if (pair >= p.nprod) continue;
+                    uint64_t da = umma_desc_sw128(st + c_pair_a[pair] * TC_STAGE_BYTES);
+                    uint64_t db = umma_desc_sw128(st + (npl + c_pair_w[pair]) * TC_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        umma_bf16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | pair | k) != 0);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(tfull0 + 8 * as);
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue
+        const int q = warp & 3;
+        for (int ti = 0;; ti++) {
+            mbar_wait(tq0 + 8 * (ti & (TCC_RING - 1)), (ti / TCC_RING) & 1);
+            const int t = tile_ids[ti & (TCC_RING - 1)];
+            if (t < 0) break;
+            int l, m0, n0;
+            decode(t, l, m0, n0);
+            const bool is_last = l == p.n_layers - 1;
+            const int as = ti & 1, aph = (ti >> 1) & 1;
+            mbar_wait(tfull0 + 8 * as, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * TC_BN + 32 * c), r);
+                if (c == TC_BN / 32 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+                }
+                if (m0 + 32 * q < B)
+                    epilogue_store_staged(r, m0 + 32 * q, lane, n0 + 32 * c, p.bias[l], B, p.Mpad,
+                                          is_last ? nullptr : p.out_planes[l], p.ld_planes, npl,
+                                          is_last ? p.last : nullptr, p.ld_last, stg);
+            }
+            if (!is_last) {
+                // publish: this warp's rows of tile (l, m, n) are in global memory
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) red_release_gpu_add(p.ctrl + 64 + l * p.row_tiles_max + m0 / TC_BM, 1);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TC_BN));
+    }
+}
+
+
 // ---------------------------------------------------------------- CTA-pair variant
 // Two CTAs of a cluster (two SMs of a TPC) work on one 256 x 128 output tile with
 // tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the W tile
@@ -875,6 +1080,7 @@ int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_ho
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_mlp_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::smem));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::smem));
     *out = t;
@@ -894,7 +1100,9 @@ size_t crlk_tc_workspace_bytes(const CrlkPolicyTc *t, int B)
     size_t Mpad = (size_t)rup(B, TC_BM);
     size_t planes = 3 * Mpad * t->max_width * sizeof(uint16_t);
     size_t last = Mpad * t->layer[t->n_hidden - 1].N * sizeof(float);
-    return 2 * planes + last + 1024;
+    // + the third plane buffer and the control words of the one-launch chain (k_mlp_chain)
+    size_t ctrl = (64 + (size_t)TCC_MAX_LAYERS * (Mpad / TC_BM)) * sizeof(int);
+    return 3 * planes + last + ((ctrl + 255) & ~(size_t)255) + 1024;
 }
 
 // The layer-0 operand planes inside a workspace: [3][Mpad][Kp0] bf16.
@@ -922,6 +1130,42 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
     static int n_sms = 0;
     if (!n_sms) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dv); }
     const bool need_persist = n_rows_dev != nullptr || a_lo_kb > 0 || t->nprod != 6;
+    // Small and mid-size batches: all hidden layers in one dataflow launch (k_mlp_chain).  CRLK_MLP_CHAIN=0
+    // restores one launch per layer (the A/B switch; results are identical -- same tiles, same k order).
+    static const int chain_env = getenv("CRLK_MLP_CHAIN") ? atoi(getenv("CRLK_MLP_CHAIN")) : 1;
+    static const int pair_forced = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
+    if (chain_env && !unfused && persist && t->n_hidden <= TCC_MAX_LAYERS && pair_forced <= 0 &&
+        (B < 24576 || pair_forced == 0)) {
+        float *lastbuf = last;
+        const size_t last_bytes = ((size_t)Mpad * t->layer[t->n_hidden - 1].N * sizeof(float) + 255) & ~(size_t)255;
+        __nv_bfloat16 *X = pl[1], *Y = (__nv_bfloat16 *)((uint8_t *)last + last_bytes);
+        int *ctrl = (int *)((uint8_t *)Y + planes_bytes);
+        ChainP cp;
+        memset(&cp, 0, sizeof cp);
+        int total = 0;
+        for (int i = 0; i < t->n_hidden; i++) {
+            const TcLayer &L = t->layer[i];
+            const __nv_bfloat16 *in = i == 0 ? pl[0] : ((i - 1) % 2 == 0 ? X : Y);
+            int rc = make_map(&cp.tmA[i], in, 3ull * Mpad, L.Kp, i == 0 ? L.Kp : t->max_width);
+            if (rc) return rc;
+            cp.tmW[i] = L.map_w;
+            cp.bias[i] = d_bias[i];
+            cp.out_planes[i] = (i == t->n_hidden - 1) ? nullptr : (i % 2 == 0 ? X : Y);
+            cp.N[i] = L.N;
+            cp.kblocks[i] = L.Kp / TC_BK;
+            total += (L.N / TC_BN) * (Mpad / TC_BM);
+        }
+        cp.last = lastbuf; cp.ld_last = t->layer[t->n_hidden - 1].N;
+        cp.n_rows_dev = n_rows_dev; cp.ctrl = ctrl;
+        cp.n_layers = t->n_hidden; cp.Mpad = Mpad; cp.B = B; cp.ld_planes = t->max_width;
+        cp.a_lo_kb = a_lo_kb; cp.nprod = t->nprod; cp.row_tiles_max = Mpad / TC_BM;
+        CRLK_CUDA(cudaMemsetAsync(ctrl, 0, (64 + (size_t)t->n_hidden * cp.row_tiles_max) * sizeof(int), st));
+        k_mlp_chain<<<total < n_sms ? total : n_sms, TC_THREADS, TCP_SMEM_BYTES, st>>>(cp);
+        CRLK_LAUNCH_CHECK();
+        *out = last;
+        *ld_out = t->layer[t->n_hidden - 1].N;
+        return CRLK_OK;
+    }
     for (int i = 0; i < t->n_hidden; i++) {
         const TcLayer &L = t->layer[i];
         CUtensorMap mapA;
