@@ -560,9 +560,11 @@ def mlp_roofline(peaks):
     big[:, :733] = torch.rand(65536, 733, device="cuda")
     ms_big = timed(lambda: ops.policy_forward(h, big), 5)
     ach_big = POLICY_FLOP * 65536 / (ms_big * 1e-3) / 1e12
-    ncu = load_ncu("r2_gemm_ncu.json")
-    return {"kernel": "k_gemm_bf16x3 (+ split, head)", "bound": "tensor", "achieved": ach, "peak": peak,
-            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms": ms, "ncu": ncu,
+    ncu = load_ncu("r2_mlp_chain_ncu.json")
+    return {"kernel": "k_mlp_chain (all hidden layers in one dataflow launch) + operand split + head; "
+                      "k_gemm_bf16x3_pair<256> per layer at 65,536 rows",
+            "bound": "tensor", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak, "traffic": ncu.get("dram_bytes") if ncu else None, "ms": ms, "ncu": ncu,
             "at_65536_rows": {"achieved": ach_big, "frac": ach_big / peak, "ms": ms_big},
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "note": "algorithmic float32 FLOP (3,600,384 per sample); the kernel issues several bf16 MMAs per "
@@ -748,7 +750,8 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
     bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
     near_gbs = 8.0 * Q * N * K / (t_near * 1e-3) / 1e9
     rl_tflops = POLICY_FLOP * (evals / world) / (t_ext_m * 1e-3) / 1e12
-    ncu = load_ncu("r2_extend_rl_ncu.json")
+    ncu = load_ncu("r2_mlp_chain_ncu.json")
+    ncu_adv = load_ncu("r2_extend_rl_ncu.json")
     return {
         "metric": "rrt_extensions_per_sec", "value": tot / (t_total * 1e-3), "unit": "extensions/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_total / K, "higher_is_better": True,
@@ -771,9 +774,10 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
                                            "rank0_shard_intact": gather_ok,
                                            "skipped": bool(world == 1 or capped)},
         "gpu_launches": K * launches,
-        "roofline": {"kernel": "extend_rl (policy GEMMs k_gemm_bf16x3* + observation / head / step kernels)",
+        "roofline": {"kernel": "extend_rl = per policy step k_mlp_chain (the actor's hidden layers, ~58 % of the pass) + "
+                               "k_rl_advance (head / motion / validity / bookkeeping / next observation)",
                      "bound": "tensor", "achieved": rl_tflops, "peak": bf16, "unit": "TFLOP/s", "frac": rl_tflops / bf16,
-                     "traffic": None, "ncu": ncu,
+                     "traffic": ncu.get("dram_bytes") if ncu else None, "ncu": ncu, "ncu_step_kernel": ncu_adv,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",
                      "policy_evaluations_per_step_per_gpu": evals / world / K,
                      "note": "algorithmic float32 FLOP of the actor (3,600,384 per policy evaluation) over the executed "

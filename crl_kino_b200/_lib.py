@@ -93,6 +93,7 @@ PROTOTYPES = {
     "crlk_policy_workspace_bytes": (I64, [P, I32]),
     "crlk_extend_rl": (C.c_int, [P, P, P, P, P, I32, P, I32, P, F32, P, P, P, P, P, P, P, P, P, P]),
     "crlk_extend_rl_workspace_bytes": (I64, [P, I32]),
+    "crlk_extend_rl_launches": (I32, [P, P, I32, I32]),
     "crlk_estimator_create": (C.c_int, [P, P, P]),
     "crlk_estimator_destroy": (C.c_int, [P]),
     "crlk_estimator_forward": (C.c_int, [P, P, I32, I32, P, P, P]),

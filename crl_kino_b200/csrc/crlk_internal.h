@@ -153,6 +153,7 @@ struct CrlkPolicyTc;
 int crlk_tc_supported(const int *dims, int n_layers);
 int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_host, CrlkPolicyTc **out);
 void crlk_tc_destroy(CrlkPolicyTc *t);
+int crlk_tc_chain_rows(int B);
 size_t crlk_tc_workspace_bytes(const CrlkPolicyTc *t, int B);
 void crlk_tc_input_planes(const CrlkPolicyTc *t, void *workspace, int B, void **planes, int *Mpad, int *Kp);
 int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const float *const *d_bias,

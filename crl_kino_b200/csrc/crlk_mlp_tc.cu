@@ -588,6 +588,10 @@ __device__ __forceinline__ void red_release_gpu_add(int *p, int v)
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// BN = feature columns of a tile: 128, or 256 (three-product mode only: the A planes of a k block are then
+// fetched once per 256 output columns -- 48 KB instead of 64 KB of operand traffic per 128 x 128 x 64 block of
+// products, which is what bounds these GEMMs; two 96 KB stages, the whole TMEM as a double-buffered accumulator).
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_mlp_chain(const __grid_constant__ ChainP p)
 {
@@ -595,8 +599,9 @@ k_mlp_chain(const __grid_constant__ ChainP p)
     if (p.n_rows_dev) B = min(B, *p.n_rows_dev);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int npl = p.nprod == 6 ? 3 : 2, nst = p.nprod == 6 ? 2 : 3;
-    const uint32_t stage_bytes = (uint32_t)(2 * npl) * TC_STAGE_BYTES;
+    constexpr uint32_t WPL = BN * TC_BK * 2;                           // bytes of one W plane tile
+    const int npl = p.nprod == 6 ? 3 : 2, nst = (BN == 256 || p.nprod == 6) ? 2 : 3;
+    const uint32_t stage_bytes = (uint32_t)npl * (TC_STAGE_BYTES + WPL);
     const uint32_t bars = base + TCF_STAGES * TCF_STAGE_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 24, tfull0 = bars + 48, tempty0 = bars + 64, tslot = bars + 80;
     const uint32_t tq0 = bars + 96;                                    // TCC_RING tile-queue barriers, then the tile ids
@@ -608,12 +613,12 @@ k_mlp_chain(const __grid_constant__ ChainP p)
 
     const int row_tiles = (B + TC_BM - 1) / TC_BM;
     int total = 0;
-    for (int l = 0; l < p.n_layers; l++) total += row_tiles * (p.N[l] / TC_BN);
+    for (int l = 0; l < p.n_layers; l++) total += row_tiles * (p.N[l] / BN);
     auto decode = [&](int t, int &l, int &m0, int &n0) {
         l = 0;
-        while (t >= row_tiles * (p.N[l] / TC_BN)) { t -= row_tiles * (p.N[l] / TC_BN); l++; }
-        const int tn = p.N[l] / TC_BN;
-        m0 = (t / tn) * TC_BM; n0 = (t % tn) * TC_BN;
+        while (t >= row_tiles * (p.N[l] / BN)) { t -= row_tiles * (p.N[l] / BN); l++; }
+        const int tn = p.N[l] / BN;
+        m0 = (t / tn) * TC_BM; n0 = (t % tn) * BN;
     };
 
     if (warp == 1 && lane == 0) {
@@ -623,7 +628,7 @@ k_mlp_chain(const __grid_constant__ ChainP p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(2 * TC_BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -653,14 +658,17 @@ k_mlp_chain(const __grid_constant__ ChainP p)
                 uint32_t st = base + s * stage_bytes;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 const bool lo = kb < a_lo;
-                mbar_expect_tx(full0 + 8 * s, ((lo ? npl : 1) + npl) * TC_STAGE_BYTES);
+                mbar_expect_tx(full0 + 8 * s, (lo ? npl : 1) * TC_STAGE_BYTES + npl * WPL);
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++)
-                    if (pl < npl) tma_load_2d(st + (npl + pl) * TC_STAGE_BYTES, mW, kb * TC_BK, pl * N + n0, full0 + 8 * s);
+                    if (pl < npl)
+                        for (int hf = 0; hf < BN / 128; hf++)      // 128-row boxes of the W map
+                            tma_load_2d(st + npl * TC_STAGE_BYTES + pl * WPL + hf * TC_STAGE_BYTES, mW, kb * TC_BK,
+                                        pl * N + n0 + hf * 128, full0 + 8 * s);
                 if (kb == 0 && l > 0) {
                     // row tile m of the previous layer: all column tiles stored by all four epilogue warps
                     const int *flag = p.ctrl + 64 + (l - 1) * p.row_tiles_max + m0 / TC_BM;
-                    const int need = 4 * (p.N[l - 1] / TC_BN);
+                    const int need = 4 * (p.N[l - 1] / BN);
                     for (uint32_t spin = 0; ld_acquire_gpu(flag) < need; spin++)
                         if (spin > (1u << 24)) __trap();
                     asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> this thread's TMA reads
@@ -673,7 +681,7 @@ k_mlp_chain(const __grid_constant__ ChainP p)
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer
-        const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
         int git = 0;
         for (int ti = 0;; ti++) {
             mbar_wait(tq0 + 8 * (ti & (TCC_RING - 1)), (ti / TCC_RING) & 1);
@@ -685,7 +693,7 @@ k_mlp_chain(const __grid_constant__ ChainP p)
             const int as = ti & 1, aph = (ti >> 1) & 1;
             mbar_wait(tempty0 + 8 * as, aph ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem + (uint32_t)(as * TC_BN);
+            const uint32_t acc = tmem + (uint32_t)(as * BN);
             for (int kb = 0; kb < kblocks; kb++, git++) {
                 int s = git % nst, ph = (git / nst) & 1;
                 uint32_t st = base + s * stage_bytes;
@@ -697,7 +705,7 @@ k_mlp_chain(const __grid_constant__ ChainP p)
                     if (!lo && c_pair_a[pair] != 0) continue;
                     if (pair >= p.nprod) continue;
                     uint64_t da = umma_desc_sw128(st + c_pair_a[pair] * TC_STAGE_BYTES);
-                    uint64_t db = umma_desc_sw128(st + (npl + c_pair_w[pair]) * TC_STAGE_BYTES);
+                    uint64_t db = umma_desc_sw128(st + npl * TC_STAGE_BYTES + c_pair_w[pair] * WPL);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++)
                         umma_bf16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | pair | k) != 0);
@@ -720,10 +728,10 @@ k_mlp_chain(const __grid_constant__ ChainP p)
             mbar_wait(tfull0 + 8 * as, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; c++) {
+            for (int c = 0; c < BN / 32; c++) {
                 uint32_t r[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * TC_BN + 32 * c), r);
-                if (c == TC_BN / 32 - 1) {
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(as * BN + 32 * c), r);
+                if (c == BN / 32 - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty0 + 8 * as);
@@ -746,7 +754,7 @@ k_mlp_chain(const __grid_constant__ ChainP p)
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TC_BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN));
     }
 }
 
@@ -1080,7 +1088,8 @@ int crlk_tc_create(const int *dims, int n_layers, const float *const *weights_ho
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
-    CRLK_CUDA(cudaFuncSetAttribute(k_mlp_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_mlp_chain<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
+    CRLK_CUDA(cudaFuncSetAttribute(k_mlp_chain<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::smem));
     CRLK_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3_pair<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::smem));
     *out = t;
@@ -1143,6 +1152,13 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
         ChainP cp;
         memset(&cp, 0, sizeof cp);
         int total = 0;
+        static const int bn_env = getenv("CRLK_MLP_BN") ? atoi(getenv("CRLK_MLP_BN")) : 256;
+        // 256-column tiles pay once a layer is many waves of tiles (measured: 0.264 vs 0.298 ms at 20,000 rows,
+        // but 0.158 vs 0.148 ms at 8,192 and 8.6 vs 7.6 ms per RL extension pass); CRLK_MLP_BN=128 / 256 forces
+        static const bool bn_forced = getenv("CRLK_MLP_BN") != nullptr;
+        bool wide = bn_env == 256 && t->nprod == 3 && (bn_forced || B >= 12288);
+        for (int i = 0; i < t->n_hidden; i++) wide = wide && t->layer[i].N % 256 == 0;
+        const int BNsel = wide ? 256 : TC_BN;
         for (int i = 0; i < t->n_hidden; i++) {
             const TcLayer &L = t->layer[i];
             const __nv_bfloat16 *in = i == 0 ? pl[0] : ((i - 1) % 2 == 0 ? X : Y);
@@ -1153,14 +1169,15 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
             cp.out_planes[i] = (i == t->n_hidden - 1) ? nullptr : (i % 2 == 0 ? X : Y);
             cp.N[i] = L.N;
             cp.kblocks[i] = L.Kp / TC_BK;
-            total += (L.N / TC_BN) * (Mpad / TC_BM);
+            total += (L.N / BNsel) * (Mpad / TC_BM);
         }
         cp.last = lastbuf; cp.ld_last = t->layer[t->n_hidden - 1].N;
         cp.n_rows_dev = n_rows_dev; cp.ctrl = ctrl;
         cp.n_layers = t->n_hidden; cp.Mpad = Mpad; cp.B = B; cp.ld_planes = t->max_width;
         cp.a_lo_kb = a_lo_kb; cp.nprod = t->nprod; cp.row_tiles_max = Mpad / TC_BM;
         CRLK_CUDA(cudaMemsetAsync(ctrl, 0, (64 + (size_t)t->n_hidden * cp.row_tiles_max) * sizeof(int), st));
-        k_mlp_chain<<<total < n_sms ? total : n_sms, TC_THREADS, TCP_SMEM_BYTES, st>>>(cp);
+        if (wide) k_mlp_chain<256><<<total < n_sms ? total : n_sms, TC_THREADS, TCP_SMEM_BYTES, st>>>(cp);
+        else k_mlp_chain<128><<<total < n_sms ? total : n_sms, TC_THREADS, TCP_SMEM_BYTES, st>>>(cp);
         CRLK_LAUNCH_CHECK();
         *out = last;
         *ld_out = t->layer[t->n_hidden - 1].N;
@@ -1213,6 +1230,14 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
     *out = last;
     *ld_out = t->layer[t->n_hidden - 1].N;
     return CRLK_OK;
+}
+
+// 1 when crlk_tc_layers_forward runs a batch of B rows as one dataflow launch (k_mlp_chain).
+int crlk_tc_chain_rows(int B)
+{
+    static const int chain_env = getenv("CRLK_MLP_CHAIN") ? atoi(getenv("CRLK_MLP_CHAIN")) : 1;
+    static const int pair_forced = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
+    return chain_env && pair_forced <= 0 && (B < 24576 || pair_forced == 0);
 }
 
 // Hidden layers: obs (float32) -> float32 activations of the last hidden layer.

@@ -689,10 +689,14 @@ static size_t rl_carve(const CrlkPolicy *p, int Q, unsigned char *base, RlWs *w)
 
 // Large batches are run as 2 or 4 slices on as many streams (see crlk_extend_rl).
 #define RL_MAX_SPLIT 4
-static int rl_splits(int Q)
+static int rl_splits(int Q, bool tc)
 {
     static const char *env = getenv("CRLK_RL_SPLIT");
     if (env) { int v = atoi(env); return v >= 4 ? 4 : v >= 2 ? 2 : 1; }
+    // With the hidden layers in one dataflow launch (k_mlp_chain) a single slice is fastest: two chains
+    // cannot share an SM, and half-size batches fill it worse (7.6 ms in one slice, 8.9 ms in two at 8192
+    // queries).  With one launch per layer two slices overlap one slice's GEMMs with the other's k_rl_advance.
+    if (tc && crlk_tc_chain_rows(Q)) return 1;
     return Q >= 2048 ? 2 : 1;
 }
 
@@ -712,6 +716,25 @@ extern "C" int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q
         if (v > best) best = v;
     }
     return best;
+}
+
+// Kernels one crlk_extend_rl call launches: per slice k_rl_init + the first observation, then per policy
+// step and slice the hidden layers (one dataflow launch, or one per layer) + k_rl_advance.
+extern "C" int32_t crlk_extend_rl_launches(const CrlkPolicy *p, const CrlkExtendParams *ext, int32_t Q,
+                                           int32_t with_noise_cursor)
+{
+    if (!p || !ext || Q <= 0) return 0;
+    const bool tc = policy_uses_tc(p);
+    const int ns = rl_splits(Q, tc);
+    int slices = 0, per_step = 0;
+    for (int i = 0; i < ns; i++) {
+        int q0, n;
+        rl_slice(Q, ns, i, &q0, &n);
+        if (n <= 0) continue;
+        slices++;
+        per_step += ((tc && crlk_tc_chain_rows(n)) ? 1 : p->n_layers - 1) + 1;
+    }
+    return 2 * slices + ext->n_max_extend * per_step + (with_noise_cursor ? 1 : 0);
 }
 
 // count[] is zeroed before this launch; the active queries become step 1's row list.
@@ -800,7 +823,7 @@ extern "C" int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const Crl
     // step by step: while one half's GEMMs hold the tensor pipe, the other half's observation /
     // motion / collision kernels use the rest of the SM.  Queries are independent, so the split
     // changes no result.
-    const int ns = rl_splits(Q);
+    const int ns = rl_splits(Q, policy_uses_tc(p));
     RlSide *side = nullptr;
     std::unique_lock<std::mutex> guard;
     if (ns > 1) {

@@ -92,9 +92,17 @@ class BatchedExtender:
                            nearest_idx=torch.empty(Q, dtype=torch.int32).pin_memory(),
                            flags=torch.empty(Q, dtype=torch.uint8).pin_memory())
         self.extend_targets = None    # extend toward these instead of the samples (cfg5)
-        chunks = (Q + rl_chunk - 1) // rl_chunk
-        self.launches_per_step = 4 if policy is None else \
-            2 + chunks * (2 + self.xp.n_max_extend * (2 + len(policy.actor.weights)) * (2 if min(Q, rl_chunk) >= 2048 else 1))
+        # kernels per step(): nearest (+ its merge pass for split trees) + gather + the extension
+        # (DWA: order + extend; policy steering: what the library says each crlk_extend_rl pass launches)
+        if policy is None:
+            self.launches_per_step = 4
+        else:
+            import ctypes as C
+            from .._lib import lib
+            n = 2
+            for q0 in range(0, Q, rl_chunk):
+                n += int(lib().crlk_extend_rl_launches(policy.actor.handle.h, C.byref(self.xp), min(Q, q0 + rl_chunk) - q0, 0))
+            self.launches_per_step = n
 
     def step(self, samples, events=None):
         """samples: float64 CUDA [Q, 5].  Returns the extension outputs (CUDA tensors)."""

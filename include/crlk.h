@@ -217,8 +217,10 @@ int crlk_policy_destroy(CrlkPolicy *p);
  * noise); act dev f32[B x 2] = clamp(tanh(mlp) + noise*eps) * scale + bias).
  * workspace dev bytes from crlk_policy_workspace_bytes(p, B).
  * Hidden layers whose widths are multiples of 128 run on the tensor cores (tcgen05, float32 operands as
- * three bf16 planes, float32 accumulation: float32-level accuracy); B >= 24,576 uses the CTA-pair
- * kernel (cta_group::2).  Other widths use a float32 SIMT GEMM. */
+ * bf16 planes, float32 accumulation: float32-level accuracy): below 24,576 rows ALL hidden layers run in one
+ * dataflow launch (k_mlp_chain: tiles of all layers pulled from one list, row-tile completion flags
+ * between layers), from 24,576 rows one launch per layer of the CTA-pair kernel (cta_group::2).  Other
+ * widths use a float32 SIMT GEMM. */
 int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_t ld_obs, const float *noise,
                         float eps, int32_t B, float *act, void *workspace, void *stream);
 int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
@@ -232,16 +234,19 @@ int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
  * row k-1 is used at step k (noise_rows >= n_max_extend).
  * workspace: crlk_extend_rl_workspace_bytes, 256-byte aligned.
  * Every policy step runs on the compacted batch of queries that are still extending (row lists and
- * counts live on the device, no host synchronisation); batches of 2048 queries or more advance as two
- * halves on `stream` and an internal second stream (joined before the call's last kernel), so the
- * GEMMs of one half overlap the observation / motion / collision kernels of the other.  Results do
- * not depend on either.  The call is not re-entrant per device (serialised internally). */
+ * counts live on the device, no host synchronisation): one launch for the actor's hidden layers and one
+ * for head + motion + validity + bookkeeping + next observation.  Batches of 24,576 queries or more (one
+ * GEMM launch per layer) advance as two halves on `stream` and an internal second stream (joined before
+ * the call's last kernel), so the GEMMs of one half overlap the other half's step kernel.  Results do
+ * not depend on either.  The call is not re-entrant per device (serialised internally).
+ * crlk_extend_rl_launches: kernels one call launches (for launch accounting; memsets not counted). */
 int crlk_extend_rl(const CrlkEnv *env, const CrlkPolicy *p, const CrlkExtendParams *ext,
                    const double *from_states, const double *targets, int32_t Q, const float *noise,
                    int32_t noise_rows, int32_t *noise_cursor, float eps, double *path, int32_t *n_steps,
                    int32_t *status, int32_t *node_step, int32_t *n_nodes, float *actions, uint8_t *flags,
                    const uint8_t *active, void *workspace, void *stream);
 int64_t crlk_extend_rl_workspace_bytes(const CrlkPolicy *p, int32_t Q);
+int32_t crlk_extend_rl_launches(const CrlkPolicy *p, const CrlkExtendParams *ext, int32_t Q, int32_t with_noise_cursor);
 
 /* ---- learned parent selection (estimator/network.py, rrt_rl_estimator.py:57-74) ---- */
 

@@ -11,6 +11,6 @@ timeout 400 ncu --set full --clock-control none --import-source on --profile-fro
 timeout 200 python tools/bench_nearest.py > gpurun_out/${tag}_plain_c.log 2>&1 &&
 timeout 400 ncu --set full --clock-control none -k regex:k_nearest -s 4 -c 1 -o gpurun_out/${tag}_nearest -f python tools/bench_nearest.py > gpurun_out/${tag}_ncu_c.log 2>&1
 timeout 200 python tools/prof_rl.py 8192 > gpurun_out/${tag}_plain_d.log 2>&1 &&
-timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"k_gemm|k_rl_advance" -s 20 -c 10 -o gpurun_out/${tag}_rl -f python tools/prof_rl.py 8192 > gpurun_out/${tag}_ncu_d.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"k_mlp_chain|k_rl_advance" -s 20 -c 10 -o gpurun_out/${tag}_rl -f python tools/prof_rl.py 8192 > gpurun_out/${tag}_ncu_d.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${tag}_rl_launches.csv python tools/prof_rl.py 8192 > gpurun_out/${tag}_ncu_e.log 2>&1
 ls -la gpurun_out/${tag}*
