@@ -95,11 +95,12 @@ class BatchedExtender:
         # kernels per step(): nearest (+ its merge pass for split trees) + gather + the extension
         # (DWA: order + extend; policy steering: what the library says each crlk_extend_rl pass launches)
         if policy is None:
-            self.launches_per_step = 4
+            # k_nearest, k_nearest_final, k_gather_rows, k_lpt_order (batches larger than the persistent grid), k_extend_dwa
+            self.launches_per_step = 5 if Q > 296 else 4
         else:
             import ctypes as C
             from .._lib import lib
-            n = 2
+            n = 3                                                  # k_nearest, k_nearest_final, k_gather_rows
             for q0 in range(0, Q, rl_chunk):
                 n += int(lib().crlk_extend_rl_launches(policy.actor.handle.h, C.byref(self.xp), min(Q, q0 + rl_chunk) - q0, 0))
             self.launches_per_step = n
