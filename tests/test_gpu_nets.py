@@ -217,3 +217,40 @@ def test_policy_forward_large_batch_pair_kernel():
         assert np.array_equal(big[lo:lo + 1024], part)
     ref = orc.actor_forward(pol.actor.weights, pol.actor.biases, obs[:256], np_(noise)[:256], 0.05)
     np.testing.assert_allclose(big[:256], ref, rtol=1e-4, atol=1e-5)
+
+
+_CHAIN_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from crl_kino_b200 import ops
+from crl_kino_b200.env import DifferentialDriveGym
+from crl_kino_b200.policy.rl_policy import load_policy
+pol = load_policy(DifferentialDriveGym(), [1024, 512, 512, 512], None, seed=5)
+rng = np.random.default_rng(9)
+B = 5000
+obs = np.concatenate([rng.normal(0, 4, (B, 4)), (rng.uniform(0, 1, (B, 729)) > 0.4).astype(np.float64)], 1)
+act = ops.policy_forward(pol.actor.handle, ops.pad_obs(obs)).cpu().numpy()
+np.save(sys.argv[2], act)
+"""
+
+
+def test_mlp_chain_equals_one_launch_per_layer(tmp_path):
+    """All hidden layers in one dataflow launch (k_mlp_chain: tiles of all layers pulled from one list,
+    row-tile completion flags between layers) against one launch per layer (CRLK_MLP_CHAIN=0) and
+    against the chain with 256-column tiles (CRLK_MLP_BN=256): the same products accumulated in the
+    same k order, so the actions must agree bit for bit -- a missed dependency or a stale read between
+    layers would not.  The switches are read once per process, hence the child processes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("chain", {}), ("per_layer", {"CRLK_MLP_CHAIN": "0"}), ("chain_bn256", {"CRLK_MLP_BN": "256"})):
+        f = str(tmp_path / (name + ".npy"))
+        r = subprocess.run([sys.executable, "-c", _CHAIN_CHILD, root, f], env=dict(os.environ, **env),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = np.load(f)
+    assert np.isfinite(outs["chain"]).all() and np.ptp(outs["chain"][:, 0]) > 0
+    assert np.array_equal(outs["chain"], outs["per_layer"])
+    assert np.array_equal(outs["chain"], outs["chain_bn256"])
