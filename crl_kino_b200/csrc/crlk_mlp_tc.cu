@@ -563,6 +563,9 @@ k_gemm_bf16x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // l + 1's output may overwrite row tile m of layer l's input: every reader of those rows (the tiles
 // (l, m, *)) has completed by then.  The first layer's input planes are a third buffer.
 #define TCC_MAX_LAYERS 4
+// From this many rows on, one launch per layer of the CTA-pair kernel beats the chain (measured: 0.799 vs 0.815 ms
+// at 65,536 rows; at 24,576 rows the chain wins, 0.312 vs 0.359 ms)
+#define TC_PAIR_MIN_ROWS 49152
 #define TCC_RING 8
 struct ChainP {
     CUtensorMap tmA[TCC_MAX_LAYERS];
@@ -1144,7 +1147,7 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
     static const int chain_env = getenv("CRLK_MLP_CHAIN") ? atoi(getenv("CRLK_MLP_CHAIN")) : 1;
     static const int pair_forced = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
     if (chain_env && !unfused && persist && t->n_hidden <= TCC_MAX_LAYERS && pair_forced <= 0 &&
-        (B < 24576 || pair_forced == 0)) {
+        (B < TC_PAIR_MIN_ROWS || pair_forced == 0)) {
         float *lastbuf = last;
         const size_t last_bytes = ((size_t)Mpad * t->layer[t->n_hidden - 1].N * sizeof(float) + 255) & ~(size_t)255;
         __nv_bfloat16 *X = pl[1], *Y = (__nv_bfloat16 *)((uint8_t *)last + last_bytes);
@@ -1195,7 +1198,7 @@ int crlk_tc_layers_forward(const CrlkPolicyTc *t, int B, void *workspace, const 
         // every pair has several tiles to work through (measured: 203 vs 177 algorithmic TFLOP/s at 65,536
         // rows), slower below that (fewer, larger tiles per wave).  CRLK_MLP_PAIR=0 / 128 / 256 forces.
         static const int pair_env = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
-        const int pair = pair_env >= 0 ? pair_env : (B >= 24576 ? 256 : 0);
+        const int pair = pair_env >= 0 ? pair_env : (B >= TC_PAIR_MIN_ROWS ? 256 : 0);
         if (pair == 256 && Mpad % (2 * TC_BM) == 0 && L.N % 256 == 0) {
             int tiles = (L.N / 256) * (Mpad / (2 * TC_BM));
             int pairs = tiles < n_sms / 2 ? tiles : n_sms / 2;
@@ -1237,7 +1240,7 @@ int crlk_tc_chain_rows(int B)
 {
     static const int chain_env = getenv("CRLK_MLP_CHAIN") ? atoi(getenv("CRLK_MLP_CHAIN")) : 1;
     static const int pair_forced = getenv("CRLK_MLP_PAIR") ? atoi(getenv("CRLK_MLP_PAIR")) : -1;
-    return chain_env && pair_forced <= 0 && (B < 24576 || pair_forced == 0);
+    return chain_env && pair_forced <= 0 && (B < TC_PAIR_MIN_ROWS || pair_forced == 0);
 }
 
 // Hidden layers: obs (float32) -> float32 activations of the last hidden layer.

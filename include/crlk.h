@@ -217,9 +217,9 @@ int crlk_policy_destroy(CrlkPolicy *p);
  * noise); act dev f32[B x 2] = clamp(tanh(mlp) + noise*eps) * scale + bias).
  * workspace dev bytes from crlk_policy_workspace_bytes(p, B).
  * Hidden layers whose widths are multiples of 128 run on the tensor cores (tcgen05, float32 operands as
- * bf16 planes, float32 accumulation: float32-level accuracy): below 24,576 rows ALL hidden layers run in one
+ * bf16 planes, float32 accumulation: float32-level accuracy): below 49,152 rows ALL hidden layers run in one
  * dataflow launch (k_mlp_chain: tiles of all layers pulled from one list, row-tile completion flags
- * between layers), from 24,576 rows one launch per layer of the CTA-pair kernel (cta_group::2).  Other
+ * between layers), from 49,152 rows one launch per layer of the CTA-pair kernel (cta_group::2).  Other
  * widths use a float32 SIMT GEMM. */
 int crlk_policy_forward(const CrlkPolicy *p, const float *obs, int32_t ld_obs, const float *noise,
                         float eps, int32_t B, float *act, void *workspace, void *stream);
@@ -235,7 +235,7 @@ int64_t crlk_policy_workspace_bytes(const CrlkPolicy *p, int32_t B);
  * workspace: crlk_extend_rl_workspace_bytes, 256-byte aligned.
  * Every policy step runs on the compacted batch of queries that are still extending (row lists and
  * counts live on the device, no host synchronisation): one launch for the actor's hidden layers and one
- * for head + motion + validity + bookkeeping + next observation.  Batches of 24,576 queries or more (one
+ * for head + motion + validity + bookkeeping + next observation.  Batches of 49,152 queries or more (one
  * GEMM launch per layer) advance as two halves on `stream` and an internal second stream (joined before
  * the call's last kernel), so the GEMMs of one half overlap the other half's step kernel.  Results do
  * not depend on either.  The call is not re-entrant per device (serialised internally).

@@ -199,15 +199,15 @@ def test_extend_rl_large_batch_split_is_invisible():
 
 
 def test_policy_forward_large_batch_pair_kernel():
-    """Batches >= 24,576 rows run the hidden layers on the CTA-pair GEMM (tcgen05.mma.cta_group::2,
-    256 x 256 tiles, W halves shared between two SMs); smaller ones on the single-CTA kernel.  Both
+    """Batches >= 49,152 rows run the hidden layers on the CTA-pair GEMM (tcgen05.mma.cta_group::2,
+    256 x 256 tiles, W halves shared between two SMs); smaller ones in the one-launch chain.  Both
     accumulate every output in the same order, so a large batch must equal, bit for bit, the same rows
     evaluated in small chunks -- and agree with the oracle's float64-checked forward pass."""
     import torch
     from crl_kino_b200 import ops
     pol = _policy(5)
     rng = np.random.default_rng(6)
-    B = 24576 + 256
+    B = 49152 + 256
     obs = np.concatenate([rng.normal(0, 4, (B, 4)), (rng.uniform(0, 1, (B, 729)) > 0.4).astype(np.float64)], 1)
     o32 = ops.pad_obs(obs)
     noise = torch.as_tensor(rng.standard_normal((B, 2)).astype(np.float32)).cuda()
