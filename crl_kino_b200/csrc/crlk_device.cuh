@@ -671,6 +671,17 @@ __device__ __forceinline__ unsigned local_map_raster(const ObsSet &os, double px
     return 2u;
 }
 
+// The same screen for a point evaluated in float32: the raster's margin (>= 1e-4 m, build_grid) is an order
+// of magnitude above the error of a float32 evaluation of body_to_world (< 2e-5 m for coordinates
+// below 100 m), so a 0 / 1 answer for the float32 point holds for the exact float64 point as well.
+__device__ __forceinline__ unsigned local_map_raster_f(const ObsSet &os, float pxf, float pyf)
+{
+    const float rx = (pxf - os.gx0) * os.rinv, ry = (pyf - os.gy0) * os.rinv;
+    if (rx >= 0.f && ry >= 0.f && rx < (float)os.rnx && ry < (float)os.rny)
+        return __ldg(&os.raster[(int)ry * os.rnx + (int)rx]);
+    return 2u;
+}
+
 template <bool WANT_NEAR = true>
 __device__ __forceinline__ bool local_map_occupied(const ObsSet &os, double px, double py, bool &near)
 {

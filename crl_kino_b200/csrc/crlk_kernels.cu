@@ -2056,7 +2056,6 @@ k_rl_advance(EnvP e, ExtP x, ObsSet os, ObsGrid og, RlAdvP a)
     {
         const bool on = lane < OBS_SIDE;
         const double by = arange_at(og.lr0, og.lr1, og.lrd, on ? lane : 0);
-        const double nsby = __dmul_rn(-ssn, by), csby = __dmul_rn(ccs, by);
         int *mq = s_queue[warp];                     // the collision queue is idle by now
         int nq = 0;
         auto point = [&](int ib, double byv_ns, double byv_cs, double &px, double &py) {
@@ -2078,15 +2077,20 @@ k_rl_advance(EnvP e, ExtP x, ObsSet os, ObsGrid og, RlAdvP a)
             __syncwarp();
         };
         static_assert(OBS_SIDE % 3 == 0, "three grid rows per iteration");
+        // The raster screen runs on a float32 evaluation of body_to_world (its margin covers the float32
+        // error, crlk_device.cuh); only the queued points are evaluated exactly, in float64, by drain().
+        // Lane i keeps the longitudinal offset of grid row i; a row's value comes by shuffle.
+        const float ccs_f = (float)ccs, ssn_f = (float)ssn, by_f = (float)by;
+        const float ox_f = fmaf(-ssn_f, by_f, (float)px0), oy_f = fmaf(ccs_f, by_f, (float)py0);
+        const float my_bx_f = (float)arange_at(og.ba0, og.ba1, og.bad, on ? lane : 0);
         for (int ib = 0; ib < OBS_SIDE; ib += 3) {
             // three independent raster loads in flight before the first vote (a vote is a
             // convergence point: the compiler does not move loads across it)
             unsigned cls[3];
 #pragma unroll
             for (int u = 0; u < 3; u++) {
-                double px, py;
-                point(ib + u, nsby, csby, px, py);
-                cls[u] = on ? local_map_raster(os, px, py) : 0u;
+                const float bx_f = __shfl_sync(0xffffffffu, my_bx_f, ib + u);
+                cls[u] = on ? local_map_raster_f(os, fmaf(ccs_f, bx_f, ox_f), fmaf(ssn_f, bx_f, oy_f)) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < 3; u++) {
