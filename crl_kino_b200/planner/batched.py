@@ -201,6 +201,33 @@ class BatchedExtender:
         s["busy"] = True
         return i
 
+    def submit(self, samples_dev, flush=None):
+        """Device-resident form of submit_host: the step runs on the slot's stream (pipe_depth steps in
+        flight), inputs and results stay in HBM; wait() returns the slot's output tensors.  `flush`
+        (a CUDA tensor, optional) is overwritten on the slot's stream before the step (bench.py's L2 flush)."""
+        if not hasattr(self, "_pipe"):
+            self._pipe_init()
+        i = self._slot
+        self._slot = (self._slot + 1) % self.pipe_depth
+        s = self._pipe[i]
+        cur = torch.cuda.current_stream()
+        s["stream"].wait_stream(cur)
+        with torch.cuda.stream(s["stream"]):
+            if flush is not None:
+                flush.fill_(i)
+            keep_out, keep_from = self.out, self.from_states
+            self.out, self.from_states = s["out"], s["from_states"]
+            s["out"] = self.step(samples_dev)
+            self.out, self.from_states = keep_out, keep_from
+            s["done"].record()
+        return i
+
+    def wait(self, ticket):
+        """Makes the current stream wait for a submit() step and returns its output tensors."""
+        s = self._pipe[ticket]
+        torch.cuda.current_stream().wait_event(s["done"])
+        return s["out"]
+
     def collect(self, ticket):
         """Results of a submit_host() call as numpy views of pinned memory (valid until the slot is reused
         pipe_depth submissions later)."""

@@ -179,6 +179,15 @@ def test_pipelined_host_api_equals_synchronous():
             assert np.array_equal(a[k], b[k]), k
         for q in range(Q):
             assert np.array_equal(a["path"][q, :ns[q]], b["path"][q, :ns[q]])
+    # the device-resident form (submit / wait: inputs and results stay in HBM, pipe_depth steps in flight)
+    tickets = [ext.submit(ops.as_dev(b)) for b in batches[:ext.pipe_depth]]
+    for a, t in zip(sync, tickets):
+        out = ext.wait(t)
+        ns = a["n_steps"]
+        assert np.array_equal(a["n_steps"], np_(out["n_steps"])) and np.array_equal(a["status"], np_(out["status"]))
+        path = np_(out["path"])
+        for q in range(Q):
+            assert np.array_equal(a["path"][q, :ns[q]], path[q, :ns[q]])
 
 
 @pytest.mark.parametrize("seed", range(10))
