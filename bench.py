@@ -672,7 +672,7 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
     K, W = args.cfg5_steps, args.cfg5_warmup
     samples = [ops.as_dev(free_states(clearance, rng, Q, 0.0, batch=1 << 17)) for _ in range(K + W)]
     goals = ops.as_dev(free_states(clearance, rng, Q, 0.5, batch=1 << 17))
-    ext = BatchedExtender(env, forest, policy=pol, eps=0.0, rl_chunk=8192)
+    ext = BatchedExtender(env, forest, policy=pol, eps=0.0, rl_chunk=8192, pipe_depth=2)
     ext.extend_targets = goals
     sampler = ClockSampler(local_rank)
     sampler.wait_first()
@@ -718,13 +718,21 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
     # ---- end to end: samples from pinned host memory, results back to the host, every step
     hs = [s.cpu().numpy() for s in samples]
     t_load0 = time.perf_counter()
-    ext.step_host(hs[0])
+    ext.collect(ext.submit_host(hs[0]))
+    ext.collect(ext.submit_host(hs[1 % len(hs)]))
     barrier()
     t0 = time.perf_counter()
-    for k in range(K):
-        ext.step_host(hs[W + k])
+    pending = None
+    n_back = 0
+    for k in range(K):                                   # two steps in flight: a step's D2H under the next step's kernels
+        t = ext.submit_host(hs[W + k])
+        if pending is not None:
+            n_back += int(ext.collect(pending)["n_steps"].shape[0])
+        pending = t
+    n_back += int(ext.collect(pending)["n_steps"].shape[0])
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    assert n_back == K * Q
     clock_windows.append((t_load0, time.perf_counter()))
     clocks = sampler.stop(clock_windows)
     clocks["window"] = "warm-up + timed steps and the end-to-end loop of this leg (same step, same load)"
@@ -766,7 +774,7 @@ def cfg5_leg(args, env, rank, local_rank, world, barrier):
                            "status_last_step_rank0": {"timeout": int((st == 0).sum()), "collision": int((st == 1).sum()),
                                                       "reached": int((st == 2).sum())}},
         "e2e": {"value": tot / t_e2e, "unit": "extensions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "BatchedExtender.step_host"},
+                "api": "BatchedExtender.submit_host / collect (two steps in flight: a step's D2H under the next step's kernels)"},
         "per_rank_ms": per_rank, "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
         "kernel_ms_per_step": {"nearest": t_near_m / K, "extend_rl": t_ext_m / K},
         "gather_ms": gather_ms, "gather": {"collective": "torch.distributed.gather over NCCL (sharding.gather_results)",

@@ -187,12 +187,18 @@ class BatchedExtender:
         s["stream"].wait_stream(cur)               # whatever the caller enqueued so far (forest updates) comes first
         with torch.cuda.stream(s["stream"]):
             s["d_in"].copy_(s["h_in"], non_blocking=True)
+            if self.policy is not None and getattr(self, "_last_done", None) is not None:
+                # policy steering: the kernels of a step fill the GPU (persistent GEMM grid), two steps side by
+                # side only slow each other down -- the next step's kernels wait for the previous step's kernels,
+                # not for its D2H, which is what the pipeline hides here
+                s["stream"].wait_event(self._last_done)
             keep_out, keep_from = self.out, self.from_states
             self.out, self.from_states = s["out"], s["from_states"]
             out = self.step(s["d_in"])
             s["out"] = out
             self.out, self.from_states = keep_out, keep_from
             s["done"].record()
+            self._last_done = s["done"]
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(s["done"])
             for k, h in s["h_out"].items():
