@@ -1007,7 +1007,11 @@ def cfg4_leg(args, env, rects, rank, local_rank, world, barrier):
                     "source": "counters maintained by k_extend_dwa (crlk_extend_dwa `stats`) x per-unit FP64 operation "
                               "counts (DESIGN.md section 4); frac_executed counts an FMA as 2 against the FMA peak, the "
                               "pipe's busy share is in roofline.ncu (fp64_pipe_pct_while_active)"}
-    ncu = load_ncu("r2_extend_ncu.json")
+    # the ncu summary belongs to the default kernel; the clearance variant (k_extend_dwa<.., true>) has its own
+    # file when one was captured, and its per-rollout clearance searches are not in the work counters
+    ncu = load_ncu("r2_extend_clr_ncu.json" if args.use_clearance else "r2_extend_ncu.json")
+    if args.use_clearance:
+        executed = None
     value = tot_ext / (t_total_max * 1e-3)
     line = {
         "metric": "rrt_extensions_per_sec", "value": value, "unit": "extensions/s",

@@ -32,8 +32,8 @@ FIELDS = {
 }
 STALLS = ["long_scoreboard", "wait", "short_scoreboard", "barrier", "math_pipe_throttle", "mio_throttle",
           "branch_resolving", "no_instruction", "lg_throttle", "not_selected", "dispatch_stall", "membar", "tex_throttle"]
-UNIT_SCALE = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6,
-              "Gbyte": 1e9}
+UNIT_SCALE = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+              "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def main():
