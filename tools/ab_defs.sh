@@ -1,6 +1,6 @@
 # A/B of a compile-time variant against the default build at equal bench settings, in ONE gpurun call
 # and without compiling on the GPU box.
-#   usage (here):   tools/ab_defs.sh CRLK_ROWMAJOR [bench flags...]
+#   usage (here):   tools/ab_defs.sh "DWA_THREADS=128 DWA_MIN_BLOCKS=4" [bench flags...]
 # builds crl_kino_b200/libcrlk_variant.so with -D<defs> next to the default libcrlk.so, then runs on the
 # box: oracle tests + bench with the default library, the same with the variant swapped in.
 set -e

@@ -1,17 +1,17 @@
-# Multi-GPU evidence on one 8-GPU box: cfg4 weak scaling at 8/4/2 ranks and cfg5 (65,536 queries) at 8 ranks.
-run() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n "$@"; }
-run 8 --steps 20 --warmup 3 --no-cpu > gpurun_out/r1j_cfg4_8gpu.json 2> gpurun_out/r1j_cfg4_8gpu.err
-run 4 --steps 20 --warmup 3 --no-cpu > gpurun_out/r1j_cfg4_4gpu.json 2> gpurun_out/r1j_cfg4_4gpu.err
-run 2 --steps 20 --warmup 3 --no-cpu > gpurun_out/r1j_cfg4_2gpu.json 2> gpurun_out/r1j_cfg4_2gpu.err
-python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r1j_cfg4_1gpu.json 2> gpurun_out/r1j_cfg4_1gpu.err
-run 8 --workload cfg5 --steps 4 --warmup 1 > gpurun_out/r1j_cfg5_8gpu.json 2> gpurun_out/r1j_cfg5_8gpu.err
-for f in gpurun_out/r1j_cfg4_?gpu.json gpurun_out/r1j_cfg5_8gpu.json; do python - "$f" <<'PY'
+# Multi-GPU evidence on one box with the driver's command: python -m torch.distributed.run ... bench.py --gpus N
+# (cfg4 weak-scaling line + the cfg5 object with the NCCL result gather), and the reference arm on the same box.
+#   gpurun --gpus 8 -- 'bash tools/scale_run.sh 8'      gpurun --gpus 2 -- 'bash tools/scale_run.sh 2'
+n=${1:-8}
+run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n "$@"; }
+timeout 800 run > gpurun_out/r2_bench_${n}gpu.json 2> gpurun_out/r2_bench_${n}gpu.err
+timeout 300 run --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_${n}gpu_reference.json 2> gpurun_out/r2_bench_${n}gpu_reference.err
+python - "gpurun_out/r2_bench_${n}gpu.json" <<'PY'
 import json, sys
 try:
-    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print(sys.argv[1], d["n_gpus"], round(d["value"]), round(d["e2e"]["value"]), d.get("planning", {}).get("queries_per_sec"))
+    d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][0])
+    c = d.get("cfg5") or {}
+    print(d["n_gpus"], "GPUs: cfg4", round(d["value"]), "e2e", round(d["e2e"]["value"]), "planning", (d.get("planning") or {}).get("queries_per_sec"),
+          "| cfg5", c.get("value"), "e2e", (c.get("e2e") or {}).get("value"), "gather ms", c.get("gather_ms"), "capped", (c.get("config") or {}).get("capped_by_memory"))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
-done
-tail -3 gpurun_out/r1j_cfg5_8gpu.err
