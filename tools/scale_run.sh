@@ -2,9 +2,9 @@
 # (cfg4 weak-scaling line + the cfg5 object with the NCCL result gather), and the reference arm on the same box.
 #   gpurun --gpus 8 -- 'bash tools/scale_run.sh 8'      gpurun --gpus 2 -- 'bash tools/scale_run.sh 2'
 n=${1:-8}
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n "$@"; }
-timeout 800 run > gpurun_out/r2_bench_${n}gpu.json 2> gpurun_out/r2_bench_${n}gpu.err
-timeout 300 run --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_${n}gpu_reference.json 2> gpurun_out/r2_bench_${n}gpu_reference.err
+run() { timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n "$@"; }
+run > gpurun_out/r2_bench_${n}gpu.json 2> gpurun_out/r2_bench_${n}gpu.err
+run --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_${n}gpu_reference.json 2> gpurun_out/r2_bench_${n}gpu_reference.err
 python - "gpurun_out/r2_bench_${n}gpu.json" <<'PY'
 import json, sys
 try:
