@@ -559,6 +559,113 @@ k_local_obs(ObsGrid og, ObsSet os, const double *__restrict__ states,
     if (threadIdx.x == 0 && near_boundary) near_boundary[b] = (uint8_t)s_near;
 }
 
+// The raster path with one WARP per observation (eight per CTA, no block barrier): lane = column of the
+// 27 x 27 sample grid, three grid rows per iteration, the raster screen on a float32 evaluation of the
+// sample points (its margin covers the float32 error, crlk_device.cuh), the few points in partly covered
+// raster cells queued and decided exactly in float64 with all lanes busy -- the observation of
+// k_rl_advance as a kernel of its own.  The serial, correctly rounded sincos of the heading (one lane)
+// is hidden by the other warps of the SM; with one CTA per observation it was a barrier-separated
+// prologue of every CTA.  Same outputs, bit for bit, as k_local_obs<false>.
+#define LOW_QUEUE 64
+__global__ void __launch_bounds__(256)
+k_local_obs_w(ObsGrid og, ObsSet os, const double *__restrict__ states, const double *__restrict__ goals,
+              int goal_stride, int B, double *obs64, float *obs32, int ld32, const int *__restrict__ list,
+              const int *__restrict__ count, __nv_bfloat16 *planes, int Mpad, int Kp)
+{
+    __shared__ int s_queue[8][LOW_QUEUE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    if (count && b >= *count) return;
+    const int q = list ? list[b] : b;
+    const double *st = states + 5 * (size_t)q;
+    double sn = 0.0, cs = 0.0;
+    if (lane == 0) crlk_sincos(st[2], &sn, &cs);
+    const double px0 = st[0], py0 = st[1];
+    const double ccs = __shfl_sync(0xffffffffu, cs, 0), ssn = __shfl_sync(0xffffffffu, sn, 0);
+    __nv_bfloat16 *p0 = planes ? planes + (size_t)b * Kp : nullptr;
+    auto put = [&](int p, bool occ) {
+        const double v = occ ? 0.0 : 1.0;
+        if (obs64) obs64[(size_t)b * (4 + OBS_NPTS) + 4 + p] = v;
+        if (obs32) obs32[(size_t)b * ld32 + 4 + p] = (float)v;
+        if (p0) p0[4 + p] = __float2bfloat16_rn((float)v);
+    };
+    const bool on = lane < OBS_SIDE;
+    const double by = arange_at(og.lr0, og.lr1, og.lrd, on ? lane : 0);
+    int *mq = s_queue[warp];
+    int nq = 0;
+    auto drain = [&]() {
+        __syncwarp();
+        for (int i = lane; i < nq; i += 32) {
+            const int p = mq[i], ib = p / OBS_SIDE, il = p - ib * OBS_SIDE;
+            double px, py;
+            body_to_world(ccs, ssn, px0, py0, arange_at(og.ba0, og.ba1, og.bad, ib), arange_at(og.lr0, og.lr1, og.lrd, il),
+                          px, py);                                    // differential_gym.py:83, exact
+            bool nearp = false;
+            put(p, local_map_occupied<true>(os, px, py, nearp));
+        }
+        nq = 0;
+        __syncwarp();
+    };
+    const float ccs_f = (float)ccs, ssn_f = (float)ssn, by_f = (float)by;
+    const float ox_f = fmaf(-ssn_f, by_f, (float)px0), oy_f = fmaf(ccs_f, by_f, (float)py0);
+    const float my_bx_f = (float)arange_at(og.ba0, og.ba1, og.bad, on ? lane : 0);
+    static_assert(OBS_SIDE % 3 == 0, "three grid rows per iteration");
+    for (int ib = 0; ib < OBS_SIDE; ib += 3) {
+        unsigned cls[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const float bx_f = __shfl_sync(0xffffffffu, my_bx_f, ib + u);
+            cls[u] = on ? local_map_raster_f(os, fmaf(ccs_f, bx_f, ox_f), fmaf(ssn_f, bx_f, oy_f)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int p = (ib + u) * OBS_SIDE + lane;
+            if (on && cls[u] < 2u) put(p, cls[u] != 0u);
+            const bool mixed = on && cls[u] >= 2u;
+            const unsigned mask = __ballot_sync(0xffffffffu, mixed);
+            if (mask) {
+                if (mixed) mq[nq + __popc(mask & ((1u << lane) - 1u))] = p;
+                nq += __popc(mask);
+                if (nq > LOW_QUEUE - 32) drain();
+            }
+        }
+    }
+    drain();
+    if (planes) {
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+        for (int c = 4 + OBS_NPTS + lane; c < Kp; c += 32) p0[c] = z;
+        for (int c = 4 + lane; c < 64; c += 32) {
+            planes[((size_t)Mpad + b) * Kp + c] = z;
+            planes[((size_t)2 * Mpad + b) * Kp + c] = z;
+        }
+    }
+    if (lane == 0) {
+        const double *g = goals + (size_t)goal_stride * q;
+        const double qx = g[0] - px0, qy = g[1] - py0;          // differential_gym.py:186-187 as R^T (g - t)
+        const double gbx = cs * qx + sn * qy, gby = (-sn) * qx + cs * qy;
+        if (obs64) {
+            double *o = obs64 + (size_t)b * (4 + OBS_NPTS);
+            o[0] = gbx; o[1] = gby; o[2] = st[3]; o[3] = st[4];
+        }
+        if (obs32) {
+            float *o = obs32 + (size_t)b * ld32;
+            o[0] = (float)gbx; o[1] = (float)gby; o[2] = (float)st[3]; o[3] = (float)st[4];
+            for (int k = 4 + OBS_NPTS; k < ld32; k++) o[k] = 0.f;
+        }
+        if (planes) {
+            const float h[4] = {(float)gbx, (float)gby, (float)st[3], (float)st[4]};
+            for (int k = 0; k < 4; k++) {
+                __nv_bfloat16 a0, a1, a2;
+                crlk_split3(h[k], a0, a1, a2);
+                p0[k] = a0;
+                planes[((size_t)Mpad + b) * Kp + k] = a1;
+                planes[((size_t)2 * Mpad + b) * Kp + k] = a2;
+            }
+        }
+    }
+}
+
 extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const double *goals,
                               int32_t goal_stride, int32_t B, double *obs64, float *obs32,
                               int32_t ld32, uint8_t *near_boundary, void *stream)
@@ -573,9 +680,9 @@ extern "C" int crlk_local_obs(const CrlkEnv *env, const double *states, const do
                                                               goal_stride, B, obs64, obs32, ld32,
                                                               near_boundary, nullptr, nullptr, nullptr, 0, 0);
     else
-        k_local_obs<false><<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
-                                                               goal_stride, B, obs64, obs32, ld32, nullptr,
-                                                               nullptr, nullptr, nullptr, 0, 0);
+        k_local_obs_w<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                                    goal_stride, B, obs64, obs32, ld32, nullptr,
+                                                                    nullptr, nullptr, 0, 0);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -587,9 +694,9 @@ int crlk_local_obs_compact(const CrlkEnv *env, const double *states, const doubl
                            float *obs32, int32_t ld32, void *planes, int32_t Mpad, int32_t Kp, void *stream)
 {
     if (Bmax == 0) return CRLK_OK;
-    k_local_obs<false><<<Bmax, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
-                                                              goal_stride, Bmax, nullptr, obs32, ld32, nullptr,
-                                                              list, count, (__nv_bfloat16 *)planes, Mpad, Kp);
+    k_local_obs_w<<<(Bmax + 7) / 8, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                                   goal_stride, Bmax, nullptr, obs32, ld32,
+                                                                   list, count, (__nv_bfloat16 *)planes, Mpad, Kp);
     CRLK_LAUNCH_CHECK();
     return CRLK_OK;
 }
@@ -661,9 +768,9 @@ extern "C" int crlk_gym_step(const CrlkEnv *env, double *states, const double *g
                                                                  actions, n_sub, B, info, reward, near_boundary);
     CRLK_LAUNCH_CHECK();
     if (obs64 || obs32) {
-        k_local_obs<false><<<B, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals, goal_stride,
-                                                               B, obs64, obs32, ld32, nullptr, nullptr, nullptr,
-                                                               nullptr, 0, 0);
+        k_local_obs_w<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(make_obs_grid(), env->os, states, goals,
+                                                                    goal_stride, B, obs64, obs32, ld32, nullptr,
+                                                                    nullptr, nullptr, 0, 0);
         CRLK_LAUNCH_CHECK();
     }
     return CRLK_OK;
